@@ -1,0 +1,246 @@
+"""ctypes binding of libffvd_b200.so (C ABI in include/ffvd_b200.h).
+
+Tensors cross the boundary as DLPack capsules: anything with ``__dlpack__`` (torch CPU/CUDA
+tensors, NumPy arrays, TF tensors via ``tf.experimental.dlpack``) is accepted.  The capsule is
+kept alive for the duration of the call and released afterwards (the library only borrows).
+There is no CPU fallback: if the shared library is missing or no B200 is visible, calls fail.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Any, Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffvd_b200.so")
+
+KERNEL_SE = 0
+KERNEL_LINEAR = 1
+FLAG_PRIOR_Z_NORMAL = 1
+FLAG_PRIOR_ONCE = 2
+FLAG_NO_GRADS = 4
+FLAG_ASYNC = 8
+
+_PROBLEM_FIELDS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR", "Y", "ctrl")
+_OUTPUT_FIELDS = ("nll", "terms", "g_X", "g_Z", "g_U", "g_logv", "g_logl", "g_logQ", "g_C", "g_d", "g_logR")
+
+
+class FFVDError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("libffvd_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+class NotPositiveDefinite(FloatingPointError):
+    """Raised when a Cholesky factorisation fails (the reference raises InvalidArgumentError)."""
+
+    def __init__(self, pivot: int, message: str):
+        super().__init__(message)
+        self.pivot = pivot
+
+
+class _Problem(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in _PROBLEM_FIELDS]
+
+
+class _Outputs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in _OUTPUT_FIELDS]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libffvd_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd, cll = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64
+    lib.ffvd_version.restype = ci
+    lib.ffvd_status_string.restype = ctypes.c_char_p
+    lib.ffvd_status_string.argtypes = [ci]
+    lib.ffvd_last_error.restype = ctypes.c_char_p
+    lib.ffvd_ctx_create.argtypes = [ci, vp, ctypes.POINTER(vp)]
+    lib.ffvd_ctx_destroy.argtypes = [vp]
+    lib.ffvd_ctx_synchronize.argtypes = [vp]
+    lib.ffvd_ctx_launch_count.argtypes = [vp]
+    lib.ffvd_ctx_launch_count.restype = cll
+    lib.ffvd_kernel_K.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    lib.ffvd_kernel_Kdiag.argtypes = [vp, ci, vp, vp, vp, vp]
+    lib.ffvd_kernel_pre_cal.argtypes = [vp, ci, vp, vp, vp, cd, vp]
+    lib.ffvd_conditional.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, vp, vp]
+    lib.ffvd_logdensity_norm_diag.argtypes = [vp, vp, vp, vp, ci, vp]
+    lib.ffvd_nll_grads_uncollapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
+    lib.ffvd_nll_grads_collapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
+    lib.ffvd_nll_grads_batched.argtypes = [vp, ci, ci, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
+    lib.ffvd_sghmc_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, cd, cd, cd, ci]
+    lib.ffvd_adam_update.argtypes = [vp, vp, vp, vp, vp, cd, cd, cd, cd, cll]
+    for name in ("ffvd_ctx_create", "ffvd_ctx_destroy", "ffvd_ctx_synchronize", "ffvd_kernel_K", "ffvd_kernel_Kdiag",
+                 "ffvd_kernel_pre_cal", "ffvd_conditional", "ffvd_logdensity_norm_diag", "ffvd_nll_grads_uncollapsed",
+                 "ffvd_nll_grads_collapsed", "ffvd_nll_grads_batched", "ffvd_sghmc_update", "ffvd_adam_update"):
+        getattr(lib, name).restype = ci
+    _lib = lib
+    return lib
+
+
+# ---- DLPack capsule plumbing ---------------------------------------------------------------
+_PyCapsule_GetPointer = ctypes.pythonapi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = ctypes.c_void_p
+_PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+
+class _Borrow:
+    """Holds DLPack capsules alive while the C call runs."""
+
+    def __init__(self):
+        self.capsules = []
+
+    def ptr(self, obj: Any) -> Optional[int]:
+        if obj is None:
+            return None
+        if not hasattr(obj, "__dlpack__"):
+            raise TypeError("expected an object with __dlpack__ (torch tensor, numpy array, ...), got %r" % type(obj))
+        cap = obj.__dlpack__()
+        self.capsules.append((cap, obj))
+        return _PyCapsule_GetPointer(cap, b"dltensor")
+
+    def release(self):
+        # un-consumed capsules run the producer's deleter when they are garbage collected
+        self.capsules.clear()
+
+
+def _check(status: int):
+    if status == 0:
+        return
+    lib = load_library()
+    msg = lib.ffvd_last_error().decode() or lib.ffvd_status_string(status).decode()
+    if status > 0:
+        raise NotPositiveDefinite(status, msg)
+    if status in (-1, -2, -3, -4):
+        raise ValueError("libffvd_b200 status %d: %s" % (status, msg))
+    raise FFVDError(status, msg)
+
+
+class Context:
+    """One context per device; work is enqueued on ``stream`` (a raw cudaStream_t handle,
+    e.g. ``torch.cuda.current_stream().cuda_stream``) or on a context-owned stream."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        _check(self._lib.ffvd_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ffvd_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self._lib.ffvd_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ffvd_ctx_launch_count(self._h))
+
+    # ---- operators
+    def kernel_K(self, kind, X, X2, logv, logl, out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_kernel_K(self._h, kind, b.ptr(X), b.ptr(X2), b.ptr(logv), b.ptr(logl), b.ptr(out)))
+        finally:
+            b.release()
+        return out
+
+    def kernel_Kdiag(self, kind, X, logv, logl, out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_kernel_Kdiag(self._h, kind, b.ptr(X), b.ptr(logv), b.ptr(logl), b.ptr(out)))
+        finally:
+            b.release()
+        return out
+
+    def kernel_pre_cal(self, kind, Z, logv, logl, jitter, out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_kernel_pre_cal(self._h, kind, b.ptr(Z), b.ptr(logv), b.ptr(logl), float(jitter), b.ptr(out)))
+        finally:
+            b.release()
+        return out
+
+    def conditional(self, kind, shared_kernel, Xnew, Z, logv, logl, f, q_sqrt, white, full_cov, jitter, mean_out, var_out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_conditional(self._h, kind, int(bool(shared_kernel)), b.ptr(Xnew), b.ptr(Z), b.ptr(logv),
+                                              b.ptr(logl), b.ptr(f), b.ptr(q_sqrt), int(bool(white)), int(bool(full_cov)),
+                                              float(jitter), b.ptr(mean_out), b.ptr(var_out)))
+        finally:
+            b.release()
+        return mean_out, var_out
+
+    def logdensity_norm_diag(self, y, ymean, Rchols, vec, out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_logdensity_norm_diag(self._h, b.ptr(y), b.ptr(ymean), b.ptr(Rchols), int(bool(vec)), b.ptr(out)))
+        finally:
+            b.release()
+        return out
+
+    def _fill(self, b: _Borrow, struct, fields, d: dict):
+        for n in fields:
+            p = b.ptr(d.get(n))
+            setattr(struct, n, p)
+
+    def nll_grads(self, kind: int, collapsed: bool, problem: dict, outputs: dict, flags: int = FLAG_PRIOR_Z_NORMAL,
+                  jitter: float = 1e-5):
+        b = _Borrow()
+        try:
+            P, O = _Problem(), _Outputs()
+            self._fill(b, P, _PROBLEM_FIELDS, problem)
+            self._fill(b, O, _OUTPUT_FIELDS, outputs)
+            fn = self._lib.ffvd_nll_grads_collapsed if collapsed else self._lib.ffvd_nll_grads_uncollapsed
+            _check(fn(self._h, kind, ctypes.byref(P), int(flags), float(jitter), ctypes.byref(O)))
+        finally:
+            b.release()
+        return outputs
+
+    def nll_grads_batched(self, kind: int, collapsed: bool, problems: Sequence[dict], outputs: Sequence[dict],
+                          flags: int = FLAG_PRIOR_Z_NORMAL, jitter: float = 1e-5):
+        n = len(problems)
+        b = _Borrow()
+        try:
+            PA, OA = (_Problem * n)(), (_Outputs * n)()
+            for i in range(n):
+                self._fill(b, PA[i], _PROBLEM_FIELDS, problems[i])
+                self._fill(b, OA[i], _OUTPUT_FIELDS, outputs[i])
+            _check(self._lib.ffvd_nll_grads_batched(self._h, kind, int(bool(collapsed)), n, PA, int(flags), float(jitter), OA))
+        finally:
+            b.release()
+        return outputs
+
+    def sghmc_update(self, theta, grad, noise, xi, g, g2, p, epsilon, mdecay, X_N, burn_in):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_sghmc_update(self._h, b.ptr(theta), b.ptr(grad), b.ptr(noise), b.ptr(xi), b.ptr(g), b.ptr(g2),
+                                               b.ptr(p), float(epsilon), float(mdecay), float(X_N), int(bool(burn_in))))
+        finally:
+            b.release()
+
+    def adam_update(self, theta, grad, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_adam_update(self._h, b.ptr(theta), b.ptr(grad), b.ptr(m), b.ptr(v), float(lr), float(beta1),
+                                              float(beta2), float(eps), int(step)))
+        finally:
+            b.release()

@@ -1,0 +1,779 @@
+// C ABI of libffvd_b200.so (see include/ffvd_b200.h).  Host-side orchestration only: tensor
+// validation, staging of host tensors, workspace management and kernel launches.  There is no
+// CPU compute path in this library.
+#include "../../include/ffvd_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "elementwise.cuh"
+#include "fused.cuh"
+#include "prep_post.cuh"
+
+using namespace ffvd;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(FFVD_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+struct ffvd_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 0;
+  int max_smem = 0;
+  int64_t launches = 0;
+  // workspace arena (grow-only, re-zeroed when the layout changes)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<long long> arena_key;
+  DevProblem* d_probs = nullptr;
+  OutPtrs* d_outs = nullptr;
+  int probs_cap = 0;
+  int* h_status = nullptr;     // pinned
+  size_t h_status_cap = 0;
+};
+
+extern "C" int ffvd_version(void) { return 100; }
+extern "C" const char* ffvd_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* ffvd_status_string(int s) {
+  switch (s) {
+    case FFVD_OK: return "ok";
+    case FFVD_E_BADARG: return "bad argument";
+    case FFVD_E_DTYPE: return "tensor is not float64";
+    case FFVD_E_SHAPE: return "shape mismatch or tensor not C-contiguous";
+    case FFVD_E_DEVICE: return "tensor on a different device than the context";
+    case FFVD_E_CUDA: return "CUDA runtime error";
+    case FFVD_E_UNSUPPORTED: return "option not supported by this build";
+    case FFVD_E_LIMIT: return "size beyond this build's limits";
+    default: return s > 0 ? "matrix not positive definite (status = 1-based failing pivot)" : "unknown status";
+  }
+}
+
+extern "C" int ffvd_ctx_create(int device, void* stream, ffvd_ctx** out) {
+  if (!out) return fail(FFVD_E_BADARG, "out is null");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(FFVD_E_DEVICE, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(FFVD_E_DEVICE, "libffvd_b200 requires an sm_100a (B200) device");
+  ffvd_ctx* c = new ffvd_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->max_smem = (int)prop.sharedMemPerBlockOptin;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(FFVD_E_CUDA, cudaGetErrorString(e)); }
+    c->own_stream = true;
+  }
+  *out = c;
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_ctx_destroy(ffvd_ctx* c) {
+  if (!c) return FFVD_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->arena) cudaFree(c->arena);
+  if (c->d_probs) cudaFree(c->d_probs);
+  if (c->d_outs) cudaFree(c->d_outs);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_ctx_synchronize(ffvd_ctx* c) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return FFVD_OK;
+}
+extern "C" int64_t ffvd_ctx_launch_count(ffvd_ctx* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// tensor import / staging
+struct Tens {
+  double* d = nullptr;     // device pointer
+  void* host = nullptr;    // host pointer if staged
+  size_t numel = 0;
+  int ndim = 0;
+  int64_t shape[4] = {1, 1, 1, 1};
+  bool staged = false, is_out = false, present = false;
+};
+
+struct Call {
+  ffvd_ctx* c;
+  std::vector<Tens> staged;    // copies of staged tensors (for copy-back / free)
+  bool touched_host = false;
+  explicit Call(ffvd_ctx* ctx) : c(ctx) {}
+  int import(DLManagedTensor* mt, bool is_out, Tens& t, const char* name, bool optional = false) {
+    t = Tens();
+    if (!mt) {
+      if (optional) return FFVD_OK;
+      return fail(FFVD_E_BADARG, std::string(name) + " is null");
+    }
+    const DLTensor& dl = mt->dl_tensor;
+    if (dl.dtype.code != 2 || dl.dtype.bits != 64 || dl.dtype.lanes != 1)
+      return fail(FFVD_E_DTYPE, std::string(name) + " must be float64");
+    if (dl.ndim > 4) return fail(FFVD_E_SHAPE, std::string(name) + ": rank > 4");
+    t.ndim = dl.ndim;
+    t.numel = 1;
+    for (int i = 0; i < dl.ndim; ++i) { t.shape[i] = dl.shape[i]; t.numel *= (size_t)dl.shape[i]; }
+    if (dl.strides) {
+      int64_t expect = 1;
+      for (int i = dl.ndim - 1; i >= 0; --i) {
+        if (dl.shape[i] != 1 && dl.strides[i] != expect)
+          return fail(FFVD_E_SHAPE, std::string(name) + " must be C-contiguous");
+        expect *= dl.shape[i];
+      }
+    }
+    t.present = true;
+    t.is_out = is_out;
+    char* base = (char*)dl.data + dl.byte_offset;
+    if (dl.device.device_type == kDLCUDA || dl.device.device_type == kDLCUDAManaged) {
+      if (dl.device.device_type == kDLCUDA && dl.device.device_id != c->device)
+        return fail(FFVD_E_DEVICE, std::string(name) + " lives on another GPU");
+      t.d = (double*)base;
+      return FFVD_OK;
+    }
+    if (dl.device.device_type != kDLCPU && dl.device.device_type != kDLCUDAHost)
+      return fail(FFVD_E_DEVICE, std::string(name) + ": unsupported DLPack device type");
+    // host tensor: explicit staging copy (a transfer, not a compute fallback)
+    t.staged = true;
+    t.host = base;
+    touched_host = true;
+    if (t.numel == 0) return FFVD_OK;
+    CUDA_TRY(cudaMallocAsync((void**)&t.d, t.numel * sizeof(double), c->stream));
+    if (!is_out) CUDA_TRY(cudaMemcpyAsync(t.d, t.host, t.numel * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    staged.push_back(t);
+    return FFVD_OK;
+  }
+  int finish(bool force_sync = false) {
+    for (auto& t : staged)
+      if (t.is_out && t.numel) CUDA_TRY(cudaMemcpyAsync(t.host, t.d, t.numel * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    for (auto& t : staged)
+      if (t.d) CUDA_TRY(cudaFreeAsync(t.d, c->stream));
+    staged.clear();
+    if (touched_host || force_sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    return FFVD_OK;
+  }
+  ~Call() {
+    for (auto& t : staged)
+      if (t.d) cudaFreeAsync(t.d, c->stream);
+  }
+};
+#define TRY(expr)            \
+  do {                       \
+    int _s = (expr);         \
+    if (_s != FFVD_OK) return _s; \
+  } while (0)
+
+static int grid1d(size_t n, int threads = 256, int cap = 148 * 16) {
+  size_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+struct Layout {
+  int nprob, nb, D, M, Mp, Din, Dy, nk;   // nk = kernels per problem (D, or 1 when shared)
+  long long sumS;
+  bool collapsed;
+  size_t off_ZT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
+      off_small, off_terms, off_status, off_utmp, total;
+  size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
+  size_t small_per;                // doubles of small accumulators per problem
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int Din, int Dy, long long sumS, bool collapsed,
+                          bool need_acc) {
+  Layout L;
+  L.nprob = nprob; L.nb = nb; L.nk = nk; L.D = D; L.M = M; L.Mp = Mp; L.Din = Din; L.Dy = Dy; L.sumS = sumS; L.collapsed = collapsed;
+  size_t o = 0;
+  const size_t mm = (size_t)Mp * Mp * sizeof(double);
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  L.off_ZT = take((size_t)nprob * Din * Mp * 8);
+  L.off_Linv = take((size_t)nprob * nk * mm);
+  L.off_LinvT = take((size_t)nprob * nk * mm);
+  L.off_utmp = take((size_t)nprob * M * D * 8);
+  L.off_Wk = take(need_acc ? (size_t)nprob * nb * mm : 0);
+  L.off_Nmat = take(collapsed ? (size_t)nprob * nb * mm : 0);
+  L.off_Hx = take(collapsed ? (size_t)nprob * nb * mm : 0);
+  L.off_HxT = take(collapsed ? (size_t)nprob * nb * mm : 0);
+  L.off_cvec = take(collapsed ? (size_t)nprob * nb * Mp * 8 : 0);
+  L.off_wvec = take(collapsed ? (size_t)nprob * nb * Mp * 8 : 0);
+  L.off_rs = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
+  L.zero_begin = o;
+  L.off_Sacc = take(need_acc ? (size_t)nprob * nb * mm : 0);
+  L.off_ubar = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
+  L.small_per = (size_t)M * Din + (size_t)D * Din + D + D + (size_t)D * Dy + Dy + Dy;
+  L.off_small = take((size_t)nprob * L.small_per * 8);
+  L.off_terms = take((size_t)sumS * FFVD_NTERMS_RAW * 8);
+  L.off_status = take((size_t)nprob * (nb > nk ? nb : nk) * sizeof(int));
+  L.zero_end = o;
+  L.total = o;
+  return L;
+}
+
+static int ensure_arena(ffvd_ctx* c, const Layout& L) {
+  std::vector<long long> key = {L.nprob, L.nb, L.nk, L.D, L.M, L.Mp, L.Din, L.Dy, L.sumS, L.collapsed ? 1 : 0, (long long)L.total};
+  if (L.total > c->arena_bytes) {
+    if (c->arena) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->arena)); c->arena = nullptr; c->arena_bytes = 0; }
+    CUDA_TRY(cudaMalloc((void**)&c->arena, L.total));
+    c->arena_bytes = L.total;
+    c->arena_key.clear();
+  }
+  if (key != c->arena_key) {
+    CUDA_TRY(cudaMemsetAsync(c->arena, 0, L.total, c->stream));   // padding of Linv etc. must be zero
+    c->arena_key = key;
+  }
+  if (c->probs_cap < L.nprob) {
+    if (c->d_probs) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->d_probs)); CUDA_TRY(cudaFree(c->d_outs)); }
+    CUDA_TRY(cudaMalloc((void**)&c->d_probs, sizeof(DevProblem) * L.nprob));
+    CUDA_TRY(cudaMalloc((void**)&c->d_outs, sizeof(OutPtrs) * L.nprob));
+    c->probs_cap = L.nprob;
+  }
+  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk);
+  if (c->h_status_cap < ns) {
+    if (c->h_status) CUDA_TRY(cudaFreeHost(c->h_status));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_status, ns * sizeof(int)));
+    c->h_status_cap = ns;
+  }
+  return FFVD_OK;
+}
+
+static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin, DevProblem& P) {
+  char* a = c->arena;
+  const size_t mm = (size_t)L.Mp * L.Mp;
+  P.ZT = (double*)(a + L.off_ZT) + (size_t)p * L.Din * L.Mp;
+  P.Linv = (double*)(a + L.off_Linv) + (size_t)p * L.nk * mm;
+  P.LinvT = (double*)(a + L.off_LinvT) + (size_t)p * L.nk * mm;
+  P.Sacc = (double*)(a + L.off_Sacc) + (size_t)p * L.nb * mm;
+  P.Wk = (double*)(a + L.off_Wk) + (size_t)p * L.nb * mm;
+  P.Nmat = (double*)(a + L.off_Nmat) + (size_t)p * L.nb * mm;
+  P.Hx = (double*)(a + L.off_Hx) + (size_t)p * L.nb * mm;
+  P.HxT = (double*)(a + L.off_HxT) + (size_t)p * L.nb * mm;
+  P.ubar = (double*)(a + L.off_ubar) + (size_t)p * L.nb * L.Mp;
+  P.cvec = (double*)(a + L.off_cvec) + (size_t)p * L.nb * L.Mp;
+  P.wvec = (double*)(a + L.off_wvec) + (size_t)p * L.nb * L.Mp;
+  P.rs = (double*)(a + L.off_rs) + (size_t)p * L.nb * L.Mp;
+  double* sm = (double*)(a + L.off_small) + (size_t)p * L.small_per;
+  P.gZ = sm; sm += (size_t)L.M * L.Din;
+  P.gl = sm; sm += (size_t)L.D * L.Din;
+  P.gv = sm; sm += L.D;
+  P.gQ = sm; sm += L.D;
+  P.gC = sm; sm += (size_t)L.D * L.Dy;
+  P.gd = sm; sm += L.Dy;
+  P.gR = sm;
+  P.terms_raw = (double*)(a + L.off_terms) + (size_t)s_begin * FFVD_NTERMS_RAW;
+  P.status = (int*)(a + L.off_status) + (size_t)p * (L.nb > L.nk ? L.nb : L.nk);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch helpers
+template <int KIND, int MODE>
+static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int nprob, long long total_items) {
+  const int ngw = Mp / 128;
+  int RB;
+  void (*kern)(const DevProblem*, int, long long) = nullptr;
+  switch (ngw) {
+    case 1: RB = 8; kern = fused_kernel<KIND, 8, 1, MODE>; break;
+    case 2: RB = 8; kern = fused_kernel<KIND, 8, 2, MODE>; break;
+    case 3: RB = 4; kern = fused_kernel<KIND, 4, 3, MODE>; break;
+    case 4: RB = 4; kern = fused_kernel<KIND, 4, 4, MODE>; break;
+    default: return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
+  }
+  const size_t smem = fused_smem_bytes(RB, Mp);
+  if ((int)smem > c->max_smem) return fail(FFVD_E_LIMIT, "fused kernel shared memory exceeds the device limit");
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = total_items < (long long)c->num_sms ? total_items : (long long)c->num_sms;
+  if (grid < 1) return FFVD_OK;
+  kern<<<(int)grid, FFVD_NTHREADS, smem, c->stream>>>(d_probs, nprob, total_items);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FFVD_OK;
+}
+static int rb_of(int Mp) { return (Mp / 128 <= 2) ? 8 : 4; }
+
+template <int KIND>
+static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter) {
+  size_t smem = (size_t)2 * L.Mp * 8;
+  const size_t full = smem + (size_t)L.M * (L.M + 1) * 8;
+  int use_smem = 0;
+  if ((int)full <= c->max_smem) { use_smem = 1; smem = full; }
+  CUDA_TRY(cudaFuncSetAttribute(kzz_prep_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kzz_prep_kernel<KIND><<<dim3(L.nk, L.nprob), 512, smem, c->stream>>>(c->d_probs, jitter, use_smem);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FFVD_OK;
+}
+
+static int launch_bgemm(ffvd_ctx* c, double* C, const double* A, const double* B, int n, double alpha, int batch,
+                        BatchMap mC, BatchMap mA, BatchMap mB) {
+  bgemm_nn_kernel<<<dim3(n / 64, n / 64, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FFVD_OK;
+}
+
+static int check_status(ffvd_ctx* c, const Layout& L) {
+  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk);
+  CUDA_TRY(cudaMemcpyAsync(c->h_status, c->arena + L.off_status, ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < ns; ++i)
+    if (c->h_status[i] != 0) {
+      char buf[160];
+      snprintf(buf, sizeof buf, "Cholesky failed: matrix %zu not positive definite at pivot %d", i, c->h_status[i]);
+      g_last_error = buf;
+      return c->h_status[i];
+    }
+  return FFVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ProbT {
+  Tens X, Z, U, logv, logl, logQ, C, d, logR, Y, ctrl;
+  Tens nll, terms, gX, gZ, gU, glogv, glogl, glogQ, gC, gd, glogR;
+  int S, T, D, Din, nc, Dy, M;
+  double* gx_scratch = nullptr;
+};
+
+static int import_problem(Call& call, int kind, const ffvd_problem* p, const ffvd_outputs* o, ProbT& t) {
+  TRY(call.import(p->X, false, t.X, "X"));
+  TRY(call.import(p->Z, false, t.Z, "Z"));
+  TRY(call.import(p->U, false, t.U, "U"));
+  TRY(call.import(p->logv, false, t.logv, "logv"));
+  TRY(call.import(p->logl, false, t.logl, "logl", kind != FFVD_KERNEL_SE));
+  TRY(call.import(p->logQ, false, t.logQ, "logQ"));
+  TRY(call.import(p->C, false, t.C, "C"));
+  TRY(call.import(p->d, false, t.d, "d"));
+  TRY(call.import(p->logR, false, t.logR, "logR"));
+  TRY(call.import(p->Y, false, t.Y, "Y"));
+  TRY(call.import(p->ctrl, false, t.ctrl, "ctrl", true));
+  if (t.X.ndim == 2) { t.S = 1; t.T = (int)t.X.shape[0] - 1; t.D = (int)t.X.shape[1]; }
+  else if (t.X.ndim == 3) { t.S = (int)t.X.shape[0]; t.T = (int)t.X.shape[1] - 1; t.D = (int)t.X.shape[2]; }
+  else return fail(FFVD_E_SHAPE, "X must be (T+1,D) or (S,T+1,D)");
+  if (t.T < 1 || t.D < 1 || t.S < 1) return fail(FFVD_E_SHAPE, "X is empty");
+  if (t.Z.ndim != 2) return fail(FFVD_E_SHAPE, "Z must be (M,Din)");
+  t.M = (int)t.Z.shape[0]; t.Din = (int)t.Z.shape[1];
+  t.nc = t.Din - t.D;
+  if (t.nc < 0) return fail(FFVD_E_SHAPE, "Z has fewer columns than X");
+  if (t.Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
+  if (t.nc > 0) {
+    if (!t.ctrl.present || t.ctrl.ndim != 2 || t.ctrl.shape[0] < t.T || t.ctrl.shape[1] != t.nc)
+      return fail(FFVD_E_SHAPE, "ctrl must be (>=T, Din-D)");
+    if (t.ctrl.shape[0] != t.T) return fail(FFVD_E_SHAPE, "ctrl must have exactly T rows");
+  }
+  if (t.U.ndim != 2 || t.U.shape[0] != t.M || t.U.shape[1] != t.D) return fail(FFVD_E_SHAPE, "U must be (M,D)");
+  if (t.logv.numel != (size_t)t.D) return fail(FFVD_E_SHAPE, "logv must be (D)");
+  if (kind == FFVD_KERNEL_SE && t.logl.numel != (size_t)t.D * t.Din) return fail(FFVD_E_SHAPE, "logl must be (D,Din)");
+  if (t.logQ.numel != (size_t)t.D) return fail(FFVD_E_SHAPE, "logQ must be (D)");
+  if (t.Y.ndim != 2 || t.Y.shape[0] != t.T) return fail(FFVD_E_SHAPE, "Y must be (T,Dy)");
+  t.Dy = (int)t.Y.shape[1];
+  if (t.C.numel != (size_t)t.D * t.Dy) return fail(FFVD_E_SHAPE, "C must be (D,Dy)");
+  if (t.d.numel != (size_t)t.Dy) return fail(FFVD_E_SHAPE, "d must be (Dy)");
+  if (t.logR.numel != (size_t)t.Dy * t.Dy) return fail(FFVD_E_SHAPE, "logR must be (Dy,Dy)");
+  if (o) {
+    TRY(call.import(o->nll, true, t.nll, "nll", true));
+    TRY(call.import(o->terms, true, t.terms, "terms", true));
+    TRY(call.import(o->g_X, true, t.gX, "g_X", true));
+    TRY(call.import(o->g_Z, true, t.gZ, "g_Z", true));
+    TRY(call.import(o->g_U, true, t.gU, "g_U", true));
+    TRY(call.import(o->g_logv, true, t.glogv, "g_logv", true));
+    TRY(call.import(o->g_logl, true, t.glogl, "g_logl", true));
+    TRY(call.import(o->g_logQ, true, t.glogQ, "g_logQ", true));
+    TRY(call.import(o->g_C, true, t.gC, "g_C", true));
+    TRY(call.import(o->g_d, true, t.gd, "g_d", true));
+    TRY(call.import(o->g_logR, true, t.glogR, "g_logR", true));
+    auto chk = [&](const Tens& g, size_t n, const char* nm) -> int {
+      if (g.present && g.numel != n) return fail(FFVD_E_SHAPE, std::string(nm) + " has the wrong number of elements");
+      return FFVD_OK;
+    };
+    TRY(chk(t.nll, t.S, "nll")); TRY(chk(t.terms, (size_t)t.S * 6, "terms")); TRY(chk(t.gX, t.X.numel, "g_X"));
+    TRY(chk(t.gZ, t.Z.numel, "g_Z")); TRY(chk(t.gU, t.U.numel, "g_U")); TRY(chk(t.glogv, t.D, "g_logv"));
+    TRY(chk(t.glogl, (size_t)t.D * t.Din, "g_logl")); TRY(chk(t.glogQ, t.D, "g_logQ")); TRY(chk(t.gC, t.C.numel, "g_C"));
+    TRY(chk(t.gd, t.Dy, "g_d")); TRY(chk(t.glogR, t.logR.numel, "g_logR"));
+  }
+  return FFVD_OK;
+}
+
+template <int KIND>
+static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* probs, int flags, double jitter,
+                   const ffvd_outputs* outs) {
+  if (!c || !probs || !outs || nprob < 1) return fail(FFVD_E_BADARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  std::vector<ProbT> pt(nprob);
+  long long sumS = 0;
+  for (int p = 0; p < nprob; ++p) {
+    TRY(import_problem(call, KIND, &probs[p], &outs[p], pt[p]));
+    if (p > 0 && (pt[p].M != pt[0].M || pt[p].D != pt[0].D || pt[p].Din != pt[0].Din || pt[p].Dy != pt[0].Dy))
+      return fail(FFVD_E_SHAPE, "batched problems must share M, D, Din, Dy");
+    if (collapsed && pt[p].S != pt[0].S) return fail(FFVD_E_UNSUPPORTED, "collapsed batched problems must share S");
+    sumS += pt[p].S;
+  }
+  const int M = pt[0].M, D = pt[0].D, Din = pt[0].Din, Dy = pt[0].Dy;
+  const int Mp = (int)align_up(M, 128);
+  if (Mp > 512) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
+  const bool no_grads = (flags & FFVD_FLAG_NO_GRADS) != 0;
+  const int nb = collapsed ? pt[0].S * D : D;
+  Layout L = make_layout(nprob, nb, D, D, M, Mp, Din, Dy, sumS, collapsed != 0, true);
+  TRY(ensure_arena(c, L));
+  const int RB = rb_of(Mp), BT = 8 * RB;
+
+  std::vector<DevProblem> hp(nprob);
+  std::vector<OutPtrs> ho(nprob);
+  long long item = 0, s_begin = 0;
+  for (int p = 0; p < nprob; ++p) {
+    ProbT& t = pt[p];
+    DevProblem& P = hp[p];
+    memset(&P, 0, sizeof P);
+    P.X = t.X.d; P.Z = t.Z.d; P.U = t.U.d; P.logv = t.logv.d; P.logl = t.logl.d; P.logQ = t.logQ.d; P.C = t.C.d;
+    P.dvec = t.d.d; P.logR = t.logR.d; P.Y = t.Y.d; P.ctrl = t.ctrl.d;
+    P.S = t.S; P.T = t.T; P.D = D; P.Din = Din; P.nc = t.nc; P.Dy = Dy; P.M = M; P.Mp = Mp; P.Dx = D; P.xrows = t.T + 1; P.hs = 1;
+    P.ntiles = (t.T + BT - 1) / BT;
+    P.item_begin = item;
+    P.nitems = (long long)D * t.S * P.ntiles;
+    item += P.nitems;
+    bind_problem(c, L, p, s_begin, P);
+    s_begin += t.S;
+    if (t.gX.present) P.gX = t.gX.d;
+    else if (!no_grads) {
+      CUDA_TRY(cudaMallocAsync((void**)&t.gx_scratch, t.X.numel * 8, c->stream));
+      P.gX = t.gx_scratch;
+    }
+    if (P.gX) CUDA_TRY(cudaMemsetAsync(P.gX, 0, t.X.numel * 8, c->stream));
+    OutPtrs& O = ho[p];
+    O.nll = t.nll.d; O.terms = t.terms.d; O.g_Z = t.gZ.d; O.g_U = t.gU.d; O.g_logv = t.glogv.d; O.g_logl = t.glogl.d;
+    O.g_logQ = t.glogQ.d; O.g_C = t.gC.d; O.g_d = t.gd.d; O.g_logR = t.glogR.d;
+  }
+  const long long total_items = item;
+  CUDA_TRY(cudaMemcpyAsync(c->d_probs, hp.data(), sizeof(DevProblem) * nprob, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->d_outs, ho.data(), sizeof(OutPtrs) * nprob, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
+
+  TRY(launch_prep<KIND>(c, L, jitter));
+  const int nz = nprob * nb;
+  const BatchMap idm = {1, 1, 1};                // z -> z
+  const BatchMap lmap = {nb, D, D};              // z -> (z / nb) * D + z % D
+  // the pools are contiguous over problems, so problem 0's pointers are the pool bases
+  double* Sacc = hp[0].Sacc; double* Wk = hp[0].Wk; double* Linv = hp[0].Linv; double* LinvT = hp[0].LinvT;
+  double* Nmat = hp[0].Nmat; double* Hx = hp[0].Hx; double* HxT = hp[0].HxT;
+  const dim3 gsym((unsigned)((size_t)M * M + 255) / 256, nb, nprob);
+
+  if (no_grads && !collapsed) {
+    TRY((launch_fused<KIND, MODE_FORWARD>(c, Mp, c->d_probs, nprob, total_items)));
+  } else if (!collapsed) {
+    TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, c->d_probs, nprob, total_items)));
+    symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 0); c->launches++;
+  } else {
+    TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, c->d_probs, nprob, total_items)));
+    symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 1); c->launches++;
+    collapsed_chol_kernel<<<dim3(nb, nprob), 512, (size_t)2 * Mp * 8, c->stream>>>(c->d_probs); c->launches++;
+    if (!no_grads) {
+      TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));          // H^{-1} = L_H^{-T} L_H^{-1}
+      collapsed_vec_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
+      TRY(launch_bgemm(c, Hx, Wk, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Mat' L^{-1}
+      TRY(launch_bgemm(c, Nmat, LinvT, Hx, Mp, 1.0, nz, idm, lmap, idm));     // N = L^{-T} Mat' L^{-1}
+      TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, c->d_probs, nprob, total_items)));
+      TRY(launch_bgemm(c, HxT, Wk, Sacc, Mp, 1.0, nz, idm, idm, idm));        // Mat' S
+      symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 2); c->launches++;   // Sacc <- Gs
+    } else {
+      // forward only still needs c for the quadratic term
+      TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));
+      collapsed_vec_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    }
+  }
+  if (!no_grads) {
+    TRY(launch_bgemm(c, Wk, Sacc, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Gs L^{-1}
+    TRY(launch_bgemm(c, Sacc, LinvT, Wk, Mp, -0.5, nz, idm, lmap, idm));      // Kbar_zz = -1/2 L^{-T} Gs L^{-1}
+    const dim3 grow((M + 7) / 8, nb, nprob);
+    wz_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    kzz_bwd_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+  }
+  finalize_kernel<KIND><<<nprob, 256, 0, c->stream>>>(c->d_probs, c->d_outs, collapsed, flags); c->launches++;
+  if (!no_grads) {
+    size_t maxn = 0;
+    for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
+    scale_gx_kernel<<<dim3(grid1d(maxn), nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  for (auto& t : pt)
+    if (t.gx_scratch) CUDA_TRY(cudaFreeAsync(t.gx_scratch, c->stream));
+  int st = FFVD_OK;
+  if (!(flags & 8)) st = check_status(c, L);
+  TRY(call.finish());
+  return st;
+}
+
+extern "C" int ffvd_nll_grads_uncollapsed(ffvd_ctx* c, int kind, const ffvd_problem* p, int flags, double jitter,
+                                          const ffvd_outputs* o) {
+  if (kind == FFVD_KERNEL_SE) return run_nll<0>(c, 0, 1, p, flags, jitter, o);
+  if (kind == FFVD_KERNEL_LINEAR) return run_nll<1>(c, 0, 1, p, flags, jitter, o);
+  return fail(FFVD_E_BADARG, "unknown kernel kind");
+}
+extern "C" int ffvd_nll_grads_collapsed(ffvd_ctx* c, int kind, const ffvd_problem* p, int flags, double jitter,
+                                        const ffvd_outputs* o) {
+  if (kind == FFVD_KERNEL_SE) return run_nll<0>(c, 1, 1, p, flags, jitter, o);
+  if (kind == FFVD_KERNEL_LINEAR) return run_nll<1>(c, 1, 1, p, flags, jitter, o);
+  return fail(FFVD_E_BADARG, "unknown kernel kind");
+}
+extern "C" int ffvd_nll_grads_batched(ffvd_ctx* c, int kind, int collapsed, int nprob, const ffvd_problem* p, int flags,
+                                      double jitter, const ffvd_outputs* o) {
+  if (kind == FFVD_KERNEL_SE) return run_nll<0>(c, collapsed, nprob, p, flags, jitter, o);
+  if (kind == FFVD_KERNEL_LINEAR) return run_nll<1>(c, collapsed, nprob, p, flags, jitter, o);
+  return fail(FFVD_E_BADARG, "unknown kernel kind");
+}
+
+// ---------------------------------------------------------------------------------------------
+// operator-level entry points
+extern "C" int ffvd_kernel_K(ffvd_ctx* c, int kind, DLManagedTensor* X, DLManagedTensor* X2, DLManagedTensor* logv,
+                             DLManagedTensor* logl, DLManagedTensor* out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tX, tX2, tv, tl, to;
+  TRY(call.import(X, false, tX, "X"));
+  TRY(call.import(X2, false, tX2, "X2", true));
+  TRY(call.import(logv, false, tv, "logv"));
+  TRY(call.import(logl, false, tl, "logl", kind != FFVD_KERNEL_SE));
+  TRY(call.import(out, true, to, "out"));
+  if (tX.ndim != 2) return fail(FFVD_E_SHAPE, "X must be (N,Din)");
+  const int N = (int)tX.shape[0], Din = (int)tX.shape[1];
+  const Tens& t2 = tX2.present ? tX2 : tX;
+  if (t2.ndim != 2 || t2.shape[1] != Din) return fail(FFVD_E_SHAPE, "X2 must be (N2,Din)");
+  const int N2 = (int)t2.shape[0];
+  if (tv.numel != 1) return fail(FFVD_E_SHAPE, "logv must be a scalar");
+  if (kind == FFVD_KERNEL_SE && tl.numel != (size_t)Din) return fail(FFVD_E_SHAPE, "logl must be (Din)");
+  if (to.numel != (size_t)N * N2) return fail(FFVD_E_SHAPE, "out must be (N,N2)");
+  if (to.numel) {
+    const int grid = grid1d(to.numel);
+    if (kind == FFVD_KERNEL_SE) kernel_K_kernel<0><<<grid, 256, 0, c->stream>>>(tX.d, t2.d, N, N2, Din, tv.d, tl.d, to.d);
+    else if (kind == FFVD_KERNEL_LINEAR) kernel_K_kernel<1><<<grid, 256, 0, c->stream>>>(tX.d, t2.d, N, N2, Din, tv.d, nullptr, to.d);
+    else return fail(FFVD_E_BADARG, "unknown kernel kind");
+    c->launches++;
+  }
+  return call.finish();
+}
+
+extern "C" int ffvd_kernel_Kdiag(ffvd_ctx* c, int kind, DLManagedTensor* X, DLManagedTensor* logv, DLManagedTensor* logl,
+                                 DLManagedTensor* out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tX, tv, tl, to;
+  TRY(call.import(X, false, tX, "X"));
+  TRY(call.import(logv, false, tv, "logv"));
+  TRY(call.import(logl, false, tl, "logl", true));
+  TRY(call.import(out, true, to, "out"));
+  if (tX.ndim != 2) return fail(FFVD_E_SHAPE, "X must be (N,Din)");
+  const int N = (int)tX.shape[0], Din = (int)tX.shape[1];
+  if (tv.numel != 1) return fail(FFVD_E_SHAPE, "logv must be a scalar");
+  if (to.numel != (size_t)N) return fail(FFVD_E_SHAPE, "out must be (N)");
+  if (N) {
+    if (kind == FFVD_KERNEL_SE) kernel_Kdiag_kernel<0><<<grid1d(N), 256, 0, c->stream>>>(tX.d, N, Din, tv.d, to.d);
+    else if (kind == FFVD_KERNEL_LINEAR) kernel_Kdiag_kernel<1><<<grid1d(N), 256, 0, c->stream>>>(tX.d, N, Din, tv.d, to.d);
+    else return fail(FFVD_E_BADARG, "unknown kernel kind");
+    c->launches++;
+  }
+  return call.finish();
+}
+
+// shared prep for kernel_pre_cal / conditional: one DevProblem with only the Z-side fields.
+static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, const Tens& tl, int nk, int R, double jitter,
+                       Layout& L, DevProblem& P) {
+  const int M = (int)tZ.shape[0], Din = (int)tZ.shape[1];
+  if (Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
+  const int Mp = (int)align_up(M, 128);
+  L = make_layout(1, nk, nk, R, M, Mp, Din, 1, 1, false, false);
+  TRY(ensure_arena(c, L));
+  memset(&P, 0, sizeof P);
+  P.Z = tZ.d; P.logv = tv.d; P.logl = tl.d;
+  P.M = M; P.Mp = Mp; P.Din = Din; P.D = R; P.hs = (nk == 1 && R != 1) ? 0 : 1; P.S = 1;
+  if (nk == 1) P.hs = 0;
+  bind_problem(c, L, 0, 0, P);
+  CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
+  if (kind == FFVD_KERNEL_SE) TRY(launch_prep<0>(c, L, jitter));
+  else if (kind == FFVD_KERNEL_LINEAR) TRY(launch_prep<1>(c, L, jitter));
+  else return fail(FFVD_E_BADARG, "unknown kernel kind");
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_kernel_pre_cal(ffvd_ctx* c, int kind, DLManagedTensor* Z, DLManagedTensor* logv, DLManagedTensor* logl,
+                                   double jitter, DLManagedTensor* LinvT_out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tZ, tv, tl, to;
+  TRY(call.import(Z, false, tZ, "Z"));
+  TRY(call.import(logv, false, tv, "logv"));
+  TRY(call.import(logl, false, tl, "logl", kind != FFVD_KERNEL_SE));
+  TRY(call.import(LinvT_out, true, to, "LinvT_out"));
+  if (tZ.ndim != 2) return fail(FFVD_E_SHAPE, "Z must be (M,Din)");
+  const int M = (int)tZ.shape[0], Din = (int)tZ.shape[1];
+  const int D = (int)tv.numel;
+  if (D < 1) return fail(FFVD_E_SHAPE, "logv must be (D)");
+  if (kind == FFVD_KERNEL_SE && tl.numel != (size_t)D * Din) return fail(FFVD_E_SHAPE, "logl must be (D,Din)");
+  if (to.numel != (size_t)D * M * M) return fail(FFVD_E_SHAPE, "LinvT_out must be (D,M,M)");
+  Layout L; DevProblem P;
+  TRY(setup_zside(c, kind, tZ, tv, tl, D, D, jitter, L, P));
+  P.hs = 1;
+  for (int d = 0; d < D; ++d)
+    CUDA_TRY(cudaMemcpy2DAsync(to.d + (size_t)d * M * M, (size_t)M * 8, P.LinvT + (size_t)d * P.Mp * P.Mp, (size_t)P.Mp * 8,
+                               (size_t)M * 8, M, cudaMemcpyDeviceToDevice, c->stream));
+  int st = check_status(c, L);
+  TRY(call.finish());
+  return st;
+}
+
+// u'[:,d] = L_d^{-1} f[:,d]  (non-white conditional).  grid (R); block 256
+__global__ void unwhiten_kernel(const DevProblem* __restrict__ probs, const double* __restrict__ f, double* __restrict__ out) {
+  const DevProblem& P = probs[0];
+  const int d = blockIdx.x, M = P.M, Mp = P.Mp, D = P.D;
+  const double* Li = P.Linv + (size_t)d * P.hs * Mp * Mp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = warp; m < M; m += 8) {
+    double t = 0.0;
+    for (int n = lane; n <= m; n += 32) t = fma(Li[(size_t)m * Mp + n], f[(size_t)n * D + d], t);
+    t = warp_sum(t);
+    if (lane == 0) out[(size_t)m * D + d] = t;
+  }
+}
+
+extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                                DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
+                                int white, int full_cov, double jitter, DLManagedTensor* mean_out, DLManagedTensor* var_out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (q_sqrt || full_cov) return fail(FFVD_E_UNSUPPORTED, "conditional: q_sqrt / full_cov are prediction-only options not built yet");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tX, tZ, tv, tl, tf, tm, tvar;
+  TRY(call.import(Xnew, false, tX, "Xnew"));
+  TRY(call.import(Z, false, tZ, "Z"));
+  TRY(call.import(logv, false, tv, "logv"));
+  TRY(call.import(logl, false, tl, "logl", kind != FFVD_KERNEL_SE));
+  TRY(call.import(f, false, tf, "f"));
+  TRY(call.import(mean_out, true, tm, "mean_out"));
+  TRY(call.import(var_out, true, tvar, "var_out"));
+  if (tX.ndim != 2 || tZ.ndim != 2 || tf.ndim != 2) return fail(FFVD_E_SHAPE, "Xnew, Z, f must be 2-d");
+  const int N = (int)tX.shape[0], Din = (int)tZ.shape[1], M = (int)tZ.shape[0], R = (int)tf.shape[1];
+  if (tX.shape[1] != Din || tf.shape[0] != M) return fail(FFVD_E_SHAPE, "Xnew (N,Din), Z (M,Din), f (M,R) expected");
+  const int nk = shared_kernel ? 1 : R;
+  if (tv.numel != (size_t)nk) return fail(FFVD_E_SHAPE, "logv must have one entry per kernel");
+  if (kind == FFVD_KERNEL_SE && tl.numel != (size_t)nk * Din) return fail(FFVD_E_SHAPE, "logl must be (kernels,Din)");
+  if (tm.numel != (size_t)N * R || tvar.numel != (size_t)N * R) return fail(FFVD_E_SHAPE, "mean/var must be (N,R)");
+  if (N == 0) return call.finish();
+  Layout L; DevProblem P;
+  TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P));
+  if (P.Mp > 512) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
+  const int RB = rb_of(P.Mp), BT = 8 * RB;
+  P.hs = shared_kernel ? 0 : 1;
+  P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;
+  P.ntiles = (N + BT - 1) / BT; P.item_begin = 0; P.nitems = (long long)R * P.ntiles;
+  P.cond_mean = tm.d; P.cond_var = tvar.d;
+  double* utmp = (double*)(c->arena + L.off_utmp);
+  P.U = tf.d;
+  CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
+  if (!white) {
+    unwhiten_kernel<<<R, 256, 0, c->stream>>>(c->d_probs, tf.d, utmp); c->launches++;
+    P.U = utmp;
+    CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, c->d_probs, 1, P.nitems)));
+  else TRY((launch_fused<1, MODE_COND>(c, P.Mp, c->d_probs, 1, P.nitems)));
+  int st = check_status(c, L);
+  TRY(call.finish());
+  return st;
+}
+
+extern "C" int ffvd_logdensity_norm_diag(ffvd_ctx* c, DLManagedTensor* y, DLManagedTensor* ymean, DLManagedTensor* Rchols,
+                                         int vec, DLManagedTensor* out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens ty, tm, tr, to;
+  TRY(call.import(y, false, ty, "y"));
+  TRY(call.import(ymean, false, tm, "ymean"));
+  TRY(call.import(Rchols, false, tr, "Rchols"));
+  TRY(call.import(out, true, to, "out"));
+  if (ty.ndim != 2 || tm.numel != ty.numel) return fail(FFVD_E_SHAPE, "y, ymean must be (N,Dy)");
+  const int N = (int)ty.shape[0], Dy = (int)ty.shape[1];
+  if (tr.numel != (size_t)Dy) return fail(FFVD_E_SHAPE, "Rchols must be (Dy)");
+  if (to.numel != (vec ? (size_t)N : (size_t)N * Dy)) return fail(FFVD_E_SHAPE, "out has the wrong size");
+  if (N) { logdensity_diag_kernel<<<grid1d(N), 256, 0, c->stream>>>(ty.d, tm.d, tr.d, N, Dy, vec, to.d); c->launches++; }
+  return call.finish();
+}
+
+extern "C" int ffvd_sghmc_update(ffvd_ctx* c, DLManagedTensor* theta, DLManagedTensor* grad, DLManagedTensor* noise,
+                                 DLManagedTensor* xi, DLManagedTensor* g, DLManagedTensor* g2, DLManagedTensor* p,
+                                 double epsilon, double mdecay, double X_N, int burn_in) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tt, tg, tn, txi, tgg, tg2, tp;
+  // in-place tensors are imported as inputs (copied in) and flagged as outputs (copied back)
+  TRY(call.import(theta, false, tt, "theta"));
+  TRY(call.import(grad, false, tg, "grad"));
+  TRY(call.import(noise, false, tn, "noise"));
+  TRY(call.import(xi, false, txi, "xi"));
+  TRY(call.import(g, false, tgg, "g"));
+  TRY(call.import(g2, false, tg2, "g2"));
+  TRY(call.import(p, false, tp, "p"));
+  const size_t n = tt.numel;
+  if (tg.numel != n || tn.numel != n || txi.numel != n || tgg.numel != n || tg2.numel != n || tp.numel != n)
+    return fail(FFVD_E_SHAPE, "all SG-HMC tensors must have the same number of elements");
+  for (auto& s : call.staged)
+    if (s.host == tt.host || s.host == tp.host || (burn_in && (s.host == txi.host || s.host == tgg.host || s.host == tg2.host)))
+      s.is_out = true;
+  if (n) {
+    const double eps_scaled = epsilon / sqrt(X_N);
+    const int grid = grid1d(n, 256, c->num_sms * 8);
+    if (burn_in) sghmc_kernel<1><<<grid, 256, 0, c->stream>>>(tt.d, tg.d, tn.d, txi.d, tgg.d, tg2.d, tp.d, n, epsilon, mdecay, eps_scaled);
+    else sghmc_kernel<0><<<grid, 256, 0, c->stream>>>(tt.d, tg.d, tn.d, txi.d, tgg.d, tg2.d, tp.d, n, epsilon, mdecay, eps_scaled);
+    c->launches++;
+  }
+  return call.finish();
+}
+
+extern "C" int ffvd_adam_update(ffvd_ctx* c, DLManagedTensor* theta, DLManagedTensor* grad, DLManagedTensor* m,
+                                DLManagedTensor* v, double lr, double beta1, double beta2, double eps, int64_t step) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (step < 1) return fail(FFVD_E_BADARG, "step is 1-based");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tt, tg, tm, tv;
+  TRY(call.import(theta, false, tt, "theta"));
+  TRY(call.import(grad, false, tg, "grad"));
+  TRY(call.import(m, false, tm, "m"));
+  TRY(call.import(v, false, tv, "v"));
+  const size_t n = tt.numel;
+  if (tg.numel != n || tm.numel != n || tv.numel != n) return fail(FFVD_E_SHAPE, "all Adam tensors must have the same size");
+  for (auto& s : call.staged)
+    if (s.host == tt.host || s.host == tm.host || s.host == tv.host) s.is_out = true;
+  if (n) {
+    const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
+    adam_kernel<<<grid1d(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(tt.d, tg.d, tm.d, tv.d, n, lr_t, beta1, beta2, eps);
+    c->launches++;
+  }
+  return call.finish();
+}

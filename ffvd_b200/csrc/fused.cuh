@@ -1,0 +1,710 @@
+// Fused per-tile GPSSM kernels (sm_100a): K tile on the fly -> L^{-1} contraction on the FP64
+// tensor pipe (DMMA m8n8k4) -> mean / variance / Gaussian log-density -> hand-derived backward.
+// Replaces, per (sample s, tile of BT time steps, output dim d), the TF sub-graph built by
+//   conditionals_multi_output.py:73-120 + dgp_model.py:337-359 (uncollapsed),
+//   conditionals_multi_output.py:230-257 (collapsed), and its tf.gradients (base_model.py:148).
+// Nothing of size T x M ever goes to HBM.
+#pragma once
+#include "ffvd_common.cuh"
+
+namespace ffvd {
+
+enum { MODE_UNCOLLAPSED = 0, MODE_COLLAPSED_P1 = 1, MODE_COLLAPSED_P2 = 2, MODE_FORWARD = 3, MODE_COND = 4 };
+
+struct Smem {
+  double* tile;     // BT x lda
+  double* xs;       // (BT+1) x XLD : X~ rows t0..t0+BT  = [x_t, ctrl_t, 1, 0..]
+  double* xsc;      // BT x XLD     : SE: x~ scaled by 1/l_j ; unused for Linear
+  double* us;       // Mp           : u_d (uncollapsed) / w'_d (collapsed pass 2)
+  double* es;       // 64           : e_t (uncollapsed) / delta_t (collapsed)
+  double* rowpart;  // 2 x 8 x 64
+  double* stage;    // 8 warps x 8 x 40
+  double* part;     // 64 x 32 (x KS folded into rows)
+  double* small;    // 64: invl2[32], sil[32]
+  double* red;      // 40: block-level reductions (smem atomics)
+};
+
+template <int RB>
+__host__ __device__ constexpr int bt_of() { return 8 * RB; }
+
+__host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp) {
+  const int BT = 8 * RB;
+  // every sub-array is rounded up to an even number of doubles so that all of them stay 16-byte aligned
+  size_t n = (size_t)BT * (Mp + 4) + 8 * 8 * 40 + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
+             (((size_t)BT * FFVD_XLD + 1) & ~(size_t)1) + Mp + 64 + 2 * 8 * 64 + 64 * 32 + 64 + 40;
+  return n * sizeof(double);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k(x_r, z_j) for the (rows 8*rb+g, cols jbase..jbase+3) owned by this lane.
+template <int KIND, int RB>
+__device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem& sm, const double* __restrict__ ZT,
+                                                int Mp, int Din, double v, int jbase, int g, int M, int nvalid) {
+  double s[RB][4];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[rb][c] = 0.0;
+  const double* xsrc = (KIND == 0) ? sm.xsc : sm.xs;
+  for (int jd = 0; jd < Din; ++jd) {
+    const double2 z01 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)jd * Mp + jbase));
+    const double2 z23 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)jd * Mp + jbase + 2));
+    double z[4] = {z01.x, z01.y, z23.x, z23.y};
+    if (KIND == 0) {
+      const double sil = sm.small[32 + jd];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) z[c] *= sil;
+    }
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      const double x = xsrc[(8 * rb + g) * FFVD_XLD + jd];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (KIND == 0) {
+          const double t = x - z[c];
+          s[rb][c] = fma(t, t, s[rb][c]);
+        } else {
+          s[rb][c] = fma(x, z[c], s[rb][c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double k = (KIND == 0) ? v * exp(-0.5 * s[rb][c]) : v * s[rb][c];
+      if (jbase + c >= M || 8 * rb + g >= nvalid) k = 0.0;
+      kv[rb][c] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// acc (BT x Mp, distributed) = Aop(tile) (BT x Mp) * B (Mp x Mp, row-major in global/L2).
+// TRI = +1: B upper triangular (B[k][n] != 0 only for k <= n);  -1: lower;  0: dense.
+// Lane (g,q) of the warp ends up with rows 8*rb+g, columns 16*group+4q+{0,1,2,3}.
+template <int RB, int NGW, int TRI, class AOp>
+__device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const double* tile, int lda,
+                                          const double* __restrict__ B, int Mp, int warp, int g, int q, AOp aop) {
+  int j0[NGW];
+  int kbeg = (TRI < 0) ? Mp : 0, kend = (TRI > 0) ? 0 : Mp;
+#pragma unroll
+  for (int ng = 0; ng < NGW; ++ng) {
+    j0[ng] = 16 * group_index(warp, ng);
+    if (TRI > 0) kend = max(kend, j0[ng] + 16);
+    if (TRI < 0) kbeg = min(kbeg, j0[ng]);
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[ng][rb][c] = 0.0;
+  }
+  double2 bcur[NGW], bnxt[NGW];
+  auto active = [&](int ng, int k0) -> bool {
+    return (TRI > 0) ? (k0 < j0[ng] + 16) : ((TRI < 0) ? (k0 >= j0[ng]) : true);
+  };
+  auto loadB = [&](int k0, double2(&b)[NGW]) {
+#pragma unroll
+    for (int ng = 0; ng < NGW; ++ng) {
+      if (active(ng, k0))
+        b[ng] = __ldg(reinterpret_cast<const double2*>(B + (size_t)(k0 + q) * Mp + j0[ng] + 2 * g));
+      else
+        b[ng] = make_double2(0.0, 0.0);
+    }
+  };
+  loadB(kbeg, bcur);
+  for (int k0 = kbeg; k0 < kend; k0 += 4) {
+    if (k0 + 4 < kend) loadB(k0 + 4, bnxt);
+    double a[RB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) a[rb] = aop(tile[(8 * rb + g) * lda + k0 + q], rb, k0 + q);
+#pragma unroll
+    for (int ng = 0; ng < NGW; ++ng) {
+      if (active(ng, k0)) {
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          dmma884(acc[ng][rb][0], acc[ng][rb][2], a[rb], bcur[ng].x);
+          dmma884(acc[ng][rb][1], acc[ng][rb][3], a[rb], bcur[ng].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int ng = 0; ng < NGW; ++ng) bcur[ng] = bnxt[ng];
+  }
+}
+
+// store the distributed (BT x Mp) fragment set into the shared tile
+template <int RB, int NGW>
+__device__ __forceinline__ void store_tile(const double (&acc)[NGW][RB][4], double* tile, int lda, int warp, int g,
+                                           int q) {
+#pragma unroll
+  for (int ng = 0; ng < NGW; ++ng) {
+    const int jb = 16 * group_index(warp, ng) + 4 * q;
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      double* p = tile + (8 * rb + g) * lda + jb;
+      *reinterpret_cast<double2*>(p) = make_double2(acc[ng][rb][0], acc[ng][rb][1]);
+      *reinterpret_cast<double2*>(p + 2) = make_double2(acc[ng][rb][2], acc[ng][rb][3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// S (lower 32x32 tiles) += tile^T tile  over the BT rows, flushed with coalesced RED.add.f64.
+template <int RB>
+__device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
+                                           int warp, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int nt = Mp >> 5;
+  const int ntiles = nt * (nt + 1) / 2;
+  for (int tix = warp; tix < ntiles; tix += FFVD_NWARPS) {
+    // decode (ti >= tj) from the linear lower-triangular index
+    int ti = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= tix) ++ti;
+    while (ti * (ti + 1) / 2 > tix) --ti;
+    const int tj = tix - ti * (ti + 1) / 2;
+    const int m0 = 32 * ti, n0 = 32 * tj;
+    double c[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+#pragma unroll 2
+    for (int k0 = 0; k0 < 8 * RB; k0 += 4) {
+      double a[4], b[4];
+      const double* row = tile + (k0 + q) * lda + g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = row[m0 + 8 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = row[n0 + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<double2*>(stage_w + g * 40 + 8 * j + 2 * q) = make_double2(c[i][j][0], c[i][j][1]);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) atomicAdd(S + (size_t)(m0 + 8 * i + r) * Mp + n0 + lane, stage_w[r * 40 + lane]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Back-propagate W (BT x Mp, in the shared tile) through K(Xc, Z):
+//   WtX~ = W^T [Xc,1]   (Mp x (Din+1))   ->  dJ/dZ rows
+//   WZ~  = W [Z,1]      (BT x (Din+1))   ->  dJ/dXc rows
+// SE: W = kbar*k;  Linear: W = kbar (the factor v is applied here).
+template <int KIND, int RB>
+__device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevProblem& P, int d, double v, double* gXs,
+                                           int t0, int nvalid, int warp, int lane, int tid) {
+  const int g = lane >> 2, q = lane & 3;
+  const int Din = P.Din, M = P.M, Mp = P.Mp, D = P.D;
+  const int nbx = (Din + 1 + 7) >> 3;           // n-blocks covering Din+1 columns
+  const int BT = 8 * RB;
+  const double* tile = sm.tile;
+  // ---- W^T X~ : warp owns m-blocks warp, warp+8, ...
+  {
+    const int nbc = Din >> 3, qc = (Din & 7) >> 1, ec = Din & 1;
+    double lacc[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) lacc[nb][0] = lacc[nb][1] = 0.0;
+    for (int mb = warp; mb < (Mp >> 3); mb += FFVD_NWARPS) {
+      double c[4][2];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) c[nb][0] = c[nb][1] = 0.0;
+#pragma unroll 2
+      for (int k0 = 0; k0 < BT; k0 += 4) {
+        const double a = tile[(k0 + q) * lda + 8 * mb + g];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+          if (nb < nbx) {
+            const double b = sm.xs[(k0 + q) * FFVD_XLD + 8 * nb + g];
+            dmma884(c[nb][0], c[nb][1], a, b);
+          }
+        }
+      }
+      // column sum of W for row m = 8*mb+g sits at column Din of the product
+      double csv = 0.0;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        if (nb == nbc) csv = ec ? c[nb][1] : c[nb][0];
+      const double cs = __shfl_sync(0xffffffffu, csv, g * 4 + qc);
+      const int m = 8 * mb + g;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        if (nb < nbx) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int jd = 8 * nb + 2 * q + e;
+            if (jd < Din && m < M) {
+              const double z = P.Z[(size_t)m * Din + jd];
+              double zb;
+              if (KIND == 0) {
+                zb = sm.small[jd] * (c[nb][e] - cs * z);
+                lacc[nb][e] -= z * zb;
+              } else {
+                zb = v * c[nb][e];
+              }
+              atomicAdd(P.gZ + (size_t)m * Din + jd, zb);
+            }
+          }
+        }
+      }
+    }
+    if (KIND == 0) {
+      // reduce over g (lanes with equal q), then one atomic per column
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double x = lacc[nb][e];
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          x += __shfl_xor_sync(0xffffffffu, x, 8);
+          x += __shfl_xor_sync(0xffffffffu, x, 16);
+          const int jd = 8 * nb + 2 * q + e;
+          if (g == 0 && nb < nbx && jd < Din) atomicAdd(P.gl + (size_t)d * Din + jd, x);
+        }
+    }
+  }
+  // ---- W Z~ : warp -> (row block rb, k slice ks)
+  {
+    constexpr int KS = FFVD_NWARPS / RB > 0 ? FFVD_NWARPS / RB : 1;
+    const int rb = warp % RB, ks = warp / RB;
+    if (ks < KS) {
+      const int klen = Mp / KS;
+      double c[4][2];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) c[nb][0] = c[nb][1] = 0.0;
+      for (int k0 = ks * klen; k0 < (ks + 1) * klen; k0 += 4) {
+        const double a = tile[(8 * rb + g) * lda + k0 + q];
+        const int m = k0 + q;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+          if (nb < nbx) {
+            const int jd = 8 * nb + g;
+            double b = 0.0;
+            if (jd < Din) b = __ldg(P.ZT + (size_t)jd * Mp + m);
+            else if (jd == Din) b = (m < M) ? 1.0 : 0.0;
+            dmma884(c[nb][0], c[nb][1], a, b);
+          }
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+        if (nb < nbx) {
+          double* p = sm.part + (size_t)(ks * BT + 8 * rb + g) * 32 + 8 * nb + 2 * q;
+          p[0] = c[nb][0];
+          p[1] = c[nb][1];
+        }
+    }
+    __syncthreads();
+    double vacc = 0.0;
+    for (int idx = tid; idx < BT * 32; idx += FFVD_NTHREADS) {
+      const int r = idx >> 5, jd = idx & 31;
+      if (jd < Din && r < nvalid) {
+        double wz = 0.0, rs = 0.0;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          wz += sm.part[(size_t)(k * BT + r) * 32 + jd];
+          rs += sm.part[(size_t)(k * BT + r) * 32 + Din];
+        }
+        const double x = sm.xs[r * FFVD_XLD + jd];
+        double xb;
+        if (KIND == 0) {
+          xb = -sm.small[jd] * (x * rs - wz);
+          atomicAdd(sm.red + 8 + jd, -x * xb);      // d/dlogl row part
+          if (jd == 0) vacc += rs;                  // d/dlogv = sum W
+        } else {
+          xb = v * wz;
+          vacc += x * xb;                           // sum kbar*k
+        }
+        if (jd < D) atomicAdd(gXs + (size_t)(t0 + r) * D + jd, xb);
+      }
+    }
+    vacc = warp_sum(vacc);
+    if (lane == 0) atomicAdd(sm.red + 7, vacc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int RB, int NGW, int MODE>
+__global__ void __launch_bounds__(FFVD_NTHREADS, 1)
+fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_items) {
+  extern __shared__ __align__(16) double smem_raw[];
+  constexpr int BT = 8 * RB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+
+  for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    // ---- decode item -> (problem, d, s, tile); d is the slowest index inside a problem
+    int pi = 0;
+    {
+      int lo = 0, hi = nprob - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (probs[mid].item_begin <= item) lo = mid; else hi = mid - 1;
+      }
+      pi = lo;
+    }
+    const DevProblem& P = probs[pi];
+    const long long li = item - P.item_begin;
+    const int tile_i = (int)(li % P.ntiles);
+    const int s = (int)((li / P.ntiles) % P.S);
+    const int d = (int)(li / ((long long)P.ntiles * P.S));
+    const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, Mp = P.Mp, nc = P.nc;
+    const int lda = Mp + 4;
+    const int t0 = tile_i * BT;
+    const int nvalid = min(BT, T - t0);
+    const double* Xs = P.X + (size_t)s * P.xrows * Dx;
+    double* gXs = (MODE == MODE_COND || MODE == MODE_FORWARD) ? nullptr : P.gX + (size_t)s * (T + 1) * D;
+
+    Smem sm;
+    {
+      double* p = smem_raw;
+      sm.tile = p; p += (size_t)BT * lda;
+      sm.stage = p; p += 8 * 8 * 40;
+      sm.xs = p; p += ((BT + 1) * FFVD_XLD + 1) & ~1;
+      sm.xsc = p; p += (BT * FFVD_XLD + 1) & ~1;
+      sm.us = p; p += Mp;
+      sm.es = p; p += 64;
+      sm.rowpart = p; p += 2 * 8 * 64;
+      sm.part = p; p += 64 * 32;
+      sm.small = p; p += 64;
+      sm.red = p;
+    }
+    const int dh = d * P.hs;
+    const double v = exp(P.logv[dh]);
+    const double Q = (MODE == MODE_COND) ? 1.0 : exp(P.logQ[d]);
+    const double invQ = 1.0 / Q;
+
+    __syncthreads();   // previous item fully done with shared memory
+    // ---- P0: stage the x tile and per-d vectors
+    if (tid < 64) {
+      double il2 = 0.0, sil = 0.0;
+      if (KIND == 0 && tid < 32 && tid < Din) {
+        const double ll = P.logl[(size_t)dh * Din + tid];
+        il2 = exp(-2.0 * ll);
+        sil = exp(-ll);
+      }
+      if (tid < 32) { sm.small[tid] = il2; sm.small[32 + tid] = sil; }
+      if (tid < 40) sm.red[tid] = 0.0;
+    }
+    for (int idx = tid; idx < (BT + 1) * FFVD_XCOLS; idx += FFVD_NTHREADS) {
+      const int r = idx >> 5, c = idx & 31;
+      const int t = t0 + r;
+      double val = 0.0;
+      if (t < P.xrows) {
+        if (c < Dx) val = Xs[(size_t)t * Dx + c];
+        else if (c < Din) val = (t < T) ? P.ctrl[(size_t)t * nc + (c - Dx)] : 0.0;
+      }
+      if (c == Din) val = (r < nvalid) ? 1.0 : 0.0;
+      if (r > nvalid && c < Din) val = 0.0;   // keep padded rows inert (row nvalid is x_{t+1} of the last valid row)
+      sm.xs[r * FFVD_XLD + c] = val;
+    }
+    for (int j = tid; j < Mp; j += FFVD_NTHREADS) {
+      double u = 0.0;
+      if (j < M) {
+        if (MODE == MODE_UNCOLLAPSED || MODE == MODE_FORWARD || MODE == MODE_COND) u = P.U[(size_t)j * D + d];
+        else if (MODE == MODE_COLLAPSED_P2) u = P.wvec[((size_t)s * D + d) * Mp + j];
+      }
+      sm.us[j] = u;
+    }
+    __syncthreads();
+    if (KIND == 0) {
+      for (int idx = tid; idx < BT * FFVD_XCOLS; idx += FFVD_NTHREADS) {
+        const int r = idx >> 5, c = idx & 31;
+        sm.xsc[r * FFVD_XLD + c] = (c < Din) ? sm.xs[r * FFVD_XLD + c] * sm.small[32 + c] : 0.0;
+      }
+      __syncthreads();
+    }
+
+    // ---- P1: K tile -> shared
+    {
+#pragma unroll
+      for (int ng = 0; ng < NGW; ++ng) {
+        double kv[RB][4];
+        const int jb = 16 * group_index(warp, ng) + 4 * q;
+        compute_k_group<KIND, RB>(kv, sm, P.ZT, Mp, Din, v, jb, g, M, nvalid);
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          double* p = sm.tile + (8 * rb + g) * lda + jb;
+          *reinterpret_cast<double2*>(p) = make_double2(kv[rb][0], kv[rb][1]);
+          *reinterpret_cast<double2*>(p + 2) = make_double2(kv[rb][2], kv[rb][3]);
+        }
+      }
+    }
+    __syncthreads();
+
+    const double* LinvT = P.LinvT + (size_t)dh * Mp * Mp;
+    const double* Linv = P.Linv + (size_t)dh * Mp * Mp;
+    double acc[NGW][RB][4];
+
+    if (MODE != MODE_COLLAPSED_P2) {
+      // ---- P2: A = K L^{-T}   (rows a_t = L^{-1} k_t)
+      tile_gemm<RB, NGW, +1>(acc, sm.tile, lda, LinvT, Mp, warp, g, q,
+                             [](double x, int, int) { return x; });
+      // row partial sums: a.u and a.a
+      {
+        double su[RB], sa[RB];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) su[rb] = sa[rb] = 0.0;
+#pragma unroll
+        for (int ng = 0; ng < NGW; ++ng) {
+          const int jb = 16 * group_index(warp, ng) + 4 * q;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double u = sm.us[jb + c];
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+              su[rb] = fma(acc[ng][rb][c], u, su[rb]);
+              sa[rb] = fma(acc[ng][rb][c], acc[ng][rb][c], sa[rb]);
+            }
+          }
+        }
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          su[rb] += __shfl_xor_sync(0xffffffffu, su[rb], 1);
+          su[rb] += __shfl_xor_sync(0xffffffffu, su[rb], 2);
+          sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 1);
+          sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 2);
+          if (q == 0) {
+            sm.rowpart[(0 * 8 + warp) * 64 + 8 * rb + g] = su[rb];
+            sm.rowpart[(1 * 8 + warp) * 64 + 8 * rb + g] = sa[rb];
+          }
+        }
+      }
+      __syncthreads();          // everyone is done reading K from the tile
+      if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RB, NGW>(acc, sm.tile, lda, warp, g, q);
+      // ---- per-row statistics (threads 0..BT-1)
+      if (tid < 64) {
+        double jxq = 0.0, jtr = 0.0, gq = 0.0, gvd = 0.0;
+        if (tid < BT) {
+          const int r = tid;
+          double e = 0.0;
+          if (r < nvalid) {
+            double su = 0.0, sa = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              su += sm.rowpart[(0 * 8 + w) * 64 + r];
+              sa += sm.rowpart[(1 * 8 + w) * 64 + r];
+            }
+            const double xd = sm.xs[r * FFVD_XLD + d], xn = sm.xs[(r + 1) * FFVD_XLD + d];
+            double kdiag = v;
+            if (KIND == 1) {
+              double ss = 0.0;
+              for (int c = 0; c < Din; ++c) ss = fma(sm.xs[r * FFVD_XLD + c], sm.xs[r * FFVD_XLD + c], ss);
+              kdiag = v * ss;
+            }
+            const double sig2 = kdiag - sa;
+            if (MODE == MODE_COND) {
+              // conditionals_multi_output.py:41,48 : fvar = Knn - sum A^2 ; fmean = A^T f
+              P.cond_mean[(size_t)(t0 + r) * D + d] = su;
+              P.cond_var[(size_t)(t0 + r) * D + d] = sig2;
+            } else if (MODE == MODE_COLLAPSED_P1) {
+              const double delta = xn - xd;
+              e = delta;                                   // b += F^T delta
+              jxq = -0.5 * delta * delta * invQ - 0.5 * log(Q);
+              jtr = -0.5 * sig2 * invQ;
+              gq = 0.5 * sig2 * invQ + 0.5 * delta * delta * invQ - 0.5;   // explicit part of dJ/dlogQ
+            } else {
+              const double res = xn - (xd + su);
+              e = res * invQ;
+              jxq = -0.5 * res * res * invQ - 0.5 * log(Q);
+              jtr = -0.5 * sig2 * invQ;
+              gq = 0.5 * res * res * invQ - 0.5 + 0.5 * sig2 * invQ;
+              if (MODE == MODE_UNCOLLAPSED) {
+                atomicAdd(gXs + (size_t)(t0 + r) * D + d, e);
+                atomicAdd(gXs + (size_t)(t0 + r + 1) * D + d, -e);
+              }
+            }
+            gvd = -0.5 * kdiag * invQ;
+            if (KIND == 1 && MODE == MODE_UNCOLLAPSED) {
+              for (int c = 0; c < D; ++c) atomicAdd(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
+            }
+          }
+          sm.es[r] = e;
+        }
+        jxq = warp_sum(jxq); jtr = warp_sum(jtr); gq = warp_sum(gq); gvd = warp_sum(gvd);
+        if (lane == 0) {
+          atomicAdd(sm.red + 0, jxq);
+          atomicAdd(sm.red + 1, jtr);
+          atomicAdd(sm.red + 2, gq);
+          atomicAdd(sm.red + 3, gvd);
+        }
+      }
+      // ---- emission term, once per (s, tile): dgp_model.py:248-250,264
+      if (d == 0 && MODE != MODE_COLLAPSED_P2 && MODE != MODE_COND && warp >= 2 && warp < 2 + (BT + 31) / 32) {
+        const int r = (warp - 2) * 32 + lane;
+        const int Dy = P.Dy;
+        double ll = 0.0;
+        for (int y = 0; y < Dy; ++y) {
+          const double Ry = exp(P.logR[y]);
+          double dy = 0.0, rr = 0.0;
+          if (r < nvalid) {
+            double yhat = P.dvec[y];
+            for (int c = 0; c < D; ++c) yhat = fma(sm.xs[(r + 1) * FFVD_XLD + c], P.C[(size_t)c * Dy + y], yhat);
+            const double res = (P.Y[(size_t)(t0 + r) * Dy + y] - yhat) / Ry;
+            ll += -0.5 * res * res - P.logR[y];
+            dy = res / Ry;
+            rr = res * res - 1.0;
+            if (MODE != MODE_FORWARD)
+              for (int c = 0; c < D; ++c) atomicAdd(gXs + (size_t)(t0 + r + 1) * D + c, dy * P.C[(size_t)c * Dy + y]);
+          }
+          if (MODE != MODE_FORWARD) {
+            for (int c = 0; c < D; ++c) {
+              const double xc1 = (r < nvalid) ? sm.xs[(r + 1) * FFVD_XLD + c] : 0.0;
+              const double t = warp_sum(dy * xc1);
+              if (lane == 0) atomicAdd(P.gC + (size_t)c * Dy + y, t);
+            }
+            const double sd = warp_sum(dy), sr = warp_sum(rr);
+            if (lane == 0) { atomicAdd(P.gd + y, sd); atomicAdd(P.gR + y, sr); }
+          }
+        }
+        ll = warp_sum(ll);
+        if (lane == 0) atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS, ll);
+      }
+      __syncthreads();          // A tile + es[] visible
+    }
+
+    if (MODE == MODE_FORWARD || MODE == MODE_COND) {
+      // forward only: flush the scalar sums and move on
+      if (MODE == MODE_FORWARD && tid == 0) {
+        atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0]);
+        atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1]);
+      }
+      continue;
+    }
+
+    if (MODE == MODE_UNCOLLAPSED || MODE == MODE_COLLAPSED_P1) {
+      // ---- ubar_j = sum_r e_r a_rj  (collapsed pass 1: b_j = sum_r delta_r f_rj), from registers
+      {
+        double er[RB];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) er[rb] = sm.es[8 * rb + g];
+#pragma unroll
+        for (int ng = 0; ng < NGW; ++ng) {
+          const int jb = 16 * group_index(warp, ng) + 4 * q;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double t = 0.0;
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) t = fma(er[rb], acc[ng][rb][c], t);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            if (g == 0 && jb + c < M) atomicAdd(P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp + jb + c, t);
+          }
+        }
+      }
+      // ---- S += A^T A
+      double* Sd = P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp;
+      syrk_flush<RB>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
+    }
+
+    if (MODE == MODE_UNCOLLAPSED) {
+      // ---- P4: Kbar = Abar L^{-1},  abar_rj = e_r u_j + a_rj / Q  formed on the fly
+      double er[RB];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) er[rb] = sm.es[8 * rb + g];
+      const double* us = sm.us;
+      tile_gemm<RB, NGW, -1>(acc, sm.tile, lda, Linv, Mp, warp, g, q,
+                             [&](double x, int rb, int k) { return fma(er[rb], us[k], x * invQ); });
+    } else if (MODE == MODE_COLLAPSED_P2) {
+      // ---- Kbar = K N + delta w'^T ; also dbar_r = k_r . w'
+      tile_gemm<RB, NGW, 0>(acc, sm.tile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, warp, g, q,
+                            [](double x, int, int) { return x; });
+    }
+
+    if (MODE == MODE_UNCOLLAPSED || MODE == MODE_COLLAPSED_P2) {
+      if (MODE == MODE_COLLAPSED_P2) {
+        // delta_r and dbar_r = sum_j k_rj w'_j (from the K tile still in shared memory)
+        for (int r = warp; r < BT; r += FFVD_NWARPS) {
+          double t = 0.0;
+          for (int j = lane; j < Mp; j += 32) t = fma(sm.tile[r * lda + j], sm.us[j], t);
+          t = warp_sum(t);
+          if (lane == 0) {
+            double delta = 0.0;
+            if (r < nvalid) {
+              delta = sm.xs[(r + 1) * FFVD_XLD + d] - sm.xs[r * FFVD_XLD + d];
+              const double gx = t - delta * invQ;
+              atomicAdd(gXs + (size_t)(t0 + r + 1) * D + d, gx);
+              atomicAdd(gXs + (size_t)(t0 + r) * D + d, -gx);
+              if (KIND == 1)
+                for (int c = 0; c < D; ++c) atomicAdd(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
+            }
+            sm.es[r] = delta;
+          }
+        }
+        if (tid < 64) {
+          // Kdiag part of d/dlogv
+          double gvd = 0.0;
+          if (tid < nvalid) {
+            double kdiag = v;
+            if (KIND == 1) {
+              double ss = 0.0;
+              for (int c = 0; c < Din; ++c) ss = fma(sm.xs[tid * FFVD_XLD + c], sm.xs[tid * FFVD_XLD + c], ss);
+              kdiag = v * ss;
+            }
+            gvd = -0.5 * kdiag * invQ;
+          }
+          gvd = warp_sum(gvd);
+          if (lane == 0) atomicAdd(sm.red + 3, gvd);
+        }
+        __syncthreads();
+      }
+      // ---- P6: W = Kbar o K (SE) or Kbar (Linear) -> shared tile
+      {
+#pragma unroll
+        for (int ng = 0; ng < NGW; ++ng) {
+          const int jb = 16 * group_index(warp, ng) + 4 * q;
+          double kv[RB][4];
+          if (KIND == 0) {
+            if (MODE == MODE_COLLAPSED_P2) {
+#pragma unroll
+              for (int rb = 0; rb < RB; ++rb) {
+                const double* p = sm.tile + (8 * rb + g) * lda + jb;
+                const double2 k01 = *reinterpret_cast<const double2*>(p);
+                const double2 k23 = *reinterpret_cast<const double2*>(p + 2);
+                kv[rb][0] = k01.x; kv[rb][1] = k01.y; kv[rb][2] = k23.x; kv[rb][3] = k23.y;
+              }
+            } else {
+              compute_k_group<KIND, RB>(kv, sm, P.ZT, Mp, Din, v, jb, g, M, nvalid);
+            }
+          }
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              double kb = acc[ng][rb][c];
+              if (MODE == MODE_COLLAPSED_P2) kb = fma(sm.es[8 * rb + g], sm.us[jb + c], kb);
+              acc[ng][rb][c] = (KIND == 0) ? kb * kv[rb][c] : ((jb + c < M && 8 * rb + g < nvalid) ? kb : 0.0);
+            }
+        }
+        __syncthreads();        // all warps done reading A (GEMM2 / SYRK) or K (pass 2)
+        store_tile<RB, NGW>(acc, sm.tile, lda, warp, g, q);
+      }
+      __syncthreads();
+      contract_W<KIND, RB>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid);
+    }
+
+    // ---- flush block-level scalars
+    __syncthreads();
+    if (tid < 32) {
+      if (tid == 0) {
+        if (MODE != MODE_COLLAPSED_P2) {
+          atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0]);
+          atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1]);
+          atomicAdd(P.gQ + d, sm.red[2]);
+        }
+        if (MODE != MODE_COLLAPSED_P1) atomicAdd(P.gv + d, sm.red[3] + sm.red[7]);
+      }
+      if (KIND == 0 && MODE != MODE_COLLAPSED_P1 && tid < Din) atomicAdd(P.gl + (size_t)d * Din + tid, sm.red[8 + tid]);
+    }
+  }
+}
+
+}  // namespace ffvd

@@ -1,0 +1,458 @@
+// Once-per-evaluation kernels around the fused tile kernel (sm_100a):
+//   kzz_prep      K(Z,Z)+jitter I -> Cholesky -> L^{-1}, L^{-T}   (conditionals_multi_output.py:124-169)
+//   bgemm_nn      batched FP64 DMMA GEMM for the O(M^3) products of the Cholesky backward
+//   symmetrize / wz / kzz_bwd / finalize   hand-derived backward through chol(Kzz) and the priors
+//   collapsed_solve  H = F^T F / Q + I, logdet, c = H^{-1} b   (conditionals_multi_output.py:246-254)
+#pragma once
+#include "ffvd_common.cuh"
+
+namespace ffvd {
+
+// ---------------------------------------------------------------------------------------------
+// device helpers operating on a generic-address matrix (shared or global)
+// In-place lower Cholesky of the leading M x M block of A (ld = lda); colbuf: M doubles of smem.
+// Returns 0 or the 1-based index of the first non-positive pivot (uniform across the block).
+__device__ int chol_inplace(double* A, int lda, int M, double* colbuf, int* flag) {
+  const int tid = threadIdx.x, nth = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+  if (tid == 0) *flag = 0;
+  for (int j = 0; j < M; ++j) {
+    __syncthreads();
+    const double piv = A[(size_t)j * lda + j];
+    if (!(piv > 0.0)) {
+      if (tid == 0) *flag = j + 1;
+      break;
+    }
+    const double ljj = sqrt(piv);
+    const double inv = 1.0 / ljj;
+    for (int i = j + 1 + tid; i < M; i += nth) {
+      const double x = A[(size_t)i * lda + j] * inv;
+      A[(size_t)i * lda + j] = x;
+      colbuf[i] = x;
+    }
+    __syncthreads();
+    if (tid == 0) A[(size_t)j * lda + j] = ljj;
+    for (int i = j + 1 + warp; i < M; i += nw) {
+      const double aij = colbuf[i];
+      double* row = A + (size_t)i * lda;
+      for (int k = j + 1 + lane; k <= i; k += 32) row[k] = fma(-aij, colbuf[k], row[k]);
+    }
+  }
+  __syncthreads();
+  return *flag;
+}
+
+// X = L^{-1} (lower) by forward substitution, one column per thread; also XT = X^T.
+// L is M x M lower (ld = ldl); X, XT are Mp x Mp row-major global buffers whose padding is
+// already zero.  rowbuf: M doubles of shared memory.
+__device__ void tri_inverse(const double* L, int ldl, int M, double* X, double* XT, int Mp, double* rowbuf) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int i = 0; i < M; ++i) {
+    __syncthreads();
+    for (int k = tid; k <= i; k += nth) rowbuf[k] = L[(size_t)i * ldl + k];
+    __syncthreads();
+    const double dinv = 1.0 / rowbuf[i];
+    for (int j = tid; j <= i; j += nth) {
+      double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = j;
+      for (; k + 3 < i; k += 4) {
+        s0 = fma(-rowbuf[k], X[(size_t)k * Mp + j], s0);
+        s1 = fma(-rowbuf[k + 1], X[(size_t)(k + 1) * Mp + j], s1);
+        s2 = fma(-rowbuf[k + 2], X[(size_t)(k + 2) * Mp + j], s2);
+        s3 = fma(-rowbuf[k + 3], X[(size_t)(k + 3) * Mp + j], s3);
+      }
+      for (; k < i; ++k) s0 = fma(-rowbuf[k], X[(size_t)k * Mp + j], s0);
+      X[(size_t)i * Mp + j] = ((s0 + s1) + (s2 + s3)) * dinv;
+    }
+  }
+  __syncthreads();
+  // transpose (XT may alias the buffer that held L: every entry of the M x M block is rewritten)
+  for (int idx = tid; idx < M * M; idx += nth) {
+    const int r = idx / M, c = idx % M;
+    XT[(size_t)r * Mp + c] = (c >= r) ? X[(size_t)c * Mp + r] : 0.0;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid (D, nprob); block 512.  Dynamic smem: 2*Mp doubles (+ M*(M+1) when use_smem).
+template <int KIND>
+__global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restrict__ probs, double jitter, int use_smem) {
+  extern __shared__ __align__(16) double sh[];
+  __shared__ int flag;
+  const DevProblem& P = probs[blockIdx.y];
+  const int d = blockIdx.x, M = P.M, Mp = P.Mp, Din = P.Din;   // d indexes kernels (grid.x = D*hs or 1)
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double* colbuf = sh;
+  double* rowbuf = sh + Mp;
+  double* Asm = sh + 2 * Mp;
+  if (d == 0) {
+    for (int idx = tid; idx < Din * Mp; idx += nth) {
+      const int jd = idx / Mp, m = idx % Mp;
+      P.ZT[idx] = (m < M) ? P.Z[(size_t)m * Din + jd] : 0.0;
+    }
+  }
+  double* Lt = P.LinvT + (size_t)d * Mp * Mp;   // global scratch for L when it does not fit in smem
+  double* A = use_smem ? Asm : Lt;
+  const int lda = use_smem ? (M + 1) : Mp;
+  const double v = exp(P.logv[d]);
+  // K(Z,Z) + jitter I, lower triangle.  kernels_multi_output.py:202-214 / kernels.py:270-276
+  for (int idx = tid; idx < M * M; idx += nth) {
+    const int m = idx / M, n = idx % M;
+    if (n > m) continue;
+    double s = 0.0;
+    for (int jd = 0; jd < Din; ++jd) {
+      const double a = P.Z[(size_t)m * Din + jd], b = P.Z[(size_t)n * Din + jd];
+      if (KIND == 0) {
+        const double il = exp(-P.logl[(size_t)d * Din + jd]);
+        const double t = a * il - b * il;
+        s = fma(t, t, s);
+      } else {
+        s = fma(a, b, s);
+      }
+    }
+    double k = (KIND == 0) ? v * exp(-0.5 * s) : v * s;
+    if (m == n) k += jitter;
+    A[(size_t)m * lda + n] = k;
+  }
+  __syncthreads();
+  const int st = chol_inplace(A, lda, M, colbuf, &flag);
+  if (tid == 0) P.status[d] = st;
+  if (st != 0) return;
+  tri_inverse(A, lda, M, P.Linv + (size_t)d * Mp * Mp, Lt, Mp, rowbuf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C[b] = alpha * A[b] * B[b]  (all n x n row-major, ld = n, n multiple of 64), FP64 DMMA.
+// grid (n/64, n/64, batch); block 256.  Batch strides in elements (0 = shared operand).
+struct BatchMap { int div, mul, mod; };   // matrix index = (z / div) * mul + (z % mod)
+__device__ __forceinline__ size_t bmap(const BatchMap& m, int z) { return (size_t)(z / m.div) * m.mul + (z % m.mod); }
+
+__global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, const double* __restrict__ A,
+                                                        const double* __restrict__ B, int n, double alpha,
+                                                        BatchMap mC, BatchMap mA, BatchMap mB) {
+  __shared__ __align__(16) double As[64][20];
+  __shared__ __align__(16) double Bs[16][68];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps: each 32 x 16
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  A += bmap(mA, blockIdx.z) * n * n; B += bmap(mB, blockIdx.z) * n * n; C += bmap(mC, blockIdx.z) * n * n;
+  double c[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 16) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * 16; idx += 256) {
+      const int r = idx >> 4, cc = idx & 15;
+      As[r][cc] = A[(size_t)(m0 + r) * n + k0 + cc];
+    }
+    for (int idx = tid; idx < 16 * 64; idx += 256) {
+      const int r = idx >> 6, cc = idx & 63;
+      Bs[r][cc] = B[(size_t)(k0 + r) * n + n0 + cc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[wm * 32 + 8 * i + g][kk + q];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = Bs[kk + q][wn * 16 + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double* p = C + (size_t)(m0 + wm * 32 + 8 * i + g) * n + n0 + wn * 16 + 8 * j + 2 * q;
+      *reinterpret_cast<double2*>(p) = make_double2(alpha * c[i][j][0], alpha * c[i][j][1]);
+    }
+}
+
+// Sacc[b] <- symmetric matrix built from the lower triangle of
+//   mode 0 (uncollapsed G):   Sacc[b]/Q_d + U[:,d] (x) ubar[d]
+//   mode 1 (collapsed):       Sacc[b]                         (S itself)
+//   mode 2 (collapsed G):     HxT[b] + c[b] (x) b[b]/Q_d       (HxT holds Mat' S)
+// grid (ceil(M*M/256), nb, nprob).
+__global__ void symmetrize_lower_kernel(const DevProblem* __restrict__ probs, int mode) {
+  const DevProblem& P = probs[blockIdx.z];
+  const int b = blockIdx.y, d = b % P.D, M = P.M, Mp = P.Mp;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * M) return;
+  const int m = (int)(idx / M), n = (int)(idx % M);
+  if (n > m) return;
+  const size_t off = (size_t)b * Mp * Mp;
+  double val;
+  if (mode == 0) {
+    val = P.Sacc[off + (size_t)m * Mp + n] * exp(-P.logQ[d]) + P.U[(size_t)m * P.D + d] * P.ubar[(size_t)b * Mp + n];
+  } else if (mode == 1) {
+    val = P.Sacc[off + (size_t)m * Mp + n];
+  } else {
+    val = P.HxT[off + (size_t)m * Mp + n] + P.cvec[(size_t)b * Mp + m] * P.ubar[(size_t)b * Mp + n] * exp(-P.logQ[d]);
+  }
+  P.Sacc[off + (size_t)m * Mp + n] = val;
+  P.Sacc[off + (size_t)n * Mp + m] = val;
+}
+
+// Wz = Kbar_zz o Kzz (SE, in place) and row sums rs[b][m]; Linear: rs unused, Wz = Kbar_zz.
+// grid (ceil(M/8), batch); block 256 (warp per row).
+template <int KIND>
+__global__ void __launch_bounds__(256) wz_kernel(const DevProblem* __restrict__ probs) {
+  // blockIdx.z = problem ; blockIdx.y = local batch (d or s*D+d)
+  const DevProblem& P = probs[blockIdx.z];
+  const int b = blockIdx.y, d = b % P.D;
+  const int M = P.M, Mp = P.Mp, Din = P.Din;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  double* Kb = P.Sacc + (size_t)b * Mp * Mp + (size_t)m * Mp;
+  double rs = 0.0;
+  if (KIND == 0) {
+    const double v = exp(P.logv[d]);
+    for (int n = lane; n < M; n += 32) {
+      double s = 0.0;
+      for (int jd = 0; jd < Din; ++jd) {
+        const double il = exp(-P.logl[(size_t)d * Din + jd]);
+        const double t = P.Z[(size_t)m * Din + jd] * il - P.Z[(size_t)n * Din + jd] * il;
+        s = fma(t, t, s);
+      }
+      const double wz = Kb[n] * v * exp(-0.5 * s);
+      Kb[n] = wz;
+      rs += wz;
+    }
+    rs = warp_sum(rs);
+  }
+  if (lane == 0) P.rs[(size_t)b * Mp + m] = rs;
+}
+
+// dJ/dZ, dJ/dlogl, dJ/dlogv contributions of Kbar_zz.  grid (ceil(M/8), batch, nprob); block (32, 8).
+template <int KIND>
+__global__ void __launch_bounds__(256) kzz_bwd_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.z];
+  const int b = blockIdx.y, d = b % P.D;
+  const int M = P.M, Mp = P.Mp, Din = P.Din;
+  const int jd = threadIdx.x & 31, mi = threadIdx.x >> 5;
+  const int m = blockIdx.x * 8 + mi;
+  double lpart = 0.0, vpart = 0.0;
+  if (m < M && jd < Din) {
+    const double* Wz = P.Sacc + (size_t)b * Mp * Mp + (size_t)m * Mp;
+    double s0 = 0.0, s1 = 0.0;
+    int n = 0;
+    for (; n + 1 < M; n += 2) {
+      s0 = fma(Wz[n], P.Z[(size_t)n * Din + jd], s0);
+      s1 = fma(Wz[n + 1], P.Z[(size_t)(n + 1) * Din + jd], s1);
+    }
+    if (n < M) s0 = fma(Wz[n], P.Z[(size_t)n * Din + jd], s0);
+    const double wzz = s0 + s1;
+    const double z = P.Z[(size_t)m * Din + jd];
+    double zb;
+    if (KIND == 0) {
+      const double il2 = exp(-2.0 * P.logl[(size_t)d * Din + jd]);
+      const double rs = P.rs[(size_t)b * Mp + m];
+      zb = -2.0 * il2 * (z * rs - wzz);
+      lpart = -z * zb;
+      if (jd == 0) vpart = rs;
+    } else {
+      zb = 2.0 * exp(P.logv[d]) * wzz;
+      vpart = 0.5 * z * zb;
+    }
+    atomicAdd(P.gZ + (size_t)m * Din + jd, zb);
+  }
+  if (KIND == 0) {
+    // reduce lpart over the 8 rows of the block through shared memory, one atomic per jd
+    __shared__ double lsm[8][32];
+    lsm[mi][jd] = lpart;
+    __syncthreads();
+    if (mi == 0 && jd < Din) {
+      double t = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += lsm[r][jd];
+      atomicAdd(P.gl + (size_t)d * Din + jd, t);
+    }
+  }
+  vpart = warp_sum(vpart);
+  if (jd == 0 && vpart != 0.0) atomicAdd(P.gv + d, vpart);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Collapsed bound, per (problem, s, d): H = S/Q + I  -> chol -> logdet, H^{-1}, c = H^{-1} b/Q,
+// quad = 1/2 b^T c /Q..., w' = L^{-T} c / Q, implicit dJ/dlogQ.   conditionals_multi_output.py:246-254
+// grid (S*D, nprob); block 512; dynamic smem 2*Mp doubles.
+// Buffers: Sacc[b] holds the full symmetric S (already symmetrized); Wk[b] <- H then L_H;
+//          Hx[b] <- L_H^{-1}; HxT[b] <- L_H^{-T}.
+__global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* __restrict__ probs) {
+  extern __shared__ __align__(16) double sh[];
+  __shared__ int flag;
+  const DevProblem& P = probs[blockIdx.y];
+  const int b = blockIdx.x, d = b % P.D, s = b / P.D;
+  const int M = P.M, Mp = P.Mp, tid = threadIdx.x, nth = blockDim.x;
+  const double iq = exp(-P.logQ[d]);
+  double* H = P.Wk + (size_t)b * Mp * Mp;
+  const double* S = P.Sacc + (size_t)b * Mp * Mp;
+  for (int idx = tid; idx < M * M; idx += nth) {
+    const int m = idx / M, n = idx % M;
+    H[(size_t)m * Mp + n] = S[(size_t)m * Mp + n] * iq + (m == n ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const int st = chol_inplace(H, Mp, M, sh, &flag);
+  if (st != 0) {
+    if (tid == 0) P.status[d] = st;
+    return;
+  }
+  // -1/2 logdet H = -sum log L_ii
+  if (tid < 32) {
+    double t = 0.0;
+    for (int i = tid; i < M; i += 32) t += log(H[(size_t)i * Mp + i]);
+    t = warp_sum(t);
+    if (tid == 0) atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -t);
+  }
+  double* X = P.Hx + (size_t)b * Mp * Mp;
+  double* XT = P.HxT + (size_t)b * Mp * Mp;
+  tri_inverse(H, Mp, M, X, XT, Mp, sh + Mp);
+}
+
+// After Hinv = L_H^{-T} L_H^{-1} is in Wk[b]:  c = Hinv b/Q ; w' = L^{-T} c / Q ; quad; dJ/dlogQ;
+// then Wk[b] <- Mat' = (I - Hinv - c c^T)/Q.     grid (S*D, nprob); block 256.
+__global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  const int b = blockIdx.x, d = b % P.D, s = b / P.D;
+  const int M = P.M, Mp = P.Mp, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double iq = exp(-P.logQ[d]);
+  double* Hinv = P.Wk + (size_t)b * Mp * Mp;
+  const double* bv = P.ubar + (size_t)b * Mp;      // unscaled F^T delta
+  double* c = P.cvec + (size_t)b * Mp;
+  double* w = P.wvec + (size_t)b * Mp;
+  const double* S = P.Sacc + (size_t)b * Mp * Mp;
+  __shared__ double red[4];
+  if (tid < 4) red[tid] = 0.0;
+  __syncthreads();
+  // c = Hinv (b/Q)
+  for (int m = warp; m < Mp; m += 8) {
+    double t = 0.0;
+    if (m < M)
+      for (int n = lane; n < M; n += 32) t = fma(Hinv[(size_t)m * Mp + n], bv[n] * iq, t);
+    t = warp_sum(t);
+    if (lane == 0) c[m] = t;
+  }
+  __syncthreads();
+  // quad = 1/2 b_s^T c ; c^T b_s ; trace Hinv ; c^T (H - I) c = c^T S c / Q
+  double qd = 0.0, tr = 0.0, csc = 0.0;
+  for (int m = tid; m < M; m += 256) {
+    qd = fma(bv[m] * iq, c[m], qd);
+    tr += Hinv[(size_t)m * Mp + m];
+  }
+  for (int m = warp; m < M; m += 8) {
+    double t = 0.0;
+    for (int n = lane; n < M; n += 32) t = fma(S[(size_t)m * Mp + n], c[n], t);
+    t = warp_sum(t);
+    if (lane == 0) csc = fma(c[m], t, csc);
+  }
+  qd = warp_sum(qd); tr = warp_sum(tr); csc = warp_sum(csc);
+  if (lane == 0) { atomicAdd(red + 0, qd); atomicAdd(red + 1, tr); atomicAdd(red + 2, csc); }
+  // w' = L^{-T} c / Q   (LinvT is upper: row m, columns n >= m)
+  const double* LT = P.LinvT + (size_t)d * Mp * Mp;
+  for (int m = warp; m < Mp; m += 8) {
+    double t = 0.0;
+    if (m < M)
+      for (int n = m + lane; n < M; n += 32) t = fma(LT[(size_t)m * Mp + n], c[n], t);
+    t = warp_sum(t);
+    if (lane == 0) w[m] = t * iq;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
+    atomicAdd(P.gQ + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
+  }
+  // Mat' in place
+  for (int idx = tid; idx < M * M; idx += 256) {
+    const int m = idx / M, n = idx % M;
+    Hinv[(size_t)m * Mp + n] = ((m == n ? 1.0 : 0.0) - Hinv[(size_t)m * Mp + n] - c[m] * c[n]) * iq;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct OutPtrs {
+  double *nll, *terms, *g_Z, *g_U, *g_logv, *g_logl, *g_logQ, *g_C, *g_d, *g_logR;
+};
+
+__device__ __forceinline__ double block_sum_sq(const double* x, int n, double shift, double* red) {
+  double t = 0.0;
+  if (x)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double y = x[i] - shift; t = fma(y, y, t); }
+  t = warp_sum(t);
+  __syncthreads();
+  if (threadIdx.x == 0) *red = 0.0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicAdd(red, t);
+  __syncthreads();
+  return *red;
+}
+
+// priors (dgp_model.py:105-143,252,326-334), -1/T scaling, term assembly (dgp_model.py:286-297).
+// grid (nprob); block 256.
+template <int KIND>
+__global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restrict__ probs, const OutPtrs* __restrict__ outs,
+                                                       int collapsed, int flags) {
+  __shared__ double red;
+  const DevProblem& P = probs[blockIdx.x];
+  const OutPtrs& O = outs[blockIdx.x];
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int M = P.M, Mp = P.Mp, D = P.D, Din = P.Din, Dy = P.Dy, S = P.S, T = P.T;
+  const double sc = -1.0 / (double)T;
+  const double npri = (flags & 2) ? 1.0 : (double)S;
+  const bool zprior = (flags & 1) != 0;
+  const double log005 = log(0.05);
+  const double pz = zprior ? -0.5 * block_sum_sq(P.Z, M * Din, 0.0, &red) : 0.0;
+  double ph = -0.5 * block_sum_sq(P.logv, D, log005, &red);
+  if (KIND == 0) ph += -0.5 * block_sum_sq(P.logl, D * Din, 0.0, &red);
+  const double pu = collapsed ? 0.0 : -0.5 * block_sum_sq(P.U, M * D, 0.0, &red);
+  const double hyp = -0.5 * (block_sum_sq(P.logQ, D, 0.0, &red) + block_sum_sq(P.C, D * Dy, 0.0, &red) +
+                             block_sum_sq(P.dvec, Dy, 0.0, &red) + block_sum_sq(P.logR, Dy * Dy, 0.0, &red));
+  for (int s = 0; s < S; ++s) {
+    const double px0 = -0.5 * block_sum_sq(P.X + (size_t)s * (T + 1) * D, D, 0.0, &red);
+    if (tid == 0) {
+      const double* r = P.terms_raw + (size_t)s * FFVD_NTERMS_RAW;
+      double t[6];
+      t[0] = sc * (pu + ph + pz + px0 + hyp);
+      t[1] = sc * r[FFVD_RAW_EMIS];
+      t[2] = sc * r[FFVD_RAW_XQ];
+      t[3] = sc * r[FFVD_RAW_TRACE];
+      t[4] = collapsed ? sc * r[FFVD_RAW_LOGDET] : 0.0;
+      t[5] = collapsed ? sc * r[FFVD_RAW_QUAD] : 0.0;
+      if (O.terms) for (int k = 0; k < 6; ++k) O.terms[(size_t)s * 6 + k] = t[k];
+      if (O.nll) O.nll[s] = ((t[0] + t[1]) + (t[2] + t[3])) + (t[4] + t[5]);
+    }
+  }
+  if (flags & 4) return;
+  if (O.g_Z) for (int i = tid; i < M * Din; i += nth) O.g_Z[i] = sc * (P.gZ[i] - (zprior ? npri * P.Z[i] : 0.0));
+  if (O.g_U) for (int i = tid; i < M * D; i += nth) {
+    const int m = i / D, d = i % D;
+    O.g_U[i] = collapsed ? 0.0 : sc * (P.ubar[(size_t)d * Mp + m] - npri * P.U[i]);
+  }
+  if (O.g_logv) for (int i = tid; i < D; i += nth) O.g_logv[i] = sc * (P.gv[i] - npri * (P.logv[i] - log005));
+  if (KIND == 0 && O.g_logl) for (int i = tid; i < D * Din; i += nth) O.g_logl[i] = sc * (P.gl[i] - npri * P.logl[i]);
+  if (O.g_logQ) for (int i = tid; i < D; i += nth) O.g_logQ[i] = sc * (P.gQ[i] - npri * P.logQ[i]);
+  if (O.g_C) for (int i = tid; i < D * Dy; i += nth) O.g_C[i] = sc * (P.gC[i] - npri * P.C[i]);
+  if (O.g_d) for (int i = tid; i < Dy; i += nth) O.g_d[i] = sc * (P.gd[i] - npri * P.dvec[i]);
+  if (O.g_logR) for (int i = tid; i < Dy * Dy; i += nth) O.g_logR[i] = sc * ((i < Dy ? P.gR[i] : 0.0) - npri * P.logR[i]);
+}
+
+// g_X = -(raw - [t==0] X_0)/T, in place.   grid (blocks, nprob)
+__global__ void scale_gx_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  const size_t per = (size_t)(P.T + 1) * P.D, n = per * P.S;
+  const double sc = -1.0 / (double)P.T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i % per;
+    double v = P.gX[i];
+    if (r < (size_t)P.D) v -= P.X[i];
+    P.gX[i] = sc * v;
+  }
+}
+
+}  // namespace ffvd

@@ -1,0 +1,142 @@
+/*
+ * ffvd_b200.h -- C ABI of libffvd_b200.so: the B200 (sm_100a) implementation of FFVD's
+ * per-iteration GPSSM log-joint + gradient evaluation and SG-HMC update.
+ *
+ * The reference (xuhuifan/FFVD) has no FFI: its hot path is a Python operator API on top of
+ * the TensorFlow runtime.  Each entry point below replaces the TF sub-graph that the cited
+ * reference function builds; the Python package `ffvd_b200` (same module / function names as
+ * `vfegpssm`) binds them with ctypes.  INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 ok; <0 error (see FFVD_E_*); >0 = 1-based index
+ *     of the failing Cholesky pivot (which matrix failed is in ffvd_last_error()).
+ *   - tensors cross the ABI as DLPack `DLManagedTensor*` (borrowed for the duration of the
+ *     call; the library never calls the deleter).  float64, C-contiguous, byte_offset honoured.
+ *     kDLCUDA tensors are used in place; kDLCPU / kDLCUDAHost tensors are staged with an
+ *     explicit cudaMemcpy in and out (a transfer, never CPU compute -- there is no CPU path).
+ *   - outputs are caller-allocated tensors.  NULL output pointers are skipped.
+ *   - work is enqueued on the context's stream; calls that return host scalars or touch host
+ *     tensors synchronise that stream before returning, pure-device calls do not.
+ */
+#ifndef FFVD_B200_H_
+#define FFVD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- minimal DLPack (v0.x "dltensor" capsule ABI) ------------------------------------- */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3, kDLCUDAManaged = 13 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;   /* code 2 = float */
+typedef struct {
+  void* data; DLDevice device; int32_t ndim; DLDataType dtype;
+  int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+  DLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct DLManagedTensor* self);
+} DLManagedTensor;
+#endif
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define FFVD_OK               0
+#define FFVD_E_BADARG        -1   /* null pointer, bad flag                                 */
+#define FFVD_E_DTYPE         -2   /* not float64                                            */
+#define FFVD_E_SHAPE         -3   /* rank / extent mismatch, or not C-contiguous            */
+#define FFVD_E_DEVICE        -4   /* tensor lives on another GPU than the context           */
+#define FFVD_E_CUDA          -5   /* CUDA runtime error (message in ffvd_last_error)        */
+#define FFVD_E_UNSUPPORTED   -6   /* valid reference option that this build does not cover  */
+#define FFVD_E_LIMIT         -7   /* size beyond this build's limits (M > 2048, Din > 31)   */
+
+#define FFVD_KERNEL_SE      0     /* kernels_multi_output.py:240-247 SquaredExponential (ARD) */
+#define FFVD_KERNEL_LINEAR  1     /* kernels.py:250-281 LinearK (scalar variance)              */
+
+/* flags for ffvd_nll_grads_* */
+#define FFVD_FLAG_PRIOR_Z_NORMAL  1   /* dgp_model.py:108-109 (prior_type="normal", the CLI default) */
+#define FFVD_FLAG_PRIOR_ONCE      2   /* count shared-parameter priors once instead of S times  */
+#define FFVD_FLAG_NO_GRADS        4   /* forward only: nll + terms                               */
+#define FFVD_FLAG_ASYNC           8   /* do not synchronise to read back the Cholesky status     */
+
+typedef struct ffvd_ctx ffvd_ctx;
+
+/* One GPSSM problem (SURVEY section 8 batch-axis contract).  Shapes:
+ *   X (S,T+1,D) or (T+1,D); Z (M,Din); U (M,D); logv (D); logl (D,Din) [SE only, else NULL];
+ *   logQ (D); C (D,Dy); d (Dy); logR (Dy,Dy); Y (T,Dy); ctrl (T,Din-D) [NULL if Din==D].
+ * Replaces the tf.Variables of dgp_model.py:56-69,176-185 and likelihoods.py:12-24,45-55. */
+typedef struct {
+  DLManagedTensor *X, *Z, *U, *logv, *logl, *logQ, *C, *d, *logR, *Y, *ctrl;
+} ffvd_problem;
+
+/* Outputs of one nll+gradient evaluation; any pointer may be NULL.
+ *   nll (S) [or () for 2-d X]; terms (S,6) = {prior, loglik, xq, trace, term1, term2}
+ *   (dgp_model.py:286-297: nll = sum of the six); g_* = d nll / d *, same shape as the
+ *   parameter; g_X per sample, all others summed over the S samples. */
+typedef struct {
+  DLManagedTensor *nll, *terms, *g_X, *g_Z, *g_U, *g_logv, *g_logl, *g_logQ, *g_C, *g_d, *g_logR;
+} ffvd_outputs;
+
+int  ffvd_version(void);
+const char* ffvd_status_string(int status);
+const char* ffvd_last_error(void);
+
+/* stream: a cudaStream_t (as void*) or NULL for a stream owned by the context. */
+int ffvd_ctx_create(int device, void* stream, ffvd_ctx** out);
+int ffvd_ctx_destroy(ffvd_ctx* ctx);
+int ffvd_ctx_synchronize(ffvd_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t ffvd_ctx_launch_count(ffvd_ctx* ctx);
+
+/* kernels_multi_output.py:202-214,246-247 / kernels.py:270-276  K(X, X2) -> out (N,N2).
+ * X2 may be NULL (K(X,X)).  logv: () ; logl: (Din) for SE, NULL for Linear. */
+int ffvd_kernel_K(ffvd_ctx*, int kind, DLManagedTensor* X, DLManagedTensor* X2,
+                  DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* out);
+/* kernels_multi_output.py:199-200 / kernels.py:278-281  Kdiag(X) -> out (N). */
+int ffvd_kernel_Kdiag(ffvd_ctx*, int kind, DLManagedTensor* X, DLManagedTensor* logv,
+                      DLManagedTensor* logl, DLManagedTensor* out);
+
+/* conditionals_multi_output.py:124-169 kernel_pre_cal: per output dim d,
+ * LinvT_out[d] = chol(K_d(Z) + jitter I)^{-T}  (D,M,M).  logv (D), logl (D,Din). */
+int ffvd_kernel_pre_cal(ffvd_ctx*, int kind, DLManagedTensor* Z, DLManagedTensor* logv,
+                        DLManagedTensor* logl, double jitter, DLManagedTensor* LinvT_out);
+
+/* conditionals_multi_output.py:73-120 (list of D kernels, f (M,D)) and, with
+ * shared_kernel=1, conditionals.py:69-107 (one kernel for all R columns of f; logv (), logl (Din)).
+ * mean_out, var_out (N,R).  Supported: full_cov=0, q_sqrt=NULL, white in {0,1}. */
+int ffvd_conditional(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                     DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f,
+                     DLManagedTensor* q_sqrt, int white, int full_cov, double jitter,
+                     DLManagedTensor* mean_out, DLManagedTensor* var_out);
+
+/* likelihoods.py:96-111 (vec=1 -> out (N)) and :89-93 (vec=0 -> out (N,Dy)); no -0.5 log 2pi. */
+int ffvd_logdensity_norm_diag(ffvd_ctx*, DLManagedTensor* y, DLManagedTensor* ymean,
+                              DLManagedTensor* Rchols, int vec, DLManagedTensor* out);
+
+/* dgp_model.py:248-297 + tf.gradients (base_model.py:148): uncollapsed q(u) (cases 1,2,3,6,7;
+ * regularizer :337-359) and collapsed-u bound (cases 4,5; conditionals_multi_output.py:230-257). */
+int ffvd_nll_grads_uncollapsed(ffvd_ctx*, int kind, const ffvd_problem* p, int flags, double jitter,
+                               const ffvd_outputs* o);
+int ffvd_nll_grads_collapsed(ffvd_ctx*, int kind, const ffvd_problem* p, int flags, double jitter,
+                             const ffvd_outputs* o);
+/* B independent problems (own Z,U,hypers,Y,T; equal M,D,Din,Dy) in one launch sequence --
+ * BASELINE config 4 (many small chains). */
+int ffvd_nll_grads_batched(ffvd_ctx*, int kind, int collapsed, int nprob, const ffvd_problem* p,
+                           int flags, double jitter, const ffvd_outputs* o);
+
+/* base_model.py:143-179 generate_update_step: one adaptive SG-HMC update, in place, Jacobi
+ * semantics.  All tensors same shape.  noise ~ N(0,1) supplied by the caller (base_model.py:171).
+ * burn_in=1 also updates xi,g,g2 (burn_in_op :179); burn_in=0 is sample_op (:178). */
+int ffvd_sghmc_update(ffvd_ctx*, DLManagedTensor* theta, DLManagedTensor* grad, DLManagedTensor* noise,
+                      DLManagedTensor* xi, DLManagedTensor* g, DLManagedTensor* g2, DLManagedTensor* p,
+                      double epsilon, double mdecay, double X_N, int burn_in);
+
+/* dgp_model.py:303-305 tf.compat.v1.train.AdamOptimizer apply (step is 1-based). */
+int ffvd_adam_update(ffvd_ctx*, DLManagedTensor* theta, DLManagedTensor* grad, DLManagedTensor* m,
+                     DLManagedTensor* v, double lr, double beta1, double beta2, double eps, int64_t step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFVD_B200_H_ */
