@@ -69,6 +69,8 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_ctx_synchronize.argtypes = [vp]
     lib.ffvd_ctx_launch_count.argtypes = [vp]
     lib.ffvd_ctx_launch_count.restype = cll
+    lib.ffvd_ctx_fused_time.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(cll)]
+    lib.ffvd_ctx_fused_time.restype = ci
     lib.ffvd_kernel_K.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     lib.ffvd_kernel_Kdiag.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.ffvd_kernel_pre_cal.argtypes = [vp, ci, vp, vp, vp, cd, vp]
@@ -132,7 +134,10 @@ class Context:
     def __init__(self, device: int = 0, stream: Optional[int] = None):
         self._lib = load_library()
         h = ctypes.c_void_p()
-        _check(self._lib.ffvd_ctx_create(int(device), ctypes.c_void_p(stream) if stream else None, ctypes.byref(h)))
+        # a raw handle of 0 is CUDA's legacy default stream (torch's default): pass cudaStreamLegacy (0x1),
+        # because NULL means "create a stream owned by the context" in the C ABI
+        sarg = None if stream is None else ctypes.c_void_p(int(stream) if int(stream) != 0 else 1)
+        _check(self._lib.ffvd_ctx_create(int(device), sarg, ctypes.byref(h)))
         self._h = h
         self.device = int(device)
 
@@ -153,6 +158,12 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.ffvd_ctx_launch_count(self._h))
+
+    def fused_time(self, reset: bool = True):
+        """(total_ms, launches) of the fused tile kernel since the last reset; synchronises."""
+        tot, cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
+        _check(self._lib.ffvd_ctx_fused_time(self._h, int(reset), ctypes.byref(tot), ctypes.byref(cnt)))
+        return tot.value, cnt.value
 
     # ---- operators
     def kernel_K(self, kind, X, X2, logv, logl, out):

@@ -1,0 +1,78 @@
+"""Mirror of `vfegpssm/conditionals_multi_output.py` for a *list* of D per-output kernels."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi
+from ._tensor import as_f64, context_for, empty_like_lib, is_torch, to_lib
+
+JITTER = 1e-5          # conditionals_multi_output.py:108,159
+
+
+def _stack_hypers(kern, ref):
+    kind = kern[0].kind
+    if any(k.kind != kind for k in kern):
+        raise ValueError("all kernels of a multi-output layer must be of the same type")
+    hv, hl = zip(*[k._hyper(ref) for k in kern])
+    if is_torch(ref):
+        import torch
+        logv = torch.cat(list(hv)).contiguous()
+        logl = torch.stack(list(hl)).contiguous() if kind == _capi.KERNEL_SE else None
+    else:
+        logv = np.ascontiguousarray(np.concatenate(hv))
+        logl = np.ascontiguousarray(np.stack(hl)) if kind == _capi.KERNEL_SE else None
+    return kind, logv, logl
+
+
+def conditional(Xnew, X, kern, f, *, full_cov=False, q_sqrt=None, white=False, return_Lm=False):
+    """`conditionals_multi_output.py:73-120`: mean (N,D), var (N,D) of D independent GPs with
+    per-output kernels `kern[kk]`, inducing inputs X (M,Din), q(u) means f (M,D).  The hot path
+    uses white=True, full_cov=False, q_sqrt=None; full_cov / q_sqrt are prediction-only options
+     and raise NotImplementedError.  `return_Lm=True` reproduces the reference's
+    ValueError."""
+    if return_Lm:
+        raise ValueError("too many values to unpack (expected 2)")      # cmo:115, reference quirk Q8
+    if full_cov or q_sqrt is not None:
+        raise NotImplementedError("full_cov / q_sqrt belong to the prediction path (SURVEY 8f)")
+    Xnew, X, f = as_f64(Xnew), as_f64(X), as_f64(f)
+    X = to_lib(Xnew, X); f = to_lib(Xnew, f)
+    kind, logv, logl = _stack_hypers(kern, Xnew)
+    Xs = Xnew[..., : kern[0].input_dim]
+    Xs = Xs.contiguous() if is_torch(Xs) else np.ascontiguousarray(Xs)
+    mean = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
+    var = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
+    context_for(Xnew).conditional(kind, False, Xs, X, logv, logl, f, None, white, False, JITTER, mean, var)
+    return mean, var
+
+
+def kernel_pre_cal(X, kern):
+    """`conditionals_multi_output.py:124-169`: list of D matrices L_d^{-T}, L_d = chol(K_d(X)+1e-5 I)."""
+    X = as_f64(X)
+    kind, logv, logl = _stack_hypers(kern, X)
+    M = X.shape[0]
+    out = empty_like_lib(X, (len(kern), M, M))
+    context_for(X).kernel_pre_cal(kind, X, logv, logl, JITTER, out)
+    return [out[d] for d in range(len(kern))]
+
+
+def collapse_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q, batch_size, Y_N):
+    """`conditionals_multi_output.py:230-257`: (-term1/Y_N, -term2/Y_N, -trace/Y_N) of the collapsed
+    bound.  `Lm_inverse_seq` is accepted for signature parity; the fused path recomputes the factors
+    on the device.  Full batch only (batch_size == Y_N, as in base_model.py:194)."""
+    if float(batch_size) != float(Y_N):
+        raise NotImplementedError("mini-batching is disabled in the reference (base_model.py:188-194)")
+    X = as_f64(X)
+    D = X.shape[1]
+    T = X.shape[0] - 1
+    Xc = to_lib(X, as_f64(X_combine))
+    ctrl = Xc[:, D:]
+    ctrl = ctrl.contiguous() if is_torch(ctrl) else np.ascontiguousarray(ctrl)
+    kind, logv, logl = _stack_hypers(kern, X)
+    zeros = lambda *s: to_lib(X, np.zeros(s))
+    Qv = to_lib(X, Q)
+    logQ = Qv.log() if is_torch(Qv) else np.log(Qv)
+    prob = dict(X=X, Z=to_lib(X, as_f64(Z)), U=zeros(Z.shape[0], D), logv=logv, logl=logl, logQ=logQ, C=zeros(D, 1),
+                d=zeros(1), logR=zeros(1, 1), Y=zeros(T, 1), ctrl=ctrl if ctrl.shape[1] > 0 else None)
+    terms = empty_like_lib(X, (1, 6))
+    context_for(X).nll_grads(kind, True, prob, dict(terms=terms), flags=_capi.FLAG_NO_GRADS, jitter=JITTER)
+    return terms[0, 4], terms[0, 5], terms[0, 3]

@@ -4,6 +4,7 @@
 #include "../../include/ffvd_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,10 @@ struct ffvd_ctx {
   int probs_cap = 0;
   int* h_status = nullptr;     // pinned
   size_t h_status_cap = 0;
+  // ring of event pairs bracketing the fused-kernel launches (bench.py reads the average)
+  static const int kRing = 256;
+  cudaEvent_t ev0[kRing], ev1[kRing];
+  long long ev_count = 0;
 };
 
 extern "C" int ffvd_version(void) { return 100; }
@@ -80,6 +85,7 @@ extern "C" int ffvd_ctx_create(int device, void* stream, ffvd_ctx** out) {
     if (e != cudaSuccess) { delete c; return fail(FFVD_E_CUDA, cudaGetErrorString(e)); }
     c->own_stream = true;
   }
+  for (int i = 0; i < ffvd_ctx::kRing; ++i) { cudaEventCreate(&c->ev0[i]); cudaEventCreate(&c->ev1[i]); }
   *out = c;
   return FFVD_OK;
 }
@@ -92,6 +98,7 @@ extern "C" int ffvd_ctx_destroy(ffvd_ctx* c) {
   if (c->d_probs) cudaFree(c->d_probs);
   if (c->d_outs) cudaFree(c->d_outs);
   if (c->h_status) cudaFreeHost(c->h_status);
+  for (int i = 0; i < ffvd_ctx::kRing; ++i) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return FFVD_OK;
@@ -103,6 +110,21 @@ extern "C" int ffvd_ctx_synchronize(ffvd_ctx* c) {
   return FFVD_OK;
 }
 extern "C" int64_t ffvd_ctx_launch_count(ffvd_ctx* c) { return c ? c->launches : 0; }
+extern "C" int ffvd_ctx_fused_time(ffvd_ctx* c, int reset, double* total_ms, int64_t* count) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const long long n = c->ev_count < ffvd_ctx::kRing ? c->ev_count : ffvd_ctx::kRing;
+  double tot = 0.0;
+  for (long long i = 0; i < n; ++i) {
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0[i], c->ev1[i]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  if (reset) c->ev_count = 0;
+  return FFVD_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // tensor import / staging
@@ -290,29 +312,50 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
 
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch helpers
+// Tile configuration per padded M: RB row blocks (BT = 8*RB time steps per tile) and resident CTAs per SM.
+// Overridable for experiments with FFVD_RB / FFVD_MINB (only the combinations instantiated below exist).
+struct FusedCfg { int rb, minb; };
+static FusedCfg fused_cfg(int Mp) {
+  FusedCfg cfg;
+  const int ngw = Mp / 128;
+  cfg.rb = (ngw <= 2) ? 8 : 4;
+  cfg.minb = 1;
+  if (const char* e = getenv("FFVD_RB")) cfg.rb = atoi(e);
+  if (const char* e = getenv("FFVD_MINB")) cfg.minb = atoi(e);
+  return cfg;
+}
+
 template <int KIND, int MODE>
 static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int nprob, long long total_items) {
   const int ngw = Mp / 128;
-  int RB;
+  const FusedCfg cfg = fused_cfg(Mp);
   void (*kern)(const DevProblem*, int, long long) = nullptr;
-  switch (ngw) {
-    case 1: RB = 8; kern = fused_kernel<KIND, 8, 1, MODE>; break;
-    case 2: RB = 8; kern = fused_kernel<KIND, 8, 2, MODE>; break;
-    case 3: RB = 4; kern = fused_kernel<KIND, 4, 3, MODE>; break;
-    case 4: RB = 4; kern = fused_kernel<KIND, 4, 4, MODE>; break;
-    default: return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
+#define FFVD_PICK(RB_, NGW_, MINB_) \
+  if (ngw == NGW_ && cfg.rb == RB_ && cfg.minb == MINB_) kern = fused_kernel<KIND, RB_, NGW_, MODE, MINB_>;
+  FFVD_PICK(8, 1, 1) FFVD_PICK(8, 2, 1) FFVD_PICK(4, 3, 1) FFVD_PICK(4, 4, 1)
+  if (KIND == 0 && MODE == MODE_UNCOLLAPSED) {
+    FFVD_PICK(4, 2, 1) FFVD_PICK(4, 2, 2) FFVD_PICK(8, 1, 2) FFVD_PICK(4, 1, 2) FFVD_PICK(2, 4, 2) FFVD_PICK(2, 3, 2)
   }
+#undef FFVD_PICK
+  if (ngw > 4) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
+  if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_MINB)");
+  const int RB = cfg.rb;
   const size_t smem = fused_smem_bytes(RB, Mp);
   if ((int)smem > c->max_smem) return fail(FFVD_E_LIMIT, "fused kernel shared memory exceeds the device limit");
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long grid = total_items < (long long)c->num_sms ? total_items : (long long)c->num_sms;
+  const long long cap = (long long)c->num_sms * cfg.minb;
+  long long grid = total_items < cap ? total_items : cap;
   if (grid < 1) return FFVD_OK;
+  const int slot = (int)(c->ev_count % ffvd_ctx::kRing);
+  cudaEventRecord(c->ev0[slot], c->stream);
   kern<<<(int)grid, FFVD_NTHREADS, smem, c->stream>>>(d_probs, nprob, total_items);
+  cudaEventRecord(c->ev1[slot], c->stream);
+  c->ev_count++;
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return FFVD_OK;
 }
-static int rb_of(int Mp) { return (Mp / 128 <= 2) ? 8 : 4; }
+static int rb_of(int Mp) { return fused_cfg(Mp).rb; }
 
 template <int KIND>
 static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter) {
@@ -457,7 +500,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     bind_problem(c, L, p, s_begin, P);
     s_begin += t.S;
     if (t.gX.present) P.gX = t.gX.d;
-    else if (!no_grads) {
+    else if (!no_grads || collapsed) {   // collapsed pass 1 always accumulates the emission gradient
       CUDA_TRY(cudaMallocAsync((void**)&t.gx_scratch, t.X.numel * 8, c->stream));
       P.gX = t.gx_scratch;
     }

@@ -46,9 +46,15 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
 #pragma unroll
     for (int c = 0; c < 4; ++c) s[rb][c] = 0.0;
   const double* xsrc = (KIND == 0) ? sm.xsc : sm.xs;
+  // one-step software pipeline on the (L1/L2-resident) Z^T loads
+  double2 n01 = __ldg(reinterpret_cast<const double2*>(ZT + jbase));
+  double2 n23 = __ldg(reinterpret_cast<const double2*>(ZT + jbase + 2));
   for (int jd = 0; jd < Din; ++jd) {
-    const double2 z01 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)jd * Mp + jbase));
-    const double2 z23 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)jd * Mp + jbase + 2));
+    const double2 z01 = n01, z23 = n23;
+    if (jd + 1 < Din) {
+      n01 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)(jd + 1) * Mp + jbase));
+      n23 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)(jd + 1) * Mp + jbase + 2));
+    }
     double z[4] = {z01.x, z01.y, z23.x, z23.y};
     if (KIND == 0) {
       const double sil = sm.small[32 + jd];
@@ -280,19 +286,28 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
       double c[4][2];
 #pragma unroll
       for (int nb = 0; nb < 4; ++nb) c[nb][0] = c[nb][1] = 0.0;
-      for (int k0 = ks * klen; k0 < (ks + 1) * klen; k0 += 4) {
-        const double a = tile[(8 * rb + g) * lda + k0 + q];
-        const int m = k0 + q;
+      // 4 k-steps per trip: all operand loads are issued before the first DMMA of the trip
+      for (int k0 = ks * klen; k0 < (ks + 1) * klen; k0 += 16) {
+        double a[4], b[4][4];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-          if (nb < nbx) {
-            const int jd = 8 * nb + g;
-            double b = 0.0;
-            if (jd < Din) b = __ldg(P.ZT + (size_t)jd * Mp + m);
-            else if (jd == Din) b = (m < M) ? 1.0 : 0.0;
-            dmma884(c[nb][0], c[nb][1], a, b);
+        for (int u = 0; u < 4; ++u) {
+          a[u] = tile[(8 * rb + g) * lda + k0 + 4 * u + q];
+          const int m = k0 + 4 * u + q;
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) {
+            b[u][nb] = 0.0;
+            if (nb < nbx) {
+              const int jd = 8 * nb + g;
+              if (jd < Din) b[u][nb] = __ldg(P.ZT + (size_t)jd * Mp + m);
+              else if (jd == Din) b[u][nb] = (m < M) ? 1.0 : 0.0;
+            }
           }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb)
+            if (nb < nbx) dmma884(c[nb][0], c[nb][1], a[u], b[u][nb]);
       }
 #pragma unroll
       for (int nb = 0; nb < 4; ++nb)
@@ -332,8 +347,8 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int RB, int NGW, int MODE>
-__global__ void __launch_bounds__(FFVD_NTHREADS, 1)
+template <int KIND, int RB, int NGW, int MODE, int MINB>
+__global__ void __launch_bounds__(FFVD_NTHREADS, MINB)
 fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_items) {
   extern __shared__ __align__(16) double smem_raw[];
   constexpr int BT = 8 * RB;
@@ -609,10 +624,16 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       // ---- P4: Kbar = Abar L^{-1},  abar_rj = e_r u_j + a_rj / Q  formed on the fly
       double er[RB];
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) er[rb] = sm.es[8 * rb + g];
+      for (int rb = 0; rb < RB; ++rb) er[rb] = sm.es[8 * rb + g] * Q;      // residual = e * Q
       const double* us = sm.us;
       tile_gemm<RB, NGW, -1>(acc, sm.tile, lda, Linv, Mp, warp, g, q,
-                             [&](double x, int rb, int k) { return fma(er[rb], us[k], x * invQ); });
+                             [&](double x, int rb, int k) { return fma(er[rb], us[k], x); });
+#pragma unroll
+      for (int ng = 0; ng < NGW; ++ng)
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[ng][rb][c] *= invQ;
     } else if (MODE == MODE_COLLAPSED_P2) {
       // ---- Kbar = K N + delta w'^T ; also dbar_r = k_r . w'
       tile_gemm<RB, NGW, 0>(acc, sm.tile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, warp, g, q,

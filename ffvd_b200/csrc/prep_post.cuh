@@ -51,6 +51,7 @@ __device__ void tri_inverse(const double* L, int ldl, int M, double* X, double* 
     for (int k = tid; k <= i; k += nth) rowbuf[k] = L[(size_t)i * ldl + k];
     __syncthreads();
     const double dinv = 1.0 / rowbuf[i];
+    for (int j = i + 1 + tid; j < M; j += nth) X[(size_t)i * Mp + j] = 0.0;   // the buffer may hold a stale dense matrix
     for (int j = tid; j <= i; j += nth) {
       double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int k = j;

@@ -82,12 +82,17 @@ int  ffvd_version(void);
 const char* ffvd_status_string(int status);
 const char* ffvd_last_error(void);
 
-/* stream: a cudaStream_t (as void*) or NULL for a stream owned by the context. */
+/* stream: a cudaStream_t (as void*) or NULL for a stream owned by the context.  To run on the legacy
+ * default stream pass cudaStreamLegacy ((void*)0x1), not 0. */
 int ffvd_ctx_create(int device, void* stream, ffvd_ctx** out);
 int ffvd_ctx_destroy(ffvd_ctx* ctx);
 int ffvd_ctx_synchronize(ffvd_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t ffvd_ctx_launch_count(ffvd_ctx* ctx);
+/* Sum of the device times (ms, CUDA events on the context's stream) and the number of fused
+ * tile-kernel launches recorded since the last reset (ring of 256); synchronises the stream.
+ * bench.py derives the roofline figure from it. */
+int ffvd_ctx_fused_time(ffvd_ctx* ctx, int reset, double* total_ms, int64_t* count);
 
 /* kernels_multi_output.py:202-214,246-247 / kernels.py:270-276  K(X, X2) -> out (N,N2).
  * X2 may be NULL (K(X,X)).  logv: () ; logl: (Din) for SE, NULL for Linear. */

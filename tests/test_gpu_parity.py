@@ -1,0 +1,378 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes + DLPack), against the CPU
+oracle and against the committed golden vectors.  Tolerance (BASELINE north star): <= 1e-9
+relative in float64, measured relative to each tensor's max-norm."""
+import copy
+
+import numpy as np
+import pytest
+
+from util import assert_close, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+PKEYS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR", "Y", "ctrl")
+GKEYS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import ffvd_b200
+    from oracle import fixtures
+    dev = torch.device("cuda:0")
+    ctx = ffvd_b200.Context(0, torch.cuda.current_stream(0).cuda_stream)
+    packed = fixtures.load_packed()
+    return dict(torch=torch, ffvd=ffvd_b200, dev=dev, ctx=ctx, problems=packed["problems"],
+                byname={p.name: p for p in packed["problems"]}, extra=packed["extra"])
+
+
+def dev_problem(env, prob):
+    torch = env["torch"]
+    return {k: (None if getattr(prob, k) is None else torch.as_tensor(np.ascontiguousarray(getattr(prob, k)),
+                                                                      dtype=torch.float64, device=env["dev"]))
+            for k in PKEYS}
+
+
+def alloc_out(env, p):
+    torch = env["torch"]
+    S = 1 if p["X"].dim() == 2 else p["X"].shape[0]
+    o = {"nll": torch.full((S,), float("nan"), dtype=torch.float64, device=env["dev"]),
+         "terms": torch.full((S, 6), float("nan"), dtype=torch.float64, device=env["dev"])}
+    for k in GKEYS:
+        if p[k] is not None:
+            o["g_" + k] = torch.full_like(p[k], float("nan"))
+    return o
+
+
+def run_cuda(env, prob, collapsed, flags=None):
+    p = dev_problem(env, prob)
+    o = alloc_out(env, p)
+    flags = env["ffvd"].FLAG_PRIOR_Z_NORMAL if flags is None else flags
+    env["ctx"].nll_grads(prob.kind, collapsed, p, o, flags=flags)
+    env["torch"].cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in o.items()}
+    if p["X"].dim() == 2:
+        res["nll"], res["terms"] = res["nll"][0], res["terms"][0]
+    return res
+
+
+def check(ref, got, tol=TOL, what=""):
+    for k in ref:
+        if k in got:
+            assert_close(ref[k], got[k], tol, "%s %s" % (what, k))
+
+
+# ------------------------------------------------------------------------------------------------
+def test_all_95_fixtures_vs_oracle(env):
+    """Every bundled warm start x {uncollapsed, collapsed}: nll, six terms and all gradients."""
+    from oracle import ffvd_oracle as O
+    worst = 0.0
+    for prob in env["problems"]:
+        for collapsed in (False, True):
+            ref = O.nll_and_grads(prob, collapsed=collapsed)
+            got = run_cuda(env, prob, collapsed)
+            for k in ref:
+                e = relerr(ref[k], got[k])
+                worst = max(worst, e)
+                assert e <= TOL, (prob.name, collapsed, k, e)
+    print("worst max-norm relative error over 95 x 2 evaluations: %.3e" % worst)
+
+
+@pytest.mark.parametrize("ds", ("dryer", "drive", "gas_furnace", "actuator", "flutter", "ballbeam"))
+@pytest.mark.parametrize("mode", ("collapsed", "uncollapsed"))
+def test_vs_reference_source_golden(env, ds, mode):
+    """CUDA vs the vectors the reference's own source produced (tests/golden/reference_shim_golden.npz)."""
+    golden = load_golden()
+    for idx in (0, 1):
+        got = run_cuda(env, env["byname"]["%s/%d" % (ds, idx)], mode == "collapsed")
+        key = "%s/%d/%s/" % (ds, idx, mode)
+        assert abs(got["nll"] - float(golden[key + "nll"])) <= TOL * abs(float(golden[key + "nll"]))
+        assert_close(golden[key + "terms"], got["terms"], TOL, key + "terms")
+        for g in GKEYS:
+            assert_close(golden[key + "g_" + g].reshape(got["g_" + g].shape), got["g_" + g], TOL, key + g)
+
+
+@pytest.mark.parametrize("collapsed", (False, True))
+def test_sample_axis(env, collapsed):
+    """S trajectories sharing Z,U,hypers: per-sample nll/terms/x-bar equal single-sample runs and
+    shared gradients are the sum over samples (SURVEY 8 batch-axis contract)."""
+    from oracle import ffvd_oracle as O
+    prob = copy.copy(env["byname"]["flutter/0"])
+    prob.X = env["extra"]["flutter/0"]
+    ref = O.nll_and_grads(prob, collapsed=collapsed)
+    got = run_cuda(env, prob, collapsed)
+    check(ref, got, what="S=4")
+    singles = []
+    for s in range(prob.X.shape[0]):
+        q = copy.copy(prob); q.X = prob.X[s]
+        singles.append(run_cuda(env, q, collapsed))
+    assert_close(np.array([r["nll"] for r in singles]), got["nll"], 1e-12)
+    assert_close(np.stack([r["g_X"] for r in singles]), got["g_X"], 1e-11)
+    assert_close(sum(r["g_Z"] for r in singles), got["g_Z"], 1e-10)
+    # FFVD_FLAG_PRIOR_ONCE: shared priors counted once
+    once = run_cuda(env, prob, collapsed, flags=env["ffvd"].FLAG_PRIOR_Z_NORMAL | env["ffvd"].FLAG_PRIOR_ONCE)
+    T = prob.Y.shape[0]
+    assert_close(got["g_Z"] - 3 * prob.Z / T, once["g_Z"], 1e-10)
+
+
+@pytest.mark.parametrize("collapsed", (False, True))
+def test_linear_kernel(env, collapsed):
+    from oracle import ffvd_oracle as O
+    prob = copy.copy(env["byname"]["gas_furnace/0"])
+    prob.kind, prob.logl, prob.logv = 1, None, np.log(np.array([1.0, 0.7, 1.3, 0.9]))
+    check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="LinearK")
+
+
+@pytest.mark.parametrize("T,M,D,S", [(1, 5, 1, 1), (7, 3, 2, 2), (64, 128, 2, 1), (65, 129, 2, 1), (130, 200, 3, 2),
+                                      (97, 300, 2, 1), (80, 512, 2, 1)])
+@pytest.mark.parametrize("collapsed", (False, True))
+def test_ragged_shapes(env, T, M, D, S, collapsed):
+    """Tile-ragged T (1, prime, multiple and multiple+1 of the tile), every padded-M template."""
+    from oracle import fixtures, ffvd_oracle as O
+    prob = fixtures.synthetic_problem(T=T, M=M, D=D, S=S, seed=T * 1000 + M)
+    check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="T%d M%d" % (T, M))
+
+
+def test_no_control_inputs_and_multi_output_y(env):
+    from oracle import fixtures, ffvd_oracle as O
+    prob = fixtures.synthetic_problem(T=50, M=20, D=3, S=1, n_ctrl=0, Dy=2)
+    prob.ctrl = np.zeros((50, 0))
+    ref = O.nll_and_grads(prob, collapsed=False)
+    q = copy.copy(prob); q.ctrl = None
+    check(ref, run_cuda(env, q, False), what="nc=0 Dy=2")
+
+
+def test_batched_chains(env):
+    """BASELINE config 4: independent chains with ragged T in one call == one call per chain."""
+    ctx, torch = env["ctx"], env["torch"]
+    names = ["actuator/3", "gas_furnace/5", "drive/2", "dryer/7", "ballbeam/1", "flutter/9"]
+    for collapsed in (False, True):
+        probs = [dev_problem(env, env["byname"][n]) for n in names]
+        outs = [alloc_out(env, p) for p in probs]
+        ctx.nll_grads_batched(0, collapsed, probs, outs)
+        torch.cuda.synchronize()
+        for n, o in zip(names, outs):
+            single = run_cuda(env, env["byname"][n], collapsed)
+            for k, v in o.items():
+                g = v.cpu().numpy()
+                assert_close(single[k], g.reshape(np.shape(single[k])), 1e-10, "%s %s" % (n, k))   # FP64 atomics: summation order differs run to run
+
+
+def test_forward_only_flag(env):
+    prob = env["byname"]["actuator/0"]
+    for collapsed in (False, True):
+        full = run_cuda(env, prob, collapsed)
+        p = dev_problem(env, prob)
+        o = {"nll": env["torch"].empty(1, dtype=env["torch"].float64, device=env["dev"]),
+             "terms": env["torch"].empty(1, 6, dtype=env["torch"].float64, device=env["dev"])}
+        env["ctx"].nll_grads(0, collapsed, p, o, flags=env["ffvd"].FLAG_PRIOR_Z_NORMAL | env["ffvd"].FLAG_NO_GRADS)
+        assert_close(full["terms"], o["terms"].cpu().numpy()[0], 1e-12)
+
+
+def test_host_numpy_tensors_are_staged(env):
+    """kDLCPU tensors in and out (explicit staging copies inside the library)."""
+    from oracle import ffvd_oracle as O
+    prob = env["byname"]["drive/0"]
+    p = {k: (None if getattr(prob, k) is None else np.ascontiguousarray(getattr(prob, k), dtype=np.float64)) for k in PKEYS}
+    o = {"nll": np.zeros(1), "terms": np.zeros((1, 6))}
+    for k in GKEYS:
+        o["g_" + k] = np.full_like(p[k], np.nan)
+    env["ctx"].nll_grads(0, False, p, o)
+    ref = O.nll_and_grads(prob, collapsed=False)
+    assert abs(o["nll"][0] - ref["nll"]) <= TOL * abs(ref["nll"])
+    for k in GKEYS:
+        assert_close(ref["g_" + k], o["g_" + k], TOL, k)
+
+
+def test_error_statuses(env):
+    ffvd, torch, ctx = env["ffvd"], env["torch"], env["ctx"]
+    prob = copy.copy(env["byname"]["drive/0"])
+    # float32 input -> ValueError (dtype)
+    p = dev_problem(env, prob); o = alloc_out(env, p)
+    p["Z"] = p["Z"].to(torch.float32)
+    with pytest.raises(ValueError):
+        ctx.nll_grads(0, False, p, o)
+    # shape mismatch
+    p = dev_problem(env, prob); o = alloc_out(env, p)
+    p["U"] = p["U"][:50].contiguous()
+    with pytest.raises(ValueError):
+        ctx.nll_grads(0, False, p, o)
+    # non-contiguous
+    p = dev_problem(env, prob); o = alloc_out(env, p)
+    p["Z"] = p["Z"].t().contiguous().t()
+    with pytest.raises(ValueError):
+        ctx.nll_grads(0, False, p, o)
+    # non-SPD Kzz (duplicate inducing points, zero jitter) -> NotPositiveDefinite, no abort
+    q = copy.copy(prob); q.Z = prob.Z.copy(); q.Z[1] = q.Z[0]
+    p = dev_problem(env, q); o = alloc_out(env, p)
+    with pytest.raises(ffvd.NotPositiveDefinite):
+        ctx.nll_grads(0, False, p, o, jitter=0.0)
+    # and the context is still usable afterwards
+    run_cuda(env, prob, False)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_operator_level_vs_golden(env):
+    """K / Kdiag / conditional / kernel_pre_cal / log-densities through the mirror API, on the golden inputs."""
+    from ffvd_b200 import conditionals, conditionals_multi_output, likelihoods
+    from ffvd_b200.kernels import LinearK
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    torch, dev = env["torch"], env["dev"]
+    g = load_golden()
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64, device=dev)
+    Z, Xn, f = (g["op/linear_single/" + k] for k in ("Z", "Xnew", "f"))
+    lk = LinearK(3, variance=1.0)
+    assert_close(g["op/linear/K"], lk.K(t(Xn), t(Z)).cpu().numpy(), 1e-13)
+    assert_close(g["op/linear/Kdiag"], lk.Kdiag(t(Xn)).cpu().numpy(), 1e-13)
+    kd = np.max(np.abs(g["op/linear/Kdiag"]))
+    for white, sfx in ((True, ""), (False, "_nonwhite")):
+        mu, var = conditionals.conditional(t(Xn), t(Z), lk, t(f), white=white)
+        # rank-deficient Kzz + 1e-7 I: cond ~ 1e9, so the (non-)whitened mean carries ~cond*eps
+        assert_close(g["op/linear_single/mean" + sfx], mu.cpu().numpy(), 1e-9 if white else 1e-6)
+        # variance tolerance is relative to max|Kdiag| for LinearK
+        assert np.max(np.abs(g["op/linear_single/var" + sfx] - var.cpu().numpy())) <= 1e-9 * kd
+    mu, var = conditionals_multi_output.conditional(t(Xn), t(Z), [lk, lk], t(f), white=True)
+    assert_close(g["op/linear_multi/mean"], mu.cpu().numpy(), 1e-9)
+    assert np.max(np.abs(g["op/linear_multi/var"] - var.cpu().numpy())) <= 1e-9 * kd
+    se = SquaredExponential(3, variance=0.37, lengthscales=np.array([0.9, 1.7, 2.6]), ARD=True)
+    se2 = SquaredExponential(3, variance=0.11, lengthscales=np.array([1.3, 0.8, 3.1]), ARD=True)
+    assert_close(g["op/se/K"], se.K(t(Xn), t(Z)).cpu().numpy(), 1e-13)
+    assert_close(g["op/se/Kzz"], se.K(t(Z)).cpu().numpy(), 1e-13)
+    assert_close(g["op/se/Kdiag"], se.Kdiag(t(Xn)).cpu().numpy(), 1e-15)
+    mu, var = conditionals_multi_output.conditional(t(Xn), t(Z), [se, se2], t(f), white=True)
+    assert_close(g["op/se_multi/mean"], mu.cpu().numpy(), TOL)
+    assert_close(g["op/se_multi/var"], var.cpu().numpy(), TOL)
+    Li = conditionals_multi_output.kernel_pre_cal(t(Z), [se, se2])
+    assert_close(g["op/se_multi/LinvT"], torch.stack(Li).cpu().numpy(), TOL)
+    y, ym, R = g["op/ld/y"], g["op/ld/ymean"], g["op/ld/R"]
+    assert_close(g["op/ld/diag"], likelihoods.logdensity_norm_diag(t(y), t(ym), t(R)).cpu().numpy(), 1e-14)
+    assert_close(g["op/ld/diag_nonvec"], likelihoods.logdensity_norm_diag_nonvec(t(y), t(ym), t(R)).cpu().numpy(), 1e-14)
+    # numpy in -> numpy out
+    K_np = se.K(np.asarray(Xn), np.asarray(Z))
+    assert isinstance(K_np, np.ndarray)
+    assert_close(g["op/se/K"], K_np, 1e-13)
+
+
+def test_conditional_on_fixture_vs_oracle(env):
+    """The regularizer's conditional (dgp_model.py:344) at fixture size, and collapse_after_kernel_precalculation."""
+    import torch as th
+    from oracle import ffvd_oracle as O
+    from ffvd_b200 import conditionals_multi_output as cmo
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    prob = env["byname"]["ballbeam/4"]
+    T = prob.Y.shape[0]
+    kerns = [SquaredExponential(5, variance=np.exp(prob.logv[k]), lengthscales=np.exp(prob.logl[k]), ARD=True) for k in range(4)]
+    Xc = np.concatenate([prob.X[:T], prob.ctrl], axis=1)
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    mu, var = cmo.conditional(t(Xc), t(prob.Z), kerns, t(prob.U), white=True)
+    ok = O._make_kernels(th.as_tensor(prob.logv), th.as_tensor(prob.logl), 0, 5)
+    rmu, rvar = O.conditional_multi_output(th.as_tensor(Xc), th.as_tensor(prob.Z), ok, th.as_tensor(prob.U), white=True)
+    assert_close(rmu.numpy(), mu.cpu().numpy(), TOL)
+    assert_close(rvar.numpy(), var.cpu().numpy(), TOL)
+    Q = np.exp(prob.logQ)
+    t1, t2, tr = cmo.collapse_after_kernel_precalculation(None, t(Xc), t(prob.X), t(prob.Z), kerns, t(Q), float(T), float(T))
+    Linv = O.kernel_pre_cal(th.as_tensor(prob.Z), ok)
+    r1, r2, rtr = O.collapse_after_kernel_precalculation(Linv, th.as_tensor(Xc), th.as_tensor(prob.X), th.as_tensor(prob.Z), ok,
+                                                         th.as_tensor(Q), float(T), float(T))
+    for a, b in ((r1, t1), (r2, t2), (rtr, tr)):
+        assert abs(float(a) - float(b)) <= TOL * abs(float(a))
+
+
+@pytest.mark.parametrize("case", (2, 7))
+def test_sghmc_kernel_vs_reference_golden(env, case):
+    torch, ctx, dev = env["torch"], env["ctx"], env["dev"]
+    g = load_golden()
+    key = "sghmc/case%d" % case
+    X_N = float(g[key + "/X_N"])
+    for i in range(int(g[key + "/nvars"])):
+        pre = "%s/var%d/" % (key, i)
+        for burn_in in (True, False):
+            ten = {n: torch.as_tensor(np.array(g[pre + n], dtype=np.float64), device=dev).clone().reshape(-1)
+                   for n in ("theta", "grad", "noise", "xi", "g", "g2", "p")}
+            ctx.sghmc_update(ten["theta"], ten["grad"], ten["noise"], ten["xi"], ten["g"], ten["g2"], ten["p"], 0.01, 0.05, X_N, burn_in)
+            torch.cuda.synchronize()
+            assert_close(g[pre + "theta_t"].reshape(-1), ten["theta"].cpu().numpy(), 1e-14)
+            assert_close(g[pre + "p_t"].reshape(-1), ten["p"].cpu().numpy(), 1e-13)
+            for n in ("xi", "g", "g2"):
+                expect = g[pre + n + "_t"] if burn_in else g[pre + n]
+                assert_close(expect.reshape(-1), ten[n].cpu().numpy(), 1e-14)
+
+
+def test_adam_kernel_vs_oracle(env):
+    from oracle import ffvd_oracle as O
+    torch, ctx, dev = env["torch"], env["ctx"], env["dev"]
+    rng = np.random.default_rng(3)
+    th, m, v = rng.standard_normal(1001), np.zeros(1001), np.zeros(1001)
+    d_th, d_m, d_v = (torch.as_tensor(a.copy(), device=dev) for a in (th, m, v))
+    for step in range(1, 5):
+        gr = rng.standard_normal(1001)
+        lr = O.adam_learning_rate(step)
+        th, m, v = O.adam_update(th, gr, m, v, step=step, lr=lr)
+        ctx.adam_update(d_th, torch.as_tensor(gr, device=dev), d_m, d_v, lr, step=step)
+    torch.cuda.synchronize()
+    assert_close(th, d_th.cpu().numpy(), 1e-14)
+    assert_close(v, d_v.cpu().numpy(), 1e-14)
+
+
+def test_dgpssm_mirror_and_sghmc_chain(env):
+    """The `vfegpssm`-shaped API end to end: DGPSSM(...).nll, the SG-HMC variable set of case 2, and
+    three scheduled updates with injected noise against the oracle driven by the same noise."""
+    from oracle import ffvd_oracle as O
+    from ffvd_b200.dgp_model import DGPSSM
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    from ffvd_b200.likelihoods import Gaussian
+    torch = env["torch"]
+    prob = copy.copy(env["byname"]["gas_furnace/2"])
+    T = prob.Y.shape[0]
+    kerns = [[SquaredExponential(5, variance=np.exp(prob.logv[k]), lengthscales=np.exp(prob.logl[k]), ARD=True) for k in range(4)]]
+    lik = Gaussian(1, 4, CC=prob.C, DD=prob.d, RR_chol=np.exp(prob.logR))
+    model = DGPSSM(prob.Y, [4], 100, kerns, lik, minibatch_size=T, window_size=64, prior_type="normal",
+                   QQ_chol=np.exp(0.5 * prob.logQ), ZZ=prob.Z, control_inputs=prob.ctrl, U_ini=prob.U, X_0_ini=prob.X[0],
+                   X_train_ini=prob.X[1:], kernel_optimization=False, U_optimization=False, U_collapse=False,
+                   Z_optimization=True, case_val=2)
+    assert model.vars == ["logv", "logl", "U"] and model.X_N == T + 1
+    assert set(model.trainable) == {"X", "Z", "logQ", "C", "d", "logR"}
+    ref = O.nll_and_grads(prob, collapsed=False)
+    assert abs(float(model.nll) - ref["nll"]) <= TOL * abs(ref["nll"])
+    # chain: burn-in, burn-in, sample with injected noise
+    rng = np.random.default_rng(11)
+    state = {n: dict(xi=np.ones_like(getattr(prob, n)), g=np.ones_like(getattr(prob, n)), g2=np.ones_like(getattr(prob, n)),
+                     p=np.zeros_like(getattr(prob, n))) for n in model.vars}
+    for burn_in in (True, True, False):
+        noise = {n: rng.standard_normal(getattr(prob, n).shape) for n in model.vars}
+        model._run_update(burn_in, noise)
+        grads = O.nll_and_grads(prob, collapsed=False)
+        for n in model.vars:
+            s = state[n]
+            th, s["xi"], s["g"], s["g2"], s["p"] = O.sghmc_update(getattr(prob, n), grads["g_" + n], noise[n], s["xi"], s["g"],
+                                                                    s["g2"], s["p"], epsilon=0.01, mdecay=0.05, X_N=T + 1, burn_in=burn_in)
+            setattr(prob, n, th)
+    torch.cuda.synchronize()
+    for n in model.vars:
+        assert_close(getattr(prob, n), model.params[n].cpu().numpy(), 1e-9, n)
+    out = model.train_hypers()
+    assert torch.isfinite(out["nll"]).all()
+
+
+def test_full_size_properties(env):
+    """At a BASELINE-config-3-shaped size that the oracle cannot finish (M=256, D=8, T=4096, S=4):
+    S-batched == per-sample, x-bar rows of a prefix are unaffected by dropping the tail's emission... 
+    and linearity of the shared gradients over samples."""
+    from oracle import fixtures
+    prob = fixtures.synthetic_problem(T=4096, M=256, D=8, S=4, seed=5)
+    got = run_cuda(env, prob, False)
+    assert np.all(np.isfinite(got["nll"]))
+    acc = None
+    for s in range(4):
+        q = copy.copy(prob); q.X = prob.X[s]
+        r = run_cuda(env, q, False)
+        assert abs(r["nll"] - got["nll"][s]) <= 1e-11 * abs(r["nll"])
+        assert_close(r["g_X"], got["g_X"][s], 1e-10)
+        acc = r if acc is None else {k: acc[k] + r[k] for k in r}
+    for k in ("g_Z", "g_U", "g_logv", "g_logl", "g_logQ", "g_C", "g_d", "g_logR"):
+        assert_close(acc[k], got[k], 1e-9, k)
+    # oracle spot check on a short prefix of sample 0 (same Z,U,hypers)
+    from oracle import ffvd_oracle as O
+    q = copy.copy(prob); q.X = prob.X[0, :129]; q.Y = prob.Y[:128]; q.ctrl = prob.ctrl[:128]
+    check(O.nll_and_grads(q, collapsed=False), run_cuda(env, q, False), what="prefix")

@@ -1,0 +1,58 @@
+"""CPU tests of the host-side mirror of the reference interface (no device work)."""
+import numpy as np
+import pytest
+
+from ffvd_b200 import _capi, distributed
+from ffvd_b200.dgp_model import sghmc_variable_names
+from ffvd_b200.kernels import LinearK, SquaredExponential as SE_U
+from ffvd_b200.kernels_multi_output import SquaredExponential
+
+
+def test_kernel_constructor_matches_reference_attributes():
+    k = SquaredExponential(5, variance=0.3, lengthscales=np.array([1., 2., 3., 4., 5.]), ARD=True, kernel_optimization=True)
+    assert k.input_dim == 5 and k.ARD is True and k.trainable
+    assert np.isclose(float(k.variance), 0.3) and np.allclose(k.lengthscales, [1, 2, 3, 4, 5])
+    assert np.isclose(float(k.logvariance), np.log(0.3))
+    k2 = SE_U(2, variance=0.1, lengthscales=1.0, U_kernel_optimization=False)    # kernels.py spelling of the kwarg
+    assert k2.ARD is False and k2.loglengthscales.shape == ()
+    with pytest.raises(TypeError):
+        SquaredExponential(2, U_kernel_optimization=True)
+
+
+def test_linear_kernel_reference_failure_modes():
+    # ARD=False with a vector variance raises exactly like the reference
+    with pytest.raises(ValueError, match="shape of variance does not match input_dim"):
+        LinearK(5, ARD=False, variance=np.ones(4))
+    assert float(LinearK(5).variance) == 1.0
+    # Q1(b): a bare kernel object instead of a list is not subscriptable
+    from ffvd_b200.dgp_model import Layer
+    with pytest.raises(TypeError):
+        Layer(None, None, None, None, LinearK(5), 4, 10, False, 4, 10, False)
+
+
+def test_ard_shape_validation():
+    with pytest.raises(ValueError, match="shape of lengthscales does not match input_dim"):
+        SquaredExponential(1, lengthscales=np.ones(2))
+
+
+@pytest.mark.parametrize("case_val,expected", [
+    (1, []), (2, ["logv", "logl", "U"]), (3, ["logv", "logl", "U", "Z"]), (4, []), (5, ["logv", "logl"]),
+    (6, []), (7, ["U", "X"])])
+def test_sghmc_variable_selection(case_val, expected):
+    # FFVD_Main.py:273-324 flag table -> dgp_model.py:213-244 selection
+    table = {1: (True, True, True, False), 2: (False, False, True, False), 3: (False, False, False, False),
+             4: (True, False, True, True), 5: (False, False, True, True), 6: (True, True, True, False),
+             7: (False, False, False, False)}
+    ko, uo, zo, uc = table[case_val]
+    assert sghmc_variable_names(_capi.KERNEL_SE, case_val, ko, True, uo, uc, zo) == expected
+
+
+def test_shard_helpers():
+    for n in (1, 7, 64, 95, 256):
+        for w in (1, 2, 4, 8):
+            blocks = [distributed.shard_range(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            assert max(b[1] - b[0] for b in blocks) - min(b[1] - b[0] for b in blocks) <= 1
+            rr = sorted(sum((distributed.round_robin(n, r, w) for r in range(w)), []))
+            assert rr == list(range(n))
