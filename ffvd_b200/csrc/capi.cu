@@ -40,6 +40,7 @@ struct ffvd_ctx {
   std::vector<long long> arena_key;
   DevProblem* d_probs = nullptr;
   OutPtrs* d_outs = nullptr;
+  double* kscr = nullptr;      // points into the arena (set by ensure_arena)
   int probs_cap = 0;
   int* h_status = nullptr;     // pinned
   size_t h_status_cap = 0;
@@ -219,7 +220,7 @@ struct Layout {
   long long sumS;
   bool collapsed;
   size_t off_ZT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
-      off_small, off_terms, off_status, off_utmp, total;
+      off_small, off_terms, off_status, off_utmp, off_kscr, total;
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
   size_t small_per;                // doubles of small accumulators per problem
 };
@@ -233,7 +234,8 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   size_t o = 0;
   const size_t mm = (size_t)Mp * Mp * sizeof(double);
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  L.off_ZT = take((size_t)nprob * Din * Mp * 8);
+  L.off_ZT = take((size_t)nprob * 32 * Mp * 8);
+  L.off_kscr = take((size_t)160 * 64 * Mp * 8);          // per-CTA K-tile scratch of the fused kernel
   L.off_Linv = take((size_t)nprob * nk * mm);
   L.off_LinvT = take((size_t)nprob * nk * mm);
   L.off_utmp = take((size_t)nprob * M * D * 8);
@@ -268,6 +270,7 @@ static int ensure_arena(ffvd_ctx* c, const Layout& L) {
     CUDA_TRY(cudaMemsetAsync(c->arena, 0, L.total, c->stream));   // padding of Linv etc. must be zero
     c->arena_key = key;
   }
+  c->kscr = (double*)(c->arena + L.off_kscr);
   if (c->probs_cap < L.nprob) {
     if (c->d_probs) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->d_probs)); CUDA_TRY(cudaFree(c->d_outs)); }
     CUDA_TRY(cudaMalloc((void**)&c->d_probs, sizeof(DevProblem) * L.nprob));
@@ -286,7 +289,7 @@ static int ensure_arena(ffvd_ctx* c, const Layout& L) {
 static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin, DevProblem& P) {
   char* a = c->arena;
   const size_t mm = (size_t)L.Mp * L.Mp;
-  P.ZT = (double*)(a + L.off_ZT) + (size_t)p * L.Din * L.Mp;
+  P.ZT = (double*)(a + L.off_ZT) + (size_t)p * 32 * L.Mp;
   P.Linv = (double*)(a + L.off_Linv) + (size_t)p * L.nk * mm;
   P.LinvT = (double*)(a + L.off_LinvT) + (size_t)p * L.nk * mm;
   P.Sacc = (double*)(a + L.off_Sacc) + (size_t)p * L.nb * mm;
@@ -312,16 +315,16 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
 
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch helpers
-// Tile configuration per padded M: RB row blocks (BT = 8*RB time steps per tile) and resident CTAs per SM.
-// Overridable for experiments with FFVD_RB / FFVD_MINB (only the combinations instantiated below exist).
-struct FusedCfg { int rb, minb; };
+// Tile configuration per padded M: RB row blocks (BT = 8*RB time steps per tile) and NW warps per CTA.
+// Overridable for experiments with FFVD_RB / FFVD_NW (only the combinations instantiated below exist).
+struct FusedCfg { int rb, nw; };
 static FusedCfg fused_cfg(int Mp) {
   FusedCfg cfg;
   const int ngw = Mp / 128;
   cfg.rb = (ngw <= 2) ? 8 : 4;
-  cfg.minb = 1;
+  cfg.nw = 8;
   if (const char* e = getenv("FFVD_RB")) cfg.rb = atoi(e);
-  if (const char* e = getenv("FFVD_MINB")) cfg.minb = atoi(e);
+  if (const char* e = getenv("FFVD_NW")) cfg.nw = atoi(e);
   return cfg;
 }
 
@@ -329,26 +332,26 @@ template <int KIND, int MODE>
 static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int nprob, long long total_items) {
   const int ngw = Mp / 128;
   const FusedCfg cfg = fused_cfg(Mp);
-  void (*kern)(const DevProblem*, int, long long) = nullptr;
-#define FFVD_PICK(RB_, NGW_, MINB_) \
-  if (ngw == NGW_ && cfg.rb == RB_ && cfg.minb == MINB_) kern = fused_kernel<KIND, RB_, NGW_, MODE, MINB_>;
-  FFVD_PICK(8, 1, 1) FFVD_PICK(8, 2, 1) FFVD_PICK(4, 3, 1) FFVD_PICK(4, 4, 1)
+  void (*kern)(const DevProblem*, int, long long, double*) = nullptr;
+#define FFVD_PICK(RB_, NGW_, NW_) \
+  if (ngw == NGW_ && cfg.rb == RB_ && cfg.nw == NW_) kern = fused_kernel<KIND, RB_, NGW_, MODE, NW_>;
+  FFVD_PICK(8, 1, 8) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 3, 8) FFVD_PICK(4, 4, 8)
   if (KIND == 0 && MODE == MODE_UNCOLLAPSED) {
-    FFVD_PICK(4, 2, 1) FFVD_PICK(4, 2, 2) FFVD_PICK(8, 1, 2) FFVD_PICK(4, 1, 2) FFVD_PICK(2, 4, 2) FFVD_PICK(2, 3, 2)
+    FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 16) FFVD_PICK(4, 3, 16) FFVD_PICK(4, 4, 16)
   }
 #undef FFVD_PICK
   if (ngw > 4) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
-  if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_MINB)");
+  if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_NW)");
   const int RB = cfg.rb;
-  const size_t smem = fused_smem_bytes(RB, Mp);
+  const size_t smem = fused_smem_bytes(RB, Mp, cfg.nw);
   if ((int)smem > c->max_smem) return fail(FFVD_E_LIMIT, "fused kernel shared memory exceeds the device limit");
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long cap = (long long)c->num_sms * cfg.minb;
+  const long long cap = (long long)c->num_sms;
   long long grid = total_items < cap ? total_items : cap;
   if (grid < 1) return FFVD_OK;
   const int slot = (int)(c->ev_count % ffvd_ctx::kRing);
   cudaEventRecord(c->ev0[slot], c->stream);
-  kern<<<(int)grid, FFVD_NTHREADS, smem, c->stream>>>(d_probs, nprob, total_items);
+  kern<<<(int)grid, 32 * cfg.nw, smem, c->stream>>>(d_probs, nprob, total_items, c->kscr);
   cudaEventRecord(c->ev1[slot], c->stream);
   c->ev_count++;
   c->launches++;

@@ -27,10 +27,10 @@ struct Smem {
 template <int RB>
 __host__ __device__ constexpr int bt_of() { return 8 * RB; }
 
-__host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp) {
+__host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp, int NW) {
   const int BT = 8 * RB;
   // every sub-array is rounded up to an even number of doubles so that all of them stay 16-byte aligned
-  size_t n = (size_t)BT * (Mp + 4) + 8 * 8 * 40 + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
+  size_t n = (size_t)BT * (Mp + 4) + (size_t)NW * 4 * 40 + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
              (((size_t)BT * FFVD_XLD + 1) & ~(size_t)1) + Mp + 64 + 2 * 8 * 64 + 64 * 32 + 64 + 40;
   return n * sizeof(double);
 }
@@ -39,7 +39,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp) {
 // k(x_r, z_j) for the (rows 8*rb+g, cols jbase..jbase+3) owned by this lane.
 template <int KIND, int RB>
 __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem& sm, const double* __restrict__ ZT,
-                                                int Mp, int Din, double v, int jbase, int g, int M, int nvalid) {
+                                                int Mp, int Din, double v, int jbase, int g, int M, int nvalid, int row0) {
   double s[RB][4];
 #pragma unroll
   for (int rb = 0; rb < RB; ++rb)
@@ -63,7 +63,7 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
     }
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
-      const double x = xsrc[(8 * rb + g) * FFVD_XLD + jd];
+      const double x = xsrc[(row0 + 8 * rb + g) * FFVD_XLD + jd];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (KIND == 0) {
@@ -80,7 +80,7 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       double k = (KIND == 0) ? v * exp(-0.5 * s[rb][c]) : v * s[rb][c];
-      if (jbase + c >= M || 8 * rb + g >= nvalid) k = 0.0;
+      if (jbase + c >= M || row0 + 8 * rb + g >= nvalid) k = 0.0;
       kv[rb][c] = k;
     }
 }
@@ -92,49 +92,57 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
 template <int RB, int NGW, int TRI, class AOp>
 __device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const double* tile, int lda,
                                           const double* __restrict__ B, int Mp, int warp, int g, int q, AOp aop) {
-  int j0[NGW];
-  int kbeg = (TRI < 0) ? Mp : 0, kend = (TRI > 0) ? 0 : Mp;
+  // per-group active k range [kb, ke) (multiples of 4) and running B pointers
+  int kb[NGW], ke[NGW];
+  const double* bp[NGW];
+  int kbeg = Mp, kend = 0;
 #pragma unroll
   for (int ng = 0; ng < NGW; ++ng) {
-    j0[ng] = 16 * group_index(warp, ng);
-    if (TRI > 0) kend = max(kend, j0[ng] + 16);
-    if (TRI < 0) kbeg = min(kbeg, j0[ng]);
+    const int j0 = 16 * group_index(warp, ng);
+    kb[ng] = (TRI < 0) ? j0 : 0;
+    ke[ng] = (TRI > 0) ? j0 + 16 : Mp;
+    kbeg = min(kbeg, kb[ng]);
+    kend = max(kend, ke[ng]);
+    bp[ng] = B + (size_t)q * Mp + j0 + 2 * g;
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[ng][rb][c] = 0.0;
   }
-  double2 bcur[NGW], bnxt[NGW];
-  auto active = [&](int ng, int k0) -> bool {
-    return (TRI > 0) ? (k0 < j0[ng] + 16) : ((TRI < 0) ? (k0 >= j0[ng]) : true);
-  };
-  auto loadB = [&](int k0, double2(&b)[NGW]) {
+#pragma unroll
+  for (int ng = 0; ng < NGW; ++ng) bp[ng] += (size_t)kbeg * Mp;
+  const size_t bstep = (size_t)4 * Mp;
+  // B fragments are streamed from L2 two k-steps ahead (register ring b0 <- b1 <- b2)
+  double2 b0[NGW], b1[NGW], b2[NGW];
+  auto loadB = [&](int k0, double2(&b)[NGW]) {     // loads the fragments of step k0, bp[] must point at step k0
 #pragma unroll
     for (int ng = 0; ng < NGW; ++ng) {
-      if (active(ng, k0))
-        b[ng] = __ldg(reinterpret_cast<const double2*>(B + (size_t)(k0 + q) * Mp + j0[ng] + 2 * g));
-      else
-        b[ng] = make_double2(0.0, 0.0);
+      if (k0 >= kb[ng] && k0 < ke[ng]) b[ng] = __ldg(reinterpret_cast<const double2*>(bp[ng]));
+      else b[ng] = make_double2(0.0, 0.0);
+      bp[ng] += bstep;
     }
   };
-  loadB(kbeg, bcur);
+  loadB(kbeg, b0);
+  loadB(kbeg + 4, b1);        // may run past kend: the range test turns it into zeros without touching memory
+  const double* ap = tile + g * lda + kbeg + q;
   for (int k0 = kbeg; k0 < kend; k0 += 4) {
-    if (k0 + 4 < kend) loadB(k0 + 4, bnxt);
+    loadB(k0 + 8, b2);
     double a[RB];
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) a[rb] = aop(tile[(8 * rb + g) * lda + k0 + q], rb, k0 + q);
+    for (int rb = 0; rb < RB; ++rb) a[rb] = aop(ap[rb * 8 * lda], rb, k0 + q);
+    ap += 4;
 #pragma unroll
     for (int ng = 0; ng < NGW; ++ng) {
-      if (active(ng, k0)) {
+      if (k0 >= kb[ng] && k0 < ke[ng]) {
 #pragma unroll
         for (int rb = 0; rb < RB; ++rb) {
-          dmma884(acc[ng][rb][0], acc[ng][rb][2], a[rb], bcur[ng].x);
-          dmma884(acc[ng][rb][1], acc[ng][rb][3], a[rb], bcur[ng].y);
+          dmma884(acc[ng][rb][0], acc[ng][rb][2], a[rb], b0[ng].x);
+          dmma884(acc[ng][rb][1], acc[ng][rb][3], a[rb], b0[ng].y);
         }
       }
     }
 #pragma unroll
-    for (int ng = 0; ng < NGW; ++ng) bcur[ng] = bnxt[ng];
+    for (int ng = 0; ng < NGW; ++ng) { b0[ng] = b1[ng]; b1[ng] = b2[ng]; }
   }
 }
 
@@ -156,13 +164,13 @@ __device__ __forceinline__ void store_tile(const double (&acc)[NGW][RB][4], doub
 
 // ---------------------------------------------------------------------------------------------
 // S (lower 32x32 tiles) += tile^T tile  over the BT rows, flushed with coalesced RED.add.f64.
-template <int RB>
+template <int RB, int NW>
 __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
                                            int warp, int lane) {
   const int g = lane >> 2, q = lane & 3;
   const int nt = Mp >> 5;
   const int ntiles = nt * (nt + 1) / 2;
-  for (int tix = warp; tix < ntiles; tix += FFVD_NWARPS) {
+  for (int tix = warp; tix < ntiles; tix += NW) {
     // decode (ti >= tj) from the linear lower-triangular index
     int ti = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
     while ((ti + 1) * (ti + 2) / 2 <= tix) ++ti;
@@ -187,15 +195,22 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
     }
+    // transpose 4 rows at a time through the per-warp staging buffer, flush with coalesced REDs
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<double2*>(stage_w + g * 40 + 8 * j + 2 * q) = make_double2(c[i][j][0], c[i][j][1]);
-      __syncwarp();
+      for (int h = 0; h < 2; ++h) {
+        __syncwarp();
+        if ((g >> 2) == h) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) atomicAdd(S + (size_t)(m0 + 8 * i + r) * Mp + n0 + lane, stage_w[r * 40 + lane]);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(stage_w + (g & 3) * 40 + 8 * j + 2 * q) = make_double2(c[i][j][0], c[i][j][1]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          atomicAdd(S + (size_t)(m0 + 8 * i + 4 * h + r) * Mp + n0 + lane, stage_w[r * 40 + lane]);
+      }
     }
   }
 }
@@ -205,7 +220,7 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
 //   WtX~ = W^T [Xc,1]   (Mp x (Din+1))   ->  dJ/dZ rows
 //   WZ~  = W [Z,1]      (BT x (Din+1))   ->  dJ/dXc rows
 // SE: W = kbar*k;  Linear: W = kbar (the factor v is applied here).
-template <int KIND, int RB>
+template <int KIND, int RB, int NW>
 __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevProblem& P, int d, double v, double* gXs,
                                            int t0, int nvalid, int warp, int lane, int tid) {
   const int g = lane >> 2, q = lane & 3;
@@ -213,13 +228,14 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
   const int nbx = (Din + 1 + 7) >> 3;           // n-blocks covering Din+1 columns
   const int BT = 8 * RB;
   const double* tile = sm.tile;
-  // ---- W^T X~ : warp owns m-blocks warp, warp+8, ...
-  {
+  // ---- W^T X~ : 8 warps own m-blocks w, w+8, ...  (NW == 16: warps 8..15, concurrently with W Z~ on warps 0..7)
+  if (NW == 8 || warp >= 8) {
+    const int wA = warp & 7;
     const int nbc = Din >> 3, qc = (Din & 7) >> 1, ec = Din & 1;
     double lacc[4][2];
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) lacc[nb][0] = lacc[nb][1] = 0.0;
-    for (int mb = warp; mb < (Mp >> 3); mb += FFVD_NWARPS) {
+    for (int mb = wA; mb < (Mp >> 3); mb += 8) {
       double c[4][2];
 #pragma unroll
       for (int nb = 0; nb < 4; ++nb) c[nb][0] = c[nb][1] = 0.0;
@@ -277,11 +293,11 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
         }
     }
   }
-  // ---- W Z~ : warp -> (row block rb, k slice ks)
+  // ---- W Z~ : warp (0..7) -> (row block rb, k slice ks)
   {
-    constexpr int KS = FFVD_NWARPS / RB > 0 ? FFVD_NWARPS / RB : 1;
+    constexpr int KS = 8 / RB > 0 ? 8 / RB : 1;
     const int rb = warp % RB, ks = warp / RB;
-    if (ks < KS) {
+    if (warp < 8 && ks < KS) {
       const int klen = Mp / KS;
       double c[4][2];
 #pragma unroll
@@ -294,14 +310,8 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           a[u] = tile[(8 * rb + g) * lda + k0 + 4 * u + q];
           const int m = k0 + 4 * u + q;
 #pragma unroll
-          for (int nb = 0; nb < 4; ++nb) {
-            b[u][nb] = 0.0;
-            if (nb < nbx) {
-              const int jd = 8 * nb + g;
-              if (jd < Din) b[u][nb] = __ldg(P.ZT + (size_t)jd * Mp + m);
-              else if (jd == Din) b[u][nb] = (m < M) ? 1.0 : 0.0;
-            }
-          }
+          for (int nb = 0; nb < 4; ++nb)      // ZT has 32 rows: Z^T, a row of ones (m < M) at Din, zeros above
+            b[u][nb] = (nb < nbx) ? __ldg(P.ZT + (size_t)(8 * nb + g) * Mp + m) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -319,7 +329,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
     }
     __syncthreads();
     double vacc = 0.0;
-    for (int idx = tid; idx < BT * 32; idx += FFVD_NTHREADS) {
+    for (int idx = tid; idx < BT * 32; idx += 32 * NW) {
       const int r = idx >> 5, jd = idx & 31;
       if (jd < Din && r < nvalid) {
         double wz = 0.0, rs = 0.0;
@@ -347,12 +357,20 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int RB, int NGW, int MODE, int MINB>
-__global__ void __launch_bounds__(FFVD_NTHREADS, MINB)
-fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_items) {
+// NW warps per CTA (8 or 16).  Warp w owns the column groups of "column warp" wc = w & 7 and the
+// row blocks [wr*RBW, (wr+1)*RBW) with wr = w >> 3, RBW = RB / (NW/8): 16 warps share one tile and
+// double the latency-hiding capacity of the SM without shrinking the tile.
+template <int KIND, int RB, int NGW, int MODE, int NW>
+__global__ void __launch_bounds__(32 * NW, 1)
+fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_items, double* __restrict__ kscr_base) {
   extern __shared__ __align__(16) double smem_raw[];
   constexpr int BT = 8 * RB;
+  constexpr int NTH = 32 * NW;
+  constexpr int RBW = RB / (NW / 8);
+  static_assert(RBW >= 1 && RBW * (NW / 8) == RB, "RB must be divisible by the row split");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int wc = warp & 7, row0 = (warp >> 3) * 8 * RBW;
+  double* kscr = kscr_base + (size_t)blockIdx.x * BT * probs[0].Mp;     // per-CTA K-tile scratch (BT x Mp)
 
   for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
     // ---- decode item -> (problem, d, s, tile); d is the slowest index inside a problem
@@ -381,7 +399,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     {
       double* p = smem_raw;
       sm.tile = p; p += (size_t)BT * lda;
-      sm.stage = p; p += 8 * 8 * 40;
+      sm.stage = p; p += NW * 4 * 40;
       sm.xs = p; p += ((BT + 1) * FFVD_XLD + 1) & ~1;
       sm.xsc = p; p += (BT * FFVD_XLD + 1) & ~1;
       sm.us = p; p += Mp;
@@ -408,7 +426,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       if (tid < 32) { sm.small[tid] = il2; sm.small[32 + tid] = sil; }
       if (tid < 40) sm.red[tid] = 0.0;
     }
-    for (int idx = tid; idx < (BT + 1) * FFVD_XCOLS; idx += FFVD_NTHREADS) {
+    for (int idx = tid; idx < (BT + 1) * FFVD_XCOLS; idx += NTH) {
       const int r = idx >> 5, c = idx & 31;
       const int t = t0 + r;
       double val = 0.0;
@@ -420,7 +438,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       if (r > nvalid && c < Din) val = 0.0;   // keep padded rows inert (row nvalid is x_{t+1} of the last valid row)
       sm.xs[r * FFVD_XLD + c] = val;
     }
-    for (int j = tid; j < Mp; j += FFVD_NTHREADS) {
+    for (int j = tid; j < Mp; j += NTH) {
       double u = 0.0;
       if (j < M) {
         if (MODE == MODE_UNCOLLAPSED || MODE == MODE_FORWARD || MODE == MODE_COND) u = P.U[(size_t)j * D + d];
@@ -430,7 +448,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
     __syncthreads();
     if (KIND == 0) {
-      for (int idx = tid; idx < BT * FFVD_XCOLS; idx += FFVD_NTHREADS) {
+      for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
         const int r = idx >> 5, c = idx & 31;
         sm.xsc[r * FFVD_XLD + c] = (c < Din) ? sm.xs[r * FFVD_XLD + c] * sm.small[32 + c] : 0.0;
       }
@@ -441,14 +459,20 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     {
 #pragma unroll
       for (int ng = 0; ng < NGW; ++ng) {
-        double kv[RB][4];
-        const int jb = 16 * group_index(warp, ng) + 4 * q;
-        compute_k_group<KIND, RB>(kv, sm, P.ZT, Mp, Din, v, jb, g, M, nvalid);
+        double kv[RBW][4];
+        const int jb = 16 * group_index(wc, ng) + 4 * q;
+        compute_k_group<KIND, RBW>(kv, sm, P.ZT, Mp, Din, v, jb, g, M, nvalid, row0);
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) {
-          double* p = sm.tile + (8 * rb + g) * lda + jb;
+        for (int rb = 0; rb < RBW; ++rb) {
+          double* p = sm.tile + (row0 + 8 * rb + g) * lda + jb;
           *reinterpret_cast<double2*>(p) = make_double2(kv[rb][0], kv[rb][1]);
           *reinterpret_cast<double2*>(p + 2) = make_double2(kv[rb][2], kv[rb][3]);
+          if (KIND == 0 && MODE == MODE_UNCOLLAPSED) {
+            // keep a copy of the K tile in this CTA's L2-resident scratch: it is needed again for W = Kbar o K
+            double* s = kscr + (size_t)(row0 + 8 * rb + g) * Mp + jb;
+            *reinterpret_cast<double2*>(s) = make_double2(kv[rb][0], kv[rb][1]);
+            *reinterpret_cast<double2*>(s + 2) = make_double2(kv[rb][2], kv[rb][3]);
+          }
         }
       }
     }
@@ -456,44 +480,45 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 
     const double* LinvT = P.LinvT + (size_t)dh * Mp * Mp;
     const double* Linv = P.Linv + (size_t)dh * Mp * Mp;
-    double acc[NGW][RB][4];
+    double acc[NGW][RBW][4];
+    double* wtile = sm.tile + (size_t)row0 * lda;     // this warp's rows of the shared tile
 
     if (MODE != MODE_COLLAPSED_P2) {
       // ---- P2: A = K L^{-T}   (rows a_t = L^{-1} k_t)
-      tile_gemm<RB, NGW, +1>(acc, sm.tile, lda, LinvT, Mp, warp, g, q,
-                             [](double x, int, int) { return x; });
+      tile_gemm<RBW, NGW, +1>(acc, wtile, lda, LinvT, Mp, wc, g, q,
+                              [](double x, int, int) { return x; });
       // row partial sums: a.u and a.a
       {
-        double su[RB], sa[RB];
+        double su[RBW], sa[RBW];
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) su[rb] = sa[rb] = 0.0;
+        for (int rb = 0; rb < RBW; ++rb) su[rb] = sa[rb] = 0.0;
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
-          const int jb = 16 * group_index(warp, ng) + 4 * q;
+          const int jb = 16 * group_index(wc, ng) + 4 * q;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const double u = sm.us[jb + c];
 #pragma unroll
-            for (int rb = 0; rb < RB; ++rb) {
+            for (int rb = 0; rb < RBW; ++rb) {
               su[rb] = fma(acc[ng][rb][c], u, su[rb]);
               sa[rb] = fma(acc[ng][rb][c], acc[ng][rb][c], sa[rb]);
             }
           }
         }
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) {
+        for (int rb = 0; rb < RBW; ++rb) {
           su[rb] += __shfl_xor_sync(0xffffffffu, su[rb], 1);
           su[rb] += __shfl_xor_sync(0xffffffffu, su[rb], 2);
           sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 1);
           sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 2);
           if (q == 0) {
-            sm.rowpart[(0 * 8 + warp) * 64 + 8 * rb + g] = su[rb];
-            sm.rowpart[(1 * 8 + warp) * 64 + 8 * rb + g] = sa[rb];
+            sm.rowpart[(0 * 8 + wc) * 64 + row0 + 8 * rb + g] = su[rb];
+            sm.rowpart[(1 * 8 + wc) * 64 + row0 + 8 * rb + g] = sa[rb];
           }
         }
       }
       __syncthreads();          // everyone is done reading K from the tile
-      if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RB, NGW>(acc, sm.tile, lda, warp, g, q);
+      if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
       // ---- per-row statistics (threads 0..BT-1)
       if (tid < 64) {
         double jxq = 0.0, jtr = 0.0, gq = 0.0, gvd = 0.0;
@@ -597,17 +622,17 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_UNCOLLAPSED || MODE == MODE_COLLAPSED_P1) {
       // ---- ubar_j = sum_r e_r a_rj  (collapsed pass 1: b_j = sum_r delta_r f_rj), from registers
       {
-        double er[RB];
+        double er[RBW];
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb) er[rb] = sm.es[8 * rb + g];
+        for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g];
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
-          const int jb = 16 * group_index(warp, ng) + 4 * q;
+          const int jb = 16 * group_index(wc, ng) + 4 * q;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             double t = 0.0;
 #pragma unroll
-            for (int rb = 0; rb < RB; ++rb) t = fma(er[rb], acc[ng][rb][c], t);
+            for (int rb = 0; rb < RBW; ++rb) t = fma(er[rb], acc[ng][rb][c], t);
             t += __shfl_xor_sync(0xffffffffu, t, 4);
             t += __shfl_xor_sync(0xffffffffu, t, 8);
             t += __shfl_xor_sync(0xffffffffu, t, 16);
@@ -617,33 +642,33 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
       // ---- S += A^T A
       double* Sd = P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp;
-      syrk_flush<RB>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
+      syrk_flush<RB, NW>(sm.tile, lda, Mp, Sd, sm.stage + warp * 4 * 40, warp, lane);
     }
 
     if (MODE == MODE_UNCOLLAPSED) {
       // ---- P4: Kbar = Abar L^{-1},  abar_rj = e_r u_j + a_rj / Q  formed on the fly
-      double er[RB];
+      double er[RBW];
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) er[rb] = sm.es[8 * rb + g] * Q;      // residual = e * Q
+      for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g] * Q;      // residual = e * Q
       const double* us = sm.us;
-      tile_gemm<RB, NGW, -1>(acc, sm.tile, lda, Linv, Mp, warp, g, q,
-                             [&](double x, int rb, int k) { return fma(er[rb], us[k], x); });
+      tile_gemm<RBW, NGW, -1>(acc, wtile, lda, Linv, Mp, wc, g, q,
+                              [&](double x, int rb, int k) { return fma(er[rb], us[k], x); });
 #pragma unroll
       for (int ng = 0; ng < NGW; ++ng)
 #pragma unroll
-        for (int rb = 0; rb < RB; ++rb)
+        for (int rb = 0; rb < RBW; ++rb)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[ng][rb][c] *= invQ;
     } else if (MODE == MODE_COLLAPSED_P2) {
       // ---- Kbar = K N + delta w'^T ; also dbar_r = k_r . w'
-      tile_gemm<RB, NGW, 0>(acc, sm.tile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, warp, g, q,
-                            [](double x, int, int) { return x; });
+      tile_gemm<RBW, NGW, 0>(acc, wtile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, g, q,
+                             [](double x, int, int) { return x; });
     }
 
     if (MODE == MODE_UNCOLLAPSED || MODE == MODE_COLLAPSED_P2) {
       if (MODE == MODE_COLLAPSED_P2) {
         // delta_r and dbar_r = sum_j k_rj w'_j (from the K tile still in shared memory)
-        for (int r = warp; r < BT; r += FFVD_NWARPS) {
+        for (int r = warp; r < BT; r += NW) {
           double t = 0.0;
           for (int j = lane; j < Mp; j += 32) t = fma(sm.tile[r * lda + j], sm.us[j], t);
           t = warp_sum(t);
@@ -681,35 +706,41 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       {
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
-          const int jb = 16 * group_index(warp, ng) + 4 * q;
-          double kv[RB][4];
+          const int jb = 16 * group_index(wc, ng) + 4 * q;
+          double kv[RBW][4];
           if (KIND == 0) {
             if (MODE == MODE_COLLAPSED_P2) {
 #pragma unroll
-              for (int rb = 0; rb < RB; ++rb) {
-                const double* p = sm.tile + (8 * rb + g) * lda + jb;
+              for (int rb = 0; rb < RBW; ++rb) {
+                const double* p = wtile + (8 * rb + g) * lda + jb;
                 const double2 k01 = *reinterpret_cast<const double2*>(p);
                 const double2 k23 = *reinterpret_cast<const double2*>(p + 2);
                 kv[rb][0] = k01.x; kv[rb][1] = k01.y; kv[rb][2] = k23.x; kv[rb][3] = k23.y;
               }
             } else {
-              compute_k_group<KIND, RB>(kv, sm, P.ZT, Mp, Din, v, jb, g, M, nvalid);
+#pragma unroll
+              for (int rb = 0; rb < RBW; ++rb) {
+                const double* s = kscr + (size_t)(row0 + 8 * rb + g) * Mp + jb;
+                const double2 k01 = __ldcg(reinterpret_cast<const double2*>(s));
+                const double2 k23 = __ldcg(reinterpret_cast<const double2*>(s + 2));
+                kv[rb][0] = k01.x; kv[rb][1] = k01.y; kv[rb][2] = k23.x; kv[rb][3] = k23.y;
+              }
             }
           }
 #pragma unroll
-          for (int rb = 0; rb < RB; ++rb)
+          for (int rb = 0; rb < RBW; ++rb)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               double kb = acc[ng][rb][c];
-              if (MODE == MODE_COLLAPSED_P2) kb = fma(sm.es[8 * rb + g], sm.us[jb + c], kb);
-              acc[ng][rb][c] = (KIND == 0) ? kb * kv[rb][c] : ((jb + c < M && 8 * rb + g < nvalid) ? kb : 0.0);
+              if (MODE == MODE_COLLAPSED_P2) kb = fma(sm.es[row0 + 8 * rb + g], sm.us[jb + c], kb);
+              acc[ng][rb][c] = (KIND == 0) ? kb * kv[rb][c] : ((jb + c < M && row0 + 8 * rb + g < nvalid) ? kb : 0.0);
             }
         }
         __syncthreads();        // all warps done reading A (GEMM2 / SYRK) or K (pass 2)
-        store_tile<RB, NGW>(acc, sm.tile, lda, warp, g, q);
+        store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
       }
       __syncthreads();
-      contract_W<KIND, RB>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid);
+      contract_W<KIND, RB, NW>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid);
     }
 
     // ---- flush block-level scalars

@@ -87,9 +87,12 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
   double* rowbuf = sh + Mp;
   double* Asm = sh + 2 * Mp;
   if (d == 0) {
-    for (int idx = tid; idx < Din * Mp; idx += nth) {
+    // Z~^T, 32 rows: Z^T (zero padded), then a row of ones over the valid inducing points, then zeros
+    for (int idx = tid; idx < 32 * Mp; idx += nth) {
       const int jd = idx / Mp, m = idx % Mp;
-      P.ZT[idx] = (m < M) ? P.Z[(size_t)m * Din + jd] : 0.0;
+      double zv = 0.0;
+      if (m < M) zv = (jd < Din) ? P.Z[(size_t)m * Din + jd] : (jd == Din ? 1.0 : 0.0);
+      P.ZT[idx] = zv;
     }
   }
   double* Lt = P.LinvT + (size_t)d * Mp * Mp;   // global scratch for L when it does not fit in smem

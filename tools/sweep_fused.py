@@ -1,5 +1,5 @@
 """Time the fused uncollapsed kernel for the tile configurations named on the command line.
-usage: python tools/sweep_fused.py T M D S  rb:minb [rb:minb ...]"""
+usage: python tools/sweep_fused.py T M D S  rb:nw [rb:nw ...]"""
 import os, subprocess, sys, json
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
     import numpy as np, torch
@@ -25,13 +25,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     e1.record(); torch.cuda.synchronize()
     ms, n = ctx.fused_time(True)
     units = S * T * D
-    print(json.dumps(dict(cfg=os.environ.get("FFVD_RB", "") + ":" + os.environ.get("FFVD_MINB", ""), fused_ms=ms / n, total_ms=e0.elapsed_time(e1) / 3,
+    print(json.dumps(dict(cfg=os.environ.get("FFVD_RB", "") + ":" + os.environ.get("FFVD_NW", ""), fused_ms=ms / n, total_ms=e0.elapsed_time(e1) / 3,
                           alg_tflops=algorithmic_flops_per_unit(M, D + 1) * units / (ms / n) * 1e-9, nll=float(out["nll"].sum()),
                           gZ=float(out["g_Z"].abs().sum()), gX=float(out["g_X"].abs().sum()))))
 else:
     T, M, D, S = sys.argv[1:5]
     for cfg in sys.argv[5:]:
-        rb, minb = cfg.split(":")
-        env = dict(os.environ, FFVD_RB=rb, FFVD_MINB=minb)
+        rb, nw = cfg.split(":")
+        env = dict(os.environ, FFVD_RB=rb, FFVD_NW=nw)
         r = subprocess.run([sys.executable, __file__, "--child", T, M, D, S], env=env, capture_output=True, text=True)
         print(r.stdout.strip() or r.stderr.strip()[-400:], flush=True)
