@@ -12,6 +12,7 @@
 #include "elementwise.cuh"
 #include "fused.cuh"
 #include "prep_post.cuh"
+#include "blocked_chol.cuh"
 
 using namespace ffvd;
 
@@ -220,7 +221,8 @@ struct Layout {
   long long sumS;
   bool collapsed;
   size_t off_ZT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
-      off_small, off_terms, off_status, off_utmp, off_kscr, total;
+      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, total;
+  int nfac;                        // matrices in the blocked-factorisation pools: nprob * max(nk, nb)
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
   size_t small_per;                // doubles of small accumulators per problem
 };
@@ -239,6 +241,9 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   L.off_Linv = take((size_t)nprob * nk * mm);
   L.off_LinvT = take((size_t)nprob * nk * mm);
   L.off_utmp = take((size_t)nprob * M * D * 8);
+  L.nfac = nprob * (nb > nk ? nb : nk);
+  L.off_Lfac = take((size_t)nprob * nk * mm);
+  L.off_Dinv = take((size_t)L.nfac * (Mp / 64) * 64 * 64 * 8);
   L.off_Wk = take(need_acc ? (size_t)nprob * nb * mm : 0);
   L.off_Nmat = take(collapsed ? (size_t)nprob * nb * mm : 0);
   L.off_Hx = take(collapsed ? (size_t)nprob * nb * mm : 0);
@@ -253,6 +258,7 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   L.off_small = take((size_t)nprob * L.small_per * 8);
   L.off_terms = take((size_t)sumS * FFVD_NTERMS_RAW * 8);
   L.off_status = take((size_t)nprob * (nb > nk ? nb : nk) * sizeof(int));
+  L.off_status2 = take((size_t)L.nfac * sizeof(int));
   L.zero_end = o;
   L.total = o;
   return L;
@@ -277,7 +283,7 @@ static int ensure_arena(ffvd_ctx* c, const Layout& L) {
     CUDA_TRY(cudaMalloc((void**)&c->d_outs, sizeof(OutPtrs) * L.nprob));
     c->probs_cap = L.nprob;
   }
-  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk);
+  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk) + (size_t)L.nfac;
   if (c->h_status_cap < ns) {
     if (c->h_status) CUDA_TRY(cudaFreeHost(c->h_status));
     CUDA_TRY(cudaMallocHost((void**)&c->h_status, ns * sizeof(int)));
@@ -318,11 +324,18 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
 // Tile configuration per padded M: RB row blocks (BT = 8*RB time steps per tile) and NW warps per CTA.
 // Overridable for experiments with FFVD_RB / FFVD_NW (only the combinations instantiated below exist).
 struct FusedCfg { int rb, nw; };
+// supported padded sizes: 128 * {1,2,3,4,6,8,12,16}
+static int pad_M(int M) {
+  static const int sizes[] = {128, 256, 384, 512, 768, 1024, 1536, 2048};
+  for (int s : sizes)
+    if (M <= s) return s;
+  return -1;
+}
 static FusedCfg fused_cfg(int Mp) {
   FusedCfg cfg;
   const int ngw = Mp / 128;
-  cfg.rb = (ngw <= 2) ? 8 : 4;
-  cfg.nw = 8;
+  cfg.rb = (ngw <= 2) ? 8 : (ngw <= 4 ? 4 : (ngw <= 8 ? 2 : 1));
+  cfg.nw = (ngw == 1) ? 16 : 8;
   if (const char* e = getenv("FFVD_RB")) cfg.rb = atoi(e);
   if (const char* e = getenv("FFVD_NW")) cfg.nw = atoi(e);
   return cfg;
@@ -335,12 +348,10 @@ static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int npro
   void (*kern)(const DevProblem*, int, long long, double*) = nullptr;
 #define FFVD_PICK(RB_, NGW_, NW_) \
   if (ngw == NGW_ && cfg.rb == RB_ && cfg.nw == NW_) kern = fused_kernel<KIND, RB_, NGW_, MODE, NW_>;
-  FFVD_PICK(8, 1, 8) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 3, 8) FFVD_PICK(4, 4, 8)
-  if (KIND == 0 && MODE == MODE_UNCOLLAPSED) {
-    FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 16) FFVD_PICK(4, 3, 16) FFVD_PICK(4, 4, 16)
-  }
+  FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 3, 8) FFVD_PICK(4, 4, 8)
+  FFVD_PICK(2, 6, 8) FFVD_PICK(2, 8, 8) FFVD_PICK(1, 12, 8) FFVD_PICK(1, 16, 8)
+  if (KIND == 0 && MODE == MODE_UNCOLLAPSED) { FFVD_PICK(8, 1, 8) }
 #undef FFVD_PICK
-  if (ngw > 4) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
   if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_NW)");
   const int RB = cfg.rb;
   const size_t smem = fused_smem_bytes(RB, Mp, cfg.nw);
@@ -360,14 +371,28 @@ static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int npro
 }
 static int rb_of(int Mp) { return fused_cfg(Mp).rb; }
 
+static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X, double* XT, int* status, int nbatch,
+                                 int M, int Mp);
+
+static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
+  if (const char* e = getenv("FFVD_BLOCKED_CHOL")) return atoi(e) != 0;
+  const size_t full = (size_t)2 * Mp * 8 + (size_t)M * (M + 1) * 8;
+  return (int)full > c->max_smem;          // single-CTA shared-memory path only while the matrix fits
+}
+
 template <int KIND>
 static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter) {
-  size_t smem = (size_t)2 * L.Mp * 8;
-  const size_t full = smem + (size_t)L.M * (L.M + 1) * 8;
-  int use_smem = 0;
-  if ((int)full <= c->max_smem) { use_smem = 1; smem = full; }
+  if (use_blocked(c, L.M, L.Mp)) {
+    double* Lfac = (double*)(c->arena + L.off_Lfac);
+    const size_t nel = (size_t)L.Mp * L.Mp > (size_t)32 * L.Mp ? (size_t)L.Mp * L.Mp : (size_t)32 * L.Mp;
+    kzz_fill_kernel<KIND><<<dim3((unsigned)((nel + 255) / 256), L.nk, L.nprob), 256, 0, c->stream>>>(c->d_probs, Lfac, jitter);
+    c->launches++;
+    return blocked_factor_invert(c, Lfac, (double*)(c->arena + L.off_Dinv), (double*)(c->arena + L.off_Linv),
+                                 (double*)(c->arena + L.off_LinvT), (int*)(c->arena + L.off_status2), L.nprob * L.nk, L.M, L.Mp);
+  }
+  size_t smem = (size_t)2 * L.Mp * 8 + (size_t)L.M * (L.M + 1) * 8;
   CUDA_TRY(cudaFuncSetAttribute(kzz_prep_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kzz_prep_kernel<KIND><<<dim3(L.nk, L.nprob), 512, smem, c->stream>>>(c->d_probs, jitter, use_smem);
+  kzz_prep_kernel<KIND><<<dim3(L.nk, L.nprob), 512, smem, c->stream>>>(c->d_probs, jitter, 1);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return FFVD_OK;
@@ -382,16 +407,38 @@ static int launch_bgemm(ffvd_ctx* c, double* C, const double* A, const double* B
 }
 
 static int check_status(ffvd_ctx* c, const Layout& L) {
-  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk);
-  CUDA_TRY(cudaMemcpyAsync(c->h_status, c->arena + L.off_status, ns * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  const size_t n1 = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk), n2 = (size_t)L.nfac;
+  CUDA_TRY(cudaMemcpyAsync(c->h_status, c->arena + L.off_status, n1 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_status + n1, c->arena + L.off_status2, n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  for (size_t i = 0; i < ns; ++i)
+  for (size_t i = 0; i < n1 + n2; ++i)
     if (c->h_status[i] != 0) {
       char buf[160];
-      snprintf(buf, sizeof buf, "Cholesky failed: matrix %zu not positive definite at pivot %d", i, c->h_status[i]);
+      snprintf(buf, sizeof buf, "Cholesky failed: matrix %zu not positive definite at pivot %d", i < n1 ? i : i - n1, c->h_status[i]);
       g_last_error = buf;
       return c->h_status[i];
     }
+  return FFVD_OK;
+}
+
+// Blocked Cholesky + inverse of nbatch matrices: A (in: SPD, lower filled; out: L), X <- L^{-1}, XT <- L^{-T}.
+static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X, double* XT, int* status, int nbatch,
+                                 int M, int Mp) {
+  const int nblk = Mp / 64;
+  const size_t sm_potrf = (size_t)2 * 64 * 65 * 8, sm_trtri = (size_t)64 * 68 * 8;
+  CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf));
+  CUDA_TRY(cudaFuncSetAttribute(trtri_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trtri));
+  for (int kb = 0; kb < nblk; ++kb) {
+    potrf_diag_kernel<<<nbatch, 256, sm_potrf, c->stream>>>(A, Dinv, status, kb, M, Mp); c->launches++;
+    const int rem = nblk - kb - 1;
+    if (rem > 0) {
+      trsm_panel_kernel<<<dim3(rem, nbatch), 256, 0, c->stream>>>(A, Dinv, kb, Mp); c->launches++;
+      syrk_trailing_kernel<<<dim3(rem * (rem + 1) / 2, nbatch), 256, 0, c->stream>>>(A, kb, Mp); c->launches++;
+    }
+  }
+  trtri_column_kernel<<<dim3(nblk, nbatch), 256, sm_trtri, c->stream>>>(A, Dinv, X, Mp); c->launches++;
+  transpose_pad_kernel<<<dim3(Mp / 32, Mp / 32, nbatch), dim3(32, 8), 0, c->stream>>>(X, XT, M, Mp); c->launches++;
+  CUDA_TRY(cudaGetLastError());
   return FFVD_OK;
 }
 
@@ -478,8 +525,8 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     sumS += pt[p].S;
   }
   const int M = pt[0].M, D = pt[0].D, Din = pt[0].Din, Dy = pt[0].Dy;
-  const int Mp = (int)align_up(M, 128);
-  if (Mp > 512) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
+  const int Mp = pad_M(M);
+  if (Mp < 0) return fail(FFVD_E_LIMIT, "M > 2048 is not supported by this build");
   const bool no_grads = (flags & FFVD_FLAG_NO_GRADS) != 0;
   const int nb = collapsed ? pt[0].S * D : D;
   Layout L = make_layout(nprob, nb, D, D, M, Mp, Din, Dy, sumS, collapsed != 0, true);
@@ -534,7 +581,13 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   } else {
     TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, c->d_probs, nprob, total_items)));
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 1); c->launches++;
-    collapsed_chol_kernel<<<dim3(nb, nprob), 512, (size_t)2 * Mp * 8, c->stream>>>(c->d_probs); c->launches++;
+    if (use_blocked(c, M, Mp)) {
+      collapsed_fill_kernel<<<dim3((unsigned)(((size_t)Mp * Mp + 255) / 256), nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+      TRY(blocked_factor_invert(c, Wk, (double*)(c->arena + L.off_Dinv), Hx, HxT, (int*)(c->arena + L.off_status2), nz, M, Mp));
+      collapsed_logdet_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    } else {
+      collapsed_chol_kernel<<<dim3(nb, nprob), 512, (size_t)2 * Mp * 8, c->stream>>>(c->d_probs); c->launches++;
+    }
     if (!no_grads) {
       TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));          // H^{-1} = L_H^{-T} L_H^{-1}
       collapsed_vec_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
@@ -649,7 +702,8 @@ static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, co
                        Layout& L, DevProblem& P) {
   const int M = (int)tZ.shape[0], Din = (int)tZ.shape[1];
   if (Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
-  const int Mp = (int)align_up(M, 128);
+  const int Mp = pad_M(M);
+  if (Mp < 0) return fail(FFVD_E_LIMIT, "M > 2048 is not supported by this build");
   L = make_layout(1, nk, nk, R, M, Mp, Din, 1, 1, false, false);
   TRY(ensure_arena(c, L));
   memset(&P, 0, sizeof P);
@@ -731,7 +785,6 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
   if (N == 0) return call.finish();
   Layout L; DevProblem P;
   TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P));
-  if (P.Mp > 512) return fail(FFVD_E_LIMIT, "M > 512 is not supported by the fused kernel in this build");
   const int RB = rb_of(P.Mp), BT = 8 * RB;
   P.hs = shared_kernel ? 0 : 1;
   P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;

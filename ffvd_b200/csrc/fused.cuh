@@ -90,15 +90,15 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
 // TRI = +1: B upper triangular (B[k][n] != 0 only for k <= n);  -1: lower;  0: dense.
 // Lane (g,q) of the warp ends up with rows 8*rb+g, columns 16*group+4q+{0,1,2,3}.
 template <int RB, int NGW, int TRI, class AOp>
-__device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const double* tile, int lda,
-                                          const double* __restrict__ B, int Mp, int warp, int g, int q, AOp aop) {
+__device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const double* tile, int lda,
+                                                const double* __restrict__ B, int Mp, int warp, int ng0, int g, int q, AOp aop) {
   // per-group active k range [kb, ke) (multiples of 4) and running B pointers
   int kb[NGW], ke[NGW];
   const double* bp[NGW];
   int kbeg = Mp, kend = 0;
 #pragma unroll
   for (int ng = 0; ng < NGW; ++ng) {
-    const int j0 = 16 * group_index(warp, ng);
+    const int j0 = 16 * group_index(warp, ng0 + ng);
     kb[ng] = (TRI < 0) ? j0 : 0;
     ke[ng] = (TRI > 0) ? j0 + 16 : Mp;
     kbeg = min(kbeg, kb[ng]);
@@ -143,6 +143,22 @@ __device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const doubl
     }
 #pragma unroll
     for (int ng = 0; ng < NGW; ++ng) { b0[ng] = b1[ng]; b1[ng] = b2[ng]; }
+  }
+}
+
+// Column groups are processed at most 4 at a time so that the B-fragment prefetch ring and the running
+// pointers stay in registers for large M (NGW up to 16); the A fragments are re-read from shared memory per chunk.
+template <int RB, int NGW, int TRI, class AOp>
+__device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const double* tile, int lda,
+                                          const double* __restrict__ B, int Mp, int warp, int g, int q, AOp aop) {
+  if constexpr (NGW <= 4) {
+    tile_gemm_chunk<RB, NGW, TRI>(acc, tile, lda, B, Mp, warp, 0, g, q, aop);
+  } else {
+    static_assert(NGW % 2 == 0, "large NGW must be even");
+    constexpr int CH = (NGW % 4 == 0) ? 4 : 2;
+#pragma unroll
+    for (int c0 = 0; c0 < NGW; c0 += CH)
+      tile_gemm_chunk<RB, CH, TRI>(reinterpret_cast<double(&)[CH][RB][4]>(acc[c0]), tile, lda, B, Mp, warp, c0, g, q, aop);
   }
 }
 

@@ -125,6 +125,76 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
   tri_inverse(A, lda, M, P.Linv + (size_t)d * Mp * Mp, Lt, Mp, rowbuf);
 }
 
+// Blocked path (M too large for shared memory): fill K(Z,Z) + jitter I (lower triangle, identity on the
+// padded diagonal) into Lfac[b], b = problem * nk + d, and write Z~^T.   grid (ceil(Mp*Mp/256), nk, nprob)
+template <int KIND>
+__global__ void __launch_bounds__(256) kzz_fill_kernel(const DevProblem* __restrict__ probs, double* __restrict__ Lfac, double jitter) {
+  const DevProblem& P = probs[blockIdx.z];
+  const int d = blockIdx.y, M = P.M, Mp = P.Mp, Din = P.Din, nk = gridDim.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d == 0 && idx < 32LL * Mp) {
+    const int jd = (int)(idx / Mp), m = (int)(idx % Mp);
+    double zv = 0.0;
+    if (m < M) zv = (jd < Din) ? P.Z[(size_t)m * Din + jd] : (jd == Din ? 1.0 : 0.0);
+    P.ZT[idx] = zv;
+  }
+  if (idx >= (long long)Mp * Mp) return;
+  const int m = (int)(idx / Mp), n = (int)(idx % Mp);
+  double k = 0.0;
+  if (n <= m) {
+    if (m < M) {
+      double s = 0.0;
+      for (int jd = 0; jd < Din; ++jd) {
+        const double a = P.Z[(size_t)m * Din + jd], b = P.Z[(size_t)n * Din + jd];
+        if (KIND == 0) {
+          const double il = exp(-P.logl[(size_t)d * Din + jd]);
+          const double t = a * il - b * il;
+          s = fma(t, t, s);
+        } else {
+          s = fma(a, b, s);
+        }
+      }
+      const double v = exp(P.logv[d]);
+      k = (KIND == 0) ? v * exp(-0.5 * s) : v * s;
+      if (m == n) k += jitter;
+    } else if (m == n) {
+      k = 1.0;
+    }
+  }
+  Lfac[((size_t)blockIdx.z * nk + d) * Mp * Mp + idx] = k;
+}
+
+// Collapsed bound, blocked path: H = S/Q + I into Wk[b] (identity on the padding).  grid (ceil(Mp*Mp/256), nb, nprob)
+__global__ void __launch_bounds__(256) collapsed_fill_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.z];
+  const int b = blockIdx.y, d = b % P.D, M = P.M, Mp = P.Mp;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Mp * Mp) return;
+  const int m = (int)(idx / Mp), n = (int)(idx % Mp);
+  double h = 0.0;
+  if (m < M && n < M) h = P.Sacc[(size_t)b * Mp * Mp + idx] * exp(-P.logQ[d]) + (m == n ? 1.0 : 0.0);
+  else if (m == n) h = 1.0;
+  P.Wk[(size_t)b * Mp * Mp + idx] = h;
+}
+
+// -1/2 logdet H = -sum_i log L_ii from the blocked factor in Wk[b].  grid (nb, nprob); block 256
+__global__ void __launch_bounds__(256) collapsed_logdet_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  const int b = blockIdx.x, s = b / P.D, M = P.M, Mp = P.Mp;
+  const double* L = P.Wk + (size_t)b * Mp * Mp;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < M; i += 256) t += log(L[(size_t)i * Mp + i]);
+  t = warp_sum(t);
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -tot);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // C[b] = alpha * A[b] * B[b]  (all n x n row-major, ld = n, n multiple of 64), FP64 DMMA.
 // grid (n/64, n/64, batch); block 256.  Batch strides in elements (0 = shared operand).

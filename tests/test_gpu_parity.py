@@ -125,7 +125,7 @@ def test_linear_kernel(env, collapsed):
 
 
 @pytest.mark.parametrize("T,M,D,S", [(1, 5, 1, 1), (7, 3, 2, 2), (64, 128, 2, 1), (65, 129, 2, 1), (130, 200, 3, 2),
-                                      (97, 300, 2, 1), (80, 512, 2, 1)])
+                                      (97, 300, 2, 1), (80, 512, 2, 1), (40, 700, 2, 1), (24, 1100, 1, 2), (12, 2048, 1, 1)])
 @pytest.mark.parametrize("collapsed", (False, True))
 def test_ragged_shapes(env, T, M, D, S, collapsed):
     """Tile-ragged T (1, prime, multiple and multiple+1 of the tile), every padded-M template."""

@@ -70,6 +70,12 @@ def main():
         cases.append(("synthetic T=257 M=200 D=2 S=1 (Mp=256)", fixtures.synthetic_problem(T=257, M=200, D=2, S=1)))
         cases.append(("synthetic T=130 M=300 D=2 S=1 (Mp=384)", fixtures.synthetic_problem(T=130, M=300, D=2, S=1)))
         cases.append(("synthetic T=100 M=500 D=2 S=2 (Mp=512)", fixtures.synthetic_problem(T=100, M=500, D=2, S=2)))
+        if len(sys.argv) > 1 and sys.argv[1] == "large":
+            cases = []
+            cases.append(("synthetic T=50 M=700 D=2 S=1 (Mp=768)", fixtures.synthetic_problem(T=50, M=700, D=2, S=1)))
+            cases.append(("synthetic T=40 M=1000 D=2 S=1 (Mp=1024)", fixtures.synthetic_problem(T=40, M=1000, D=2, S=1)))
+            cases.append(("synthetic T=30 M=1400 D=1 S=1 (Mp=1536)", fixtures.synthetic_problem(T=30, M=1400, D=1, S=1)))
+            cases.append(("synthetic T=20 M=2048 D=1 S=1 (Mp=2048)", fixtures.synthetic_problem(T=20, M=2048, D=1, S=1)))
     for tag, prob in cases:
         for collapsed in (False, True):
             t = time.time()
