@@ -12,7 +12,8 @@ import os
 from typing import Any, Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libffvd_b200.so")
+# FFVD_B200_LIB selects another build of the same library (e.g. the -DFFVD_PHASE_TIMING diagnostic build)
+LIB_PATH = os.environ.get("FFVD_B200_LIB") or os.path.join(_HERE, "lib", "libffvd_b200.so")
 
 KERNEL_SE = 0
 KERNEL_LINEAR = 1
@@ -71,6 +72,7 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_ctx_launch_count.restype = cll
     lib.ffvd_ctx_fused_time.argtypes = [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(cll)]
     lib.ffvd_ctx_fused_time.restype = ci
+    lib.ffvd_debug_phase_clocks.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_uint64)]
     lib.ffvd_kernel_K.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     lib.ffvd_kernel_Kdiag.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.ffvd_kernel_pre_cal.argtypes = [vp, ci, vp, vp, vp, cd, vp]
@@ -164,6 +166,12 @@ class Context:
         tot, cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
         _check(self._lib.ffvd_ctx_fused_time(self._h, int(reset), ctypes.byref(tot), ctypes.byref(cnt)))
         return tot.value, cnt.value
+
+    def phase_clocks(self, reset: bool = True):
+        """Diagnostic builds only (-DFFVD_PHASE_TIMING): per-phase SM clock totals of the fused kernel."""
+        buf = (ctypes.c_uint64 * 16)()
+        _check(self._lib.ffvd_debug_phase_clocks(self._h, int(reset), buf))
+        return list(buf)
 
     # ---- operators
     def kernel_K(self, kind, X, X2, logv, logl, out):

@@ -128,6 +128,22 @@ extern "C" int ffvd_ctx_fused_time(ffvd_ctx* c, int reset, double* total_ms, int
   return FFVD_OK;
 }
 
+extern "C" int ffvd_debug_phase_clocks(ffvd_ctx* c, int reset, uint64_t* out16) {
+#ifdef FFVD_PHASE_TIMING
+  if (!c || !out16) return fail(FFVD_E_BADARG, "null argument");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpyFromSymbol(out16, g_phase_clocks, 16 * sizeof(uint64_t)));
+  if (reset) {
+    uint64_t z[16] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(g_phase_clocks, z, sizeof z));
+  }
+  return FFVD_OK;
+#else
+  (void)c; (void)reset; (void)out16;
+  return fail(FFVD_E_UNSUPPORTED, "library was not built with -DFFVD_PHASE_TIMING");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // tensor import / staging
 struct Tens {
@@ -236,7 +252,7 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   size_t o = 0;
   const size_t mm = (size_t)Mp * Mp * sizeof(double);
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  L.off_ZT = take((size_t)nprob * 32 * Mp * 8);
+  L.off_ZT = take((size_t)nprob * 64 * Mp * 8);          // Z~^T and its fragment-ordered copy
   L.off_kscr = take((size_t)160 * 64 * Mp * 8);          // per-CTA K-tile scratch of the fused kernel
   L.off_Linv = take((size_t)nprob * nk * mm);
   L.off_LinvT = take((size_t)nprob * nk * mm);
@@ -295,7 +311,8 @@ static int ensure_arena(ffvd_ctx* c, const Layout& L) {
 static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin, DevProblem& P) {
   char* a = c->arena;
   const size_t mm = (size_t)L.Mp * L.Mp;
-  P.ZT = (double*)(a + L.off_ZT) + (size_t)p * 32 * L.Mp;
+  P.ZT = (double*)(a + L.off_ZT) + (size_t)p * 64 * L.Mp;
+  P.Zf = P.ZT + (size_t)32 * L.Mp;
   P.Linv = (double*)(a + L.off_Linv) + (size_t)p * L.nk * mm;
   P.LinvT = (double*)(a + L.off_LinvT) + (size_t)p * L.nk * mm;
   P.Sacc = (double*)(a + L.off_Sacc) + (size_t)p * L.nb * mm;
@@ -348,9 +365,14 @@ static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int npro
   void (*kern)(const DevProblem*, int, long long, double*) = nullptr;
 #define FFVD_PICK(RB_, NGW_, NW_) \
   if (ngw == NGW_ && cfg.rb == RB_ && cfg.nw == NW_) kern = fused_kernel<KIND, RB_, NGW_, MODE, NW_>;
+#ifdef FFVD_DEV_MINIMAL
+  // kernel-development build (seconds instead of minutes): SE uncollapsed only, three tile shapes
+  if constexpr (KIND == 0 && MODE == MODE_UNCOLLAPSED) { FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 4, 8) }
+#else
   FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 3, 8) FFVD_PICK(4, 4, 8)
   FFVD_PICK(2, 6, 8) FFVD_PICK(2, 8, 8) FFVD_PICK(1, 12, 8) FFVD_PICK(1, 16, 8)
   if (KIND == 0 && MODE == MODE_UNCOLLAPSED) { FFVD_PICK(8, 1, 8) }
+#endif
 #undef FFVD_PICK
   if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_NW)");
   const int RB = cfg.rb;

@@ -5,7 +5,8 @@
 
 #define FFVD_NTHREADS 256
 #define FFVD_NWARPS 8
-#define FFVD_XLD 33            // row stride of the x-tile arrays in shared memory (doubles)
+#define FFVD_XLD 36            // row stride of the x-tile arrays in shared memory (doubles); 36 = 4 mod 16 keeps the
+                               // DMMA fragment reads (row q, column g) and the per-row reads conflict free per half-warp
 #define FFVD_XCOLS 32          // padded column count of X~ = [x, ctrl, 1, 0...]
 #define FFVD_MAX_DIN 31
 #define FFVD_NTERMS_RAW 8      // raw per-sample sums, see below
@@ -22,7 +23,8 @@ struct DevProblem {
   // inputs
   const double *X, *Z, *U, *logv, *logl, *logQ, *C, *dvec, *logR, *Y, *ctrl;
   // derived inputs (written by kzz_prep)
-  double *ZT;          // [Din][Mp]   transposed, zero padded inducing inputs
+  double *ZT;          // [32][Mp]    Z~^T: transposed, zero padded inducing inputs, then a row of ones (m < M), zeros
+  double *Zf;          // [Mp/4][4][32] the same matrix in DMMA B-fragment order: entry ((m>>2)*4 + (jd>>3))*32 + (jd&7)*4 + (m&3)
   double *Linv;        // [D][Mp][Mp] L^{-1}  (lower), zero padded
   double *LinvT;       // [D][Mp][Mp] L^{-T}  (upper)
   // accumulators (zeroed before each evaluation)
@@ -59,6 +61,49 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+
+// exp(x) for x <= ~0 (the SE kernel argument -r^2/2), branch free so that independent evaluations interleave:
+// x = n ln2 + r, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^n applied to the exponent bits.
+// <= 1 ulp from the correctly rounded result on [-700, 1e-9] (checked on the host against libm); x < -700 clamps
+// to exp(-700) ~ 1e-304, i.e. 0 at the scale of every quantity the kernels form.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  x = fmax(x, -700.0);
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nd = t - 6755399441055744.0;
+  double r = fma(nd, -6.93147180369123816490e-01, x);
+  r = fma(nd, -1.90821492927058770002e-10, r);
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// Fire-and-forget FP64 add to GLOBAL memory.  atomicAdd() on a pointer whose address space the compiler cannot prove
+// (every pointer loaded from DevProblem) becomes ATOM.E.ADD + a predicate wait + shared/local CAS fall-backs, i.e. a
+// synchronous L2 round trip per call; the explicit red.global is one REDG with no return value.
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v));
+}
+
+// 16-byte read-only load that does not allocate in L1: the L^{-1} / L^{-T} operand streams are used once per tile,
+// keeping them out of L1 leaves it to the small reused arrays (Z~^T, Zf).
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

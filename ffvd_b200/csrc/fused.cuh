@@ -9,6 +9,27 @@
 
 namespace ffvd {
 
+// Optional per-phase cycle accounting (build with -DFFVD_PHASE_TIMING; tools/phase_timing.py).  Thread 0 of
+// every CTA adds the clock64() delta since its previous mark to g_phase_clocks[i]; phases end at CTA
+// barriers, so thread 0's timeline is the CTA's.
+#ifdef FFVD_PHASE_TIMING
+__device__ unsigned long long g_phase_clocks[16];
+#define FFVD_MARK(i)                                                                 \
+  do {                                                                               \
+    if (tid == 0) {                                                                  \
+      const long long _now = clock64();                                              \
+      atomicAdd(&g_phase_clocks[i], (unsigned long long)(_now - _phase_last));       \
+      _phase_last = _now;                                                            \
+    }                                                                                \
+  } while (0)
+#else
+#define FFVD_MARK(i) do { } while (0)
+#endif
+
+#ifndef FFVD_ABLATE
+#define FFVD_ABLATE 0      // timing experiments only: 1 = no S REDs, 2 = no SYRK, 3 = no L^{-1} operand loads
+#endif
+
 enum { MODE_UNCOLLAPSED = 0, MODE_COLLAPSED_P1 = 1, MODE_COLLAPSED_P2 = 2, MODE_FORWARD = 3, MODE_COND = 4 };
 
 struct Smem {
@@ -18,25 +39,36 @@ struct Smem {
   double* us;       // Mp           : u_d (uncollapsed) / w'_d (collapsed pass 2)
   double* es;       // 64           : e_t (uncollapsed) / delta_t (collapsed)
   double* rowpart;  // 2 x 8 x 64
-  double* stage;    // 8 warps x 8 x 40
-  double* part;     // 64 x 32 (x KS folded into rows)
+  double* stage;    // NW warps x 8 x 40
+  double* part;     // 128 x 32: partial products of W [Z,1] per k slice (overlays xsc)
   double* small;    // 64: invl2[32], sil[32]
+  double* xn2h;     // 64: SE: -1/2 |x~_r|^2 of the scaled rows
+  double* sc;       // 8: per-item scalars v, Q, 1/Q, log Q
   double* red;      // 40: block-level reductions (smem atomics)
 };
 
 template <int RB>
 __host__ __device__ constexpr int bt_of() { return 8 * RB; }
 
+// xsc (SE: scaled x rows, used while the K tile is formed) and part (128 x 32 partial products of W [Z,1], used by the
+// last phase) share one region
+__host__ __device__ inline size_t fused_xsc_part_doubles(int BT) {
+  const size_t a = ((size_t)BT * FFVD_XLD + 1) & ~(size_t)1, b = 128 * 32;
+  return a > b ? a : b;
+}
+
 __host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp, int NW) {
   const int BT = 8 * RB;
   // every sub-array is rounded up to an even number of doubles so that all of them stay 16-byte aligned
-  size_t n = (size_t)BT * (Mp + 4) + (size_t)NW * 4 * 40 + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
-             (((size_t)BT * FFVD_XLD + 1) & ~(size_t)1) + Mp + 64 + 2 * 8 * 64 + 64 * 32 + 64 + 40;
+  size_t n = (size_t)BT * (Mp + 4) + (size_t)NW * 8 * 40 + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
+             fused_xsc_part_doubles(BT) + Mp + 64 + 2 * 8 * 64 + 64 + 64 + 8 + 40;
   return n * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k(x_r, z_j) for the (rows 8*rb+g, cols jbase..jbase+3) owned by this lane.
+// SE follows the reference's expansion (kernels_multi_output.py:163-182): r^2 = |x~|^2 + |z~|^2 - 2 x~.z~ with
+// x~ = x/l, z~ = z/l, so the inner loop is one FMA per (element, input dim); exp through the branch-free exp_nonpos.
 template <int KIND, int RB>
 __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem& sm, const double* __restrict__ ZT,
                                                 int Mp, int Din, double v, int jbase, int g, int M, int nvalid, int row0) {
@@ -45,7 +77,8 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
   for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
     for (int c = 0; c < 4; ++c) s[rb][c] = 0.0;
-  const double* xsrc = (KIND == 0) ? sm.xsc : sm.xs;
+  double zz[4] = {0.0, 0.0, 0.0, 0.0};
+  const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + g) * FFVD_XLD;
   // one-step software pipeline on the (L1/L2-resident) Z^T loads
   double2 n01 = __ldg(reinterpret_cast<const double2*>(ZT + jbase));
   double2 n23 = __ldg(reinterpret_cast<const double2*>(ZT + jbase + 2));
@@ -59,90 +92,130 @@ __device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem&
     if (KIND == 0) {
       const double sil = sm.small[32 + jd];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) z[c] *= sil;
+      for (int c = 0; c < 4; ++c) {
+        z[c] *= sil;
+        zz[c] = fma(z[c], z[c], zz[c]);
+      }
     }
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
-      const double x = xsrc[(row0 + 8 * rb + g) * FFVD_XLD + jd];
+      const double x = xsrc[8 * rb * FFVD_XLD + jd];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (KIND == 0) {
-          const double t = x - z[c];
-          s[rb][c] = fma(t, t, s[rb][c]);
-        } else {
-          s[rb][c] = fma(x, z[c], s[rb][c]);
-        }
-      }
+      for (int c = 0; c < 4; ++c) s[rb][c] = fma(x, z[c], s[rb][c]);
     }
   }
+  if (KIND == 0) {
 #pragma unroll
-  for (int rb = 0; rb < RB; ++rb)
+    for (int c = 0; c < 4; ++c) zz[c] *= -0.5;
+  }
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    const double hx = (KIND == 0) ? sm.xn2h[row0 + 8 * rb + g] : 0.0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      double k = (KIND == 0) ? v * exp(-0.5 * s[rb][c]) : v * s[rb][c];
+      double k = (KIND == 0) ? v * exp_nonpos(s[rb][c] + (hx + zz[c])) : v * s[rb][c];
       if (jbase + c >= M || row0 + 8 * rb + g >= nvalid) k = 0.0;
       kv[rb][c] = k;
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // acc (BT x Mp, distributed) = Aop(tile) (BT x Mp) * B (Mp x Mp, row-major in global/L2).
 // TRI = +1: B upper triangular (B[k][n] != 0 only for k <= n);  -1: lower;  0: dense.
 // Lane (g,q) of the warp ends up with rows 8*rb+g, columns 16*group+4q+{0,1,2,3}.
+//
+// The k range is cut into segments on which the set of column groups with non-zero B rows is fixed at compile
+// time (a suffix of the warp's groups for TRI > 0, a prefix for TRI < 0: the groups are in ascending column order),
+// so no DMMA is ever issued predicated-off -- on sm_100a a predicated-off DMMA still occupies the tensor pipe.
+// B fragments stream from L2 through a 4-slot register ring, 3 k-steps ahead; the k loop is unrolled by 4 (segment
+// lengths are multiples of 16 rows) so ring slots are static and no register moves are needed.
+template <int RB, int NG, int LO, int HI, int TRI, class AOp>
+__device__ __forceinline__ void gemm_segment(double (&acc)[NG][RB][4], double2 (&ring)[4][NG], const double* aq, int lda,
+                                             const double* bq, int Mp, const int (&joff)[NG], int kbeg, int kend, AOp aop,
+                                             int q) {
+  // loads issued in this segment: groups [LO,HI) unconditionally (the k-step they are for is inside their non-zero
+  // range), plus one boundary group under a predicate:
+  //   TRI > 0: group LO only while the step is still below its end  (kl < joff[LO] + 16)
+  //   TRI < 0: group HI (if any) once the step has reached its start (kl >= joff[HI])
+  //   loads past the matrix (kl >= Mp) are suppressed
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kc = k0 + 4 * u;              // k-step computed now (ring slot u)
+      const int kl = kc + 12;                 // k-step loaded now  (ring slot (u + 3) & 3)
+      const double* bl = bq + (size_t)kl * Mp;
+#pragma unroll
+      for (int ng = 0; ng < NG; ++ng) {
+        bool doit = (ng >= LO && ng < HI);
+        if (TRI > 0 && ng == LO) doit = kl < joff[LO] + 16;
+        if (TRI < 0 && ng == HI) doit = kl >= joff[ng];
+        if (TRI <= 0) doit = doit && (kl < Mp);
+        if ((ng >= LO && ng < HI) || (TRI < 0 && ng == HI)) {
+          if (doit) ring[(u + 3) & 3][ng] = ldg_stream2(bl + joff[ng]);
+        }
+      }
+      double a[RB];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) a[rb] = aop(aq[rb * 8 * lda + kc], rb, kc + q);
+#pragma unroll
+      for (int ng = LO; ng < HI; ++ng) {
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          dmma884(acc[ng][rb][0], acc[ng][rb][2], a[rb], ring[u][ng].x);
+          dmma884(acc[ng][rb][1], acc[ng][rb][3], a[rb], ring[u][ng].y);
+        }
+      }
+    }
+  }
+}
+
+template <int RB, int NG, int A, int TRI, class AOp>
+__device__ __forceinline__ void gemm_segments(double (&acc)[NG][RB][4], double2 (&ring)[4][NG], const double* aq, int lda,
+                                              const double* bq, int Mp, const int (&joff)[NG], AOp aop, int q) {
+  if constexpr (A < NG) {
+    if constexpr (TRI > 0) {
+      const int kbeg = (A == 0) ? 0 : joff[A - 1 < 0 ? 0 : A - 1] + 16;
+      gemm_segment<RB, NG, A, NG, TRI>(acc, ring, aq, lda, bq, Mp, joff, kbeg, joff[A] + 16, aop, q);
+    } else {
+      const int kend = (A + 1 < NG) ? joff[A + 1 < NG ? A + 1 : A] : Mp;
+      gemm_segment<RB, NG, 0, A + 1, TRI>(acc, ring, aq, lda, bq, Mp, joff, joff[A], kend, aop, q);
+    }
+    gemm_segments<RB, NG, A + 1, TRI>(acc, ring, aq, lda, bq, Mp, joff, aop, q);
+  }
+}
+
 template <int RB, int NGW, int TRI, class AOp>
 __device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const double* tile, int lda,
                                                 const double* __restrict__ B, int Mp, int warp, int ng0, int g, int q, AOp aop) {
-  // per-group active k range [kb, ke) (multiples of 4) and running B pointers
-  int kb[NGW], ke[NGW];
-  const double* bp[NGW];
-  int kbeg = Mp, kend = 0;
+  int joff[NGW];
 #pragma unroll
   for (int ng = 0; ng < NGW; ++ng) {
-    const int j0 = 16 * group_index(warp, ng0 + ng);
-    kb[ng] = (TRI < 0) ? j0 : 0;
-    ke[ng] = (TRI > 0) ? j0 + 16 : Mp;
-    kbeg = min(kbeg, kb[ng]);
-    kend = max(kend, ke[ng]);
-    bp[ng] = B + (size_t)q * Mp + j0 + 2 * g;
+    joff[ng] = 16 * group_index(warp, ng0 + ng);
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[ng][rb][c] = 0.0;
   }
+  const double* bq = B + (size_t)q * Mp + 2 * g;
+  const double* aq = tile + g * lda + q;
+  double2 ring[4][NGW];
+  // prologue: the first three k-steps of the first segment
+  const int kfirst = (TRI < 0) ? joff[0] : 0;
 #pragma unroll
-  for (int ng = 0; ng < NGW; ++ng) bp[ng] += (size_t)kbeg * Mp;
-  const size_t bstep = (size_t)4 * Mp;
-  // B fragments are streamed from L2 two k-steps ahead (register ring b0 <- b1 <- b2)
-  double2 b0[NGW], b1[NGW], b2[NGW];
-  auto loadB = [&](int k0, double2(&b)[NGW]) {     // loads the fragments of step k0, bp[] must point at step k0
-#pragma unroll
-    for (int ng = 0; ng < NGW; ++ng) {
-      if (k0 >= kb[ng] && k0 < ke[ng]) b[ng] = __ldg(reinterpret_cast<const double2*>(bp[ng]));
-      else b[ng] = make_double2(0.0, 0.0);
-      bp[ng] += bstep;
-    }
-  };
-  loadB(kbeg, b0);
-  loadB(kbeg + 4, b1);        // may run past kend: the range test turns it into zeros without touching memory
-  const double* ap = tile + g * lda + kbeg + q;
-  for (int k0 = kbeg; k0 < kend; k0 += 4) {
-    loadB(k0 + 8, b2);
-    double a[RB];
-#pragma unroll
-    for (int rb = 0; rb < RB; ++rb) a[rb] = aop(ap[rb * 8 * lda], rb, k0 + q);
-    ap += 4;
+  for (int u = 0; u < 3; ++u)
 #pragma unroll
     for (int ng = 0; ng < NGW; ++ng) {
-      if (k0 >= kb[ng] && k0 < ke[ng]) {
-#pragma unroll
-        for (int rb = 0; rb < RB; ++rb) {
-          dmma884(acc[ng][rb][0], acc[ng][rb][2], a[rb], b0[ng].x);
-          dmma884(acc[ng][rb][1], acc[ng][rb][3], a[rb], b0[ng].y);
-        }
-      }
+      ring[u][ng] = make_double2(0.0, 0.0);
+      const bool active = (TRI < 0) ? (ng == 0) : true;    // TRI < 0 starts with group 0 alone; else every group is live at k = 0
+      if (active) ring[u][ng] = ldg_stream2(bq + (size_t)(kfirst + 4 * u) * Mp + joff[ng]);
     }
 #pragma unroll
-    for (int ng = 0; ng < NGW; ++ng) { b0[ng] = b1[ng]; b1[ng] = b2[ng]; }
+  for (int ng = 0; ng < NGW; ++ng) ring[3][ng] = make_double2(0.0, 0.0);
+  if constexpr (TRI == 0) {
+    gemm_segment<RB, NGW, 0, NGW, 0>(acc, ring, aq, lda, bq, Mp, joff, 0, Mp, aop, q);
+  } else {
+    gemm_segments<RB, NGW, 0, TRI>(acc, ring, aq, lda, bq, Mp, joff, aop, q);
   }
 }
 
@@ -180,53 +253,72 @@ __device__ __forceinline__ void store_tile(const double (&acc)[NGW][RB][4], doub
 
 // ---------------------------------------------------------------------------------------------
 // S (lower 32x32 tiles) += tile^T tile  over the BT rows, flushed with coalesced RED.add.f64.
-template <int RB, int NW>
-__device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
-                                           int warp, int lane) {
+// Work units: the nt(nt-1)/2 strictly-lower tiles (16 8x8 blocks each) followed by the nt diagonal tiles (only the
+// 10 blocks on or below the diagonal are formed), dealt to the warps in snake order so the per-warp block counts
+// differ by at most a few percent (Mp = 256: 64 vs 68 blocks).
+template <int RB, bool DIAG>
+__device__ __forceinline__ void syrk_tile(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
+                                          int m0, int n0, int lane) {
   const int g = lane >> 2, q = lane & 3;
-  const int nt = Mp >> 5;
-  const int ntiles = nt * (nt + 1) / 2;
-  for (int tix = warp; tix < ntiles; tix += NW) {
-    // decode (ti >= tj) from the linear lower-triangular index
-    int ti = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= tix) ++ti;
-    while (ti * (ti + 1) / 2 > tix) --ti;
-    const int tj = tix - ti * (ti + 1) / 2;
-    const int m0 = 32 * ti, n0 = 32 * tj;
-    double c[4][4][2];
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < 8 * RB; k0 += 4) {
+    double a[4], b[4];
+    const double* row = tile + (k0 + q) * lda + g;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = row[m0 + 8 * i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = DIAG ? a[j] : row[n0 + 8 * j];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
-#pragma unroll 2
-    for (int k0 = 0; k0 < 8 * RB; k0 += 4) {
-      double a[4], b[4];
-      const double* row = tile + (k0 + q) * lda + g;
+      for (int j = 0; j < 4; ++j)
+        if (!DIAG || j <= i) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+  }
+  // transpose 8 rows at a time through the per-warp staging buffer (8 x 40 doubles), flush with coalesced REDs
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = row[m0 + 8 * i];
+  for (int i = 0; i < 4; ++i) {
+    __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = row[n0 + 8 * j];
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<double2*>(stage_w + g * 40 + 8 * j + 2 * q) = make_double2(c[i][j][0], c[i][j][1]);
+    __syncwarp();
+    const int ncol = DIAG ? 8 * (i + 1) : 32;      // diagonal tiles: nothing right of block column i in block row i
+    if (lane < ncol) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
-    }
-    // transpose 4 rows at a time through the per-warp staging buffer, flush with coalesced REDs
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        __syncwarp();
-        if ((g >> 2) == h) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<double2*>(stage_w + (g & 3) * 40 + 8 * j + 2 * q) = make_double2(c[i][j][0], c[i][j][1]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-          atomicAdd(S + (size_t)(m0 + 8 * i + 4 * h + r) * Mp + n0 + lane, stage_w[r * 40 + lane]);
+      for (int r = 0; r < 8; ++r) {
+#if FFVD_ABLATE != 1
+        red_add(S + (size_t)(m0 + 8 * i + r) * Mp + n0 + lane, stage_w[r * 40 + lane]);
+#else
+        if (stage_w[r * 40 + lane] == 1.2345e300) red_add(S, 1.0);
+#endif
       }
+    }
+  }
+}
+
+template <int RB, int NW>
+__device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
+                                           int warp, int lane) {
+  const int nt = Mp >> 5;
+  const int nfull = nt * (nt - 1) / 2, nunits = nfull + nt;
+  for (int i = 0;; ++i) {
+    const int u = i * NW + ((i & 1) ? (NW - 1 - warp) : warp);
+    if (u >= nunits) break;
+    if (u < nfull) {
+      // decode (ti > tj) from the linear strictly-lower index u = ti(ti-1)/2 + tj
+      int ti = (int)((sqrtf(8.0f * (float)u + 1.0f) + 1.0f) * 0.5f);
+      while (ti * (ti - 1) / 2 > u) --ti;
+      while ((ti + 1) * ti / 2 <= u) ++ti;
+      const int tj = u - ti * (ti - 1) / 2;
+      syrk_tile<RB, false>(tile, lda, Mp, S, stage_w, 32 * ti, 32 * tj, lane);
+    } else {
+      const int t = u - nfull;
+      syrk_tile<RB, true>(tile, lda, Mp, S, stage_w, 32 * t, 32 * t, lane);
     }
   }
 }
@@ -236,68 +328,98 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
 //   WtX~ = W^T [Xc,1]   (Mp x (Din+1))   ->  dJ/dZ rows
 //   WZ~  = W [Z,1]      (BT x (Din+1))   ->  dJ/dXc rows
 // SE: W = kbar*k;  Linear: W = kbar (the factor v is applied here).
-template <int KIND, int RB, int NW>
+// Both products run on the tensor pipe with every global operand (Z~ fragments, the Z values of the epilogue)
+// requested ahead of its use, and all reductions end in fire-and-forget global REDs.
+// NBM = compile-time bound on the 8-column blocks of [Xc,1] / [Z,1] (2 for Din <= 15, else 4).
+template <int KIND, int RB, int NGW, int NW, int NBM>
 __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevProblem& P, int d, double v, double* gXs,
-                                           int t0, int nvalid, int warp, int lane, int tid) {
+                                           int t0, int nvalid, int warp, int lane, int tid
+#ifdef FFVD_PHASE_TIMING
+                                           , long long& _phase_last
+#endif
+                                           ) {
   const int g = lane >> 2, q = lane & 3;
   const int Din = P.Din, M = P.M, Mp = P.Mp, D = P.D;
-  const int nbx = (Din + 1 + 7) >> 3;           // n-blocks covering Din+1 columns
-  const int BT = 8 * RB;
+  const int nbx = (Din + 1 + 7) >> 3;           // n-blocks covering Din+1 columns (<= NBM)
+  constexpr int BT = 8 * RB;
   const double* tile = sm.tile;
   // ---- W^T X~ : 8 warps own m-blocks w, w+8, ...  (NW == 16: warps 8..15, concurrently with W Z~ on warps 0..7)
   if (NW == 8 || warp >= 8) {
     const int wA = warp & 7;
-    const int nbc = Din >> 3, qc = (Din & 7) >> 1, ec = Din & 1;
-    double lacc[4][2];
+    constexpr int NMB = 2 * NGW;                 // m-blocks per warp = (Mp/8)/8
+    constexpr int MCH = NMB < 4 ? NMB : 4;       // processed MCH at a time
+    const int nbc = Din >> 3, qc = (Din & 7) >> 1, ec = Din & 1;   // where column Din (the ones) sits in a C fragment
+    double lacc[NBM][2];
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) lacc[nb][0] = lacc[nb][1] = 0.0;
-    for (int mb = wA; mb < (Mp >> 3); mb += 8) {
-      double c[4][2];
+    for (int nb = 0; nb < NBM; ++nb) lacc[nb][0] = lacc[nb][1] = 0.0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < NMB; i0 += MCH) {
+      double zr[MCH][NBM][2];
+      if (KIND == 0) {
+        // Z values of the epilogue, requested before the product (rows of Z~^T above Din are one / zero: harmless)
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) c[nb][0] = c[nb][1] = 0.0;
+        for (int u = 0; u < MCH; ++u)
+#pragma unroll
+          for (int nb = 0; nb < NBM; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              zr[u][nb][e] = (nb < nbx) ? __ldg(P.ZT + (size_t)(8 * nb + 2 * q + e) * Mp + 8 * (wA + 8 * (i0 + u)) + g) : 0.0;
+      }
+      double c[MCH][NBM][2];
+#pragma unroll
+      for (int u = 0; u < MCH; ++u)
+#pragma unroll
+        for (int nb = 0; nb < NBM; ++nb) c[u][nb][0] = c[u][nb][1] = 0.0;
+      const double* arow = tile + q * lda + 8 * (wA + 8 * i0) + g;
+      const double* brow = sm.xs + q * FFVD_XLD + g;
 #pragma unroll 2
       for (int k0 = 0; k0 < BT; k0 += 4) {
-        const double a = tile[(k0 + q) * lda + 8 * mb + g];
+        double b[NBM];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-          if (nb < nbx) {
-            const double b = sm.xs[(k0 + q) * FFVD_XLD + 8 * nb + g];
-            dmma884(c[nb][0], c[nb][1], a, b);
-          }
+        for (int nb = 0; nb < NBM; ++nb) b[nb] = (nb < nbx) ? brow[k0 * FFVD_XLD + 8 * nb] : 0.0;
+#pragma unroll
+        for (int u = 0; u < MCH; ++u) {
+          const double a = arow[k0 * lda + 64 * u];
+#pragma unroll
+          for (int nb = 0; nb < NBM; ++nb)
+            if (nb < nbx) dmma884(c[u][nb][0], c[u][nb][1], a, b[nb]);
         }
       }
-      // column sum of W for row m = 8*mb+g sits at column Din of the product
-      double csv = 0.0;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb)
-        if (nb == nbc) csv = ec ? c[nb][1] : c[nb][0];
-      const double cs = __shfl_sync(0xffffffffu, csv, g * 4 + qc);
-      const int m = 8 * mb + g;
+      for (int u = 0; u < MCH; ++u) {
+        // column sum of W for row m = 8*mb+g sits at column Din of the product
+        double csv = 0.0;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) {
-        if (nb < nbx) {
+        for (int nb = 0; nb < NBM; ++nb)
+          if (nb == nbc) csv = ec ? c[u][nb][1] : c[u][nb][0];
+        const double cs = __shfl_sync(0xffffffffu, csv, g * 4 + qc);
+        const int m = 8 * (wA + 8 * (i0 + u)) + g;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int jd = 8 * nb + 2 * q + e;
-            if (jd < Din && m < M) {
-              const double z = P.Z[(size_t)m * Din + jd];
-              double zb;
-              if (KIND == 0) {
-                zb = sm.small[jd] * (c[nb][e] - cs * z);
-                lacc[nb][e] -= z * zb;
-              } else {
-                zb = v * c[nb][e];
+        for (int nb = 0; nb < NBM; ++nb) {
+          if (nb < nbx) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int jd = 8 * nb + 2 * q + e;
+              if (jd < Din && m < M) {
+                double zb;
+                if (KIND == 0) {
+                  const double z = zr[u][nb][e];
+                  zb = sm.small[jd] * (c[u][nb][e] - cs * z);
+                  lacc[nb][e] = fma(-z, zb, lacc[nb][e]);
+                } else {
+                  zb = v * c[u][nb][e];
+                }
+                red_add(P.gZ + (size_t)m * Din + jd, zb);
               }
-              atomicAdd(P.gZ + (size_t)m * Din + jd, zb);
             }
           }
         }
       }
     }
     if (KIND == 0) {
-      // reduce over g (lanes with equal q), then one atomic per column
+      // reduce over g (lanes with equal q), then one RED per column
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb)
+      for (int nb = 0; nb < NBM; ++nb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           double x = lacc[nb][e];
@@ -305,70 +427,97 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           x += __shfl_xor_sync(0xffffffffu, x, 8);
           x += __shfl_xor_sync(0xffffffffu, x, 16);
           const int jd = 8 * nb + 2 * q + e;
-          if (g == 0 && nb < nbx && jd < Din) atomicAdd(P.gl + (size_t)d * Din + jd, x);
+          if (g == 0 && nb < nbx && jd < Din) red_add(P.gl + (size_t)d * Din + jd, x);
         }
     }
   }
-  // ---- W Z~ : warp (0..7) -> (row block rb, k slice ks)
-  {
-    constexpr int KS = 8 / RB > 0 ? 8 / RB : 1;
-    const int rb = warp % RB, ks = warp / RB;
-    if (warp < 8 && ks < KS) {
-      const int klen = Mp / KS;
-      double c[4][2];
+  FFVD_MARK(8);
+  // ---- W Z~ : warps 0..7 -> (group of RPW row blocks, k slice).  B fragments come coalesced from the fragment-ordered
+  //      Zf, requested PF trips (of 4 k-steps) ahead; each fragment feeds RPW DMMAs.
+  constexpr int RPW = RB >= 2 ? 2 : 1;
+  constexpr int RG = RB / RPW;                 // row groups
+  constexpr int KS = 8 / RG;                   // k slices (RB = 8: 2, 4: 4, 2: 8, 1: 8)
+  constexpr int KLEN = 128 * NGW / KS;         // columns of W per slice
+  constexpr int TRIPS = KLEN / 16;
+  constexpr int PF = 2;
+  static_assert(KS * BT <= 128, "part holds 128 rows");
+  if (warp < 8) {
+    const int rg = warp % RG, ks = warp / RG;
+    double c[RPW][NBM][2];
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) c[nb][0] = c[nb][1] = 0.0;
-      // 4 k-steps per trip: all operand loads are issued before the first DMMA of the trip
-      for (int k0 = ks * klen; k0 < (ks + 1) * klen; k0 += 16) {
-        double a[4], b[4][4];
+    for (int r = 0; r < RPW; ++r)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          a[u] = tile[(8 * rb + g) * lda + k0 + 4 * u + q];
-          const int m = k0 + 4 * u + q;
+      for (int nb = 0; nb < NBM; ++nb) c[r][nb][0] = c[r][nb][1] = 0.0;
+    const double* zf = P.Zf + (size_t)(ks * (KLEN / 4)) * 128 + lane;
+    const double* ap = tile + (8 * RPW * rg + g) * lda + ks * KLEN + q;
+    double b[TRIPS][4][NBM];                   // fully unrolled below: lives in registers by liveness
 #pragma unroll
-          for (int nb = 0; nb < 4; ++nb)      // ZT has 32 rows: Z^T, a row of ones (m < M) at Din, zeros above
-            b[u][nb] = (nb < nbx) ? __ldg(P.ZT + (size_t)(8 * nb + g) * Mp + m) : 0.0;
-        }
+    for (int t = 0; t < PF && t < TRIPS; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int nb = 0; nb < NBM; ++nb) b[t][u][nb] = (nb < nbx) ? __ldg(zf + ((t * 4 + u) * 4 + nb) * 32) : 0.0;
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) {
+      if (t + PF < TRIPS) {
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int nb = 0; nb < 4; ++nb)
-            if (nb < nbx) dmma884(c[nb][0], c[nb][1], a[u], b[u][nb]);
+          for (int nb = 0; nb < NBM; ++nb)
+            b[t + PF][u][nb] = (nb < nbx) ? __ldg(zf + (((t + PF) * 4 + u) * 4 + nb) * 32) : 0.0;
       }
+      double a[RPW][4];
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb)
-        if (nb < nbx) {
-          double* p = sm.part + (size_t)(ks * BT + 8 * rb + g) * 32 + 8 * nb + 2 * q;
-          p[0] = c[nb][0];
-          p[1] = c[nb][1];
-        }
+      for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[r][u] = ap[r * 8 * lda + 16 * t + 4 * u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+          for (int nb = 0; nb < NBM; ++nb)
+            if (nb < nbx) dmma884(c[r][nb][0], c[r][nb][1], a[r][u], b[t][u][nb]);
     }
-    __syncthreads();
-    double vacc = 0.0;
-    for (int idx = tid; idx < BT * 32; idx += 32 * NW) {
-      const int r = idx >> 5, jd = idx & 31;
-      if (jd < Din && r < nvalid) {
-        double wz = 0.0, rs = 0.0;
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          wz += sm.part[(size_t)(k * BT + r) * 32 + jd];
-          rs += sm.part[(size_t)(k * BT + r) * 32 + Din];
-        }
-        const double x = sm.xs[r * FFVD_XLD + jd];
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int nb = 0; nb < NBM; ++nb)
+        if (nb < nbx)
+          *reinterpret_cast<double2*>(sm.part + (size_t)(ks * BT + 8 * (RPW * rg + r) + g) * 32 + 8 * nb + 2 * q) =
+              make_double2(c[r][nb][0], c[r][nb][1]);
+  }
+  FFVD_MARK(9);
+  __syncthreads();
+  FFVD_MARK(10);
+  // ---- rows of dJ/dXc: warp -> rows warp, warp+NW, ...; lane -> input column
+  {
+    double lsum = 0.0, vacc = 0.0;
+    const double il2 = (KIND == 0) ? sm.small[lane] : 0.0;
+    for (int r = warp; r < nvalid; r += NW) {
+      double wz = 0.0, rs = 0.0;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        wz += sm.part[(size_t)(k * BT + r) * 32 + lane];
+        rs += sm.part[(size_t)(k * BT + r) * 32 + Din];
+      }
+      if (lane < Din) {
+        const double x = sm.xs[r * FFVD_XLD + lane];
         double xb;
         if (KIND == 0) {
-          xb = -sm.small[jd] * (x * rs - wz);
-          atomicAdd(sm.red + 8 + jd, -x * xb);      // d/dlogl row part
-          if (jd == 0) vacc += rs;                  // d/dlogv = sum W
+          xb = -il2 * (x * rs - wz);
+          lsum = fma(-x, xb, lsum);                 // d/dlogl row part
+          if (lane == 0) vacc += rs;                // d/dlogv = sum W
         } else {
           xb = v * wz;
-          vacc += x * xb;                           // sum kbar*k
+          vacc = fma(x, xb, vacc);                  // sum kbar*k
         }
-        if (jd < D) atomicAdd(gXs + (size_t)(t0 + r) * D + jd, xb);
+        if (lane < D) red_add(gXs + (size_t)(t0 + r) * D + lane, xb);
       }
     }
+    if (KIND == 0 && lane < Din) red_add(P.gl + (size_t)d * Din + lane, lsum);
     vacc = warp_sum(vacc);
-    if (lane == 0) atomicAdd(sm.red + 7, vacc);
+    if (lane == 0) red_add(P.gv + d, vacc);
   }
 }
 
@@ -388,6 +537,9 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
   const int wc = warp & 7, row0 = (warp >> 3) * 8 * RBW;
   double* kscr = kscr_base + (size_t)blockIdx.x * BT * probs[0].Mp;     // per-CTA K-tile scratch (BT x Mp)
 
+#ifdef FFVD_PHASE_TIMING
+  long long _phase_last = clock64();
+#endif
   for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
     // ---- decode item -> (problem, d, s, tile); d is the slowest index inside a problem
     int pi = 0;
@@ -415,20 +567,18 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     {
       double* p = smem_raw;
       sm.tile = p; p += (size_t)BT * lda;
-      sm.stage = p; p += NW * 4 * 40;
+      sm.stage = p; p += NW * 8 * 40;
       sm.xs = p; p += ((BT + 1) * FFVD_XLD + 1) & ~1;
-      sm.xsc = p; p += (BT * FFVD_XLD + 1) & ~1;
+      sm.xsc = p; sm.part = p; p += fused_xsc_part_doubles(BT);
       sm.us = p; p += Mp;
       sm.es = p; p += 64;
       sm.rowpart = p; p += 2 * 8 * 64;
-      sm.part = p; p += 64 * 32;
       sm.small = p; p += 64;
+      sm.xn2h = p; p += 64;
+      sm.sc = p; p += 8;
       sm.red = p;
     }
     const int dh = d * P.hs;
-    const double v = exp(P.logv[dh]);
-    const double Q = (MODE == MODE_COND) ? 1.0 : exp(P.logQ[d]);
-    const double invQ = 1.0 / Q;
 
     __syncthreads();   // previous item fully done with shared memory
     // ---- P0: stage the x tile and per-d vectors
@@ -441,6 +591,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
       if (tid < 32) { sm.small[tid] = il2; sm.small[32 + tid] = sil; }
       if (tid < 40) sm.red[tid] = 0.0;
+      if (tid == 40) sm.sc[0] = exp(P.logv[dh]);
+      if (tid == 41) {
+        const double lq = (MODE == MODE_COND) ? 0.0 : P.logQ[d];
+        const double Qv = exp(lq);
+        sm.sc[1] = Qv; sm.sc[2] = 1.0 / Qv; sm.sc[3] = lq;
+      }
     }
     for (int idx = tid; idx < (BT + 1) * FFVD_XCOLS; idx += NTH) {
       const int r = idx >> 5, c = idx & 31;
@@ -463,13 +619,25 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       sm.us[j] = u;
     }
     __syncthreads();
+    const double v = sm.sc[0], Q = sm.sc[1], invQ = sm.sc[2], logQd = sm.sc[3];
     if (KIND == 0) {
       for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
         const int r = idx >> 5, c = idx & 31;
         sm.xsc[r * FFVD_XLD + c] = (c < Din) ? sm.xs[r * FFVD_XLD + c] * sm.small[32 + c] : 0.0;
       }
+      if (tid >= NTH - BT) {
+        // -1/2 |x~_r|^2 from the same rounded products the tile code reads
+        const int r = tid - (NTH - BT);
+        double a = 0.0;
+        for (int c = 0; c < Din; ++c) {
+          const double t = sm.xs[r * FFVD_XLD + c] * sm.small[32 + c];
+          a = fma(t, t, a);
+        }
+        sm.xn2h[r] = -0.5 * a;
+      }
       __syncthreads();
     }
+    FFVD_MARK(0);
 
     // ---- P1: K tile -> shared
     {
@@ -493,6 +661,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
     }
     __syncthreads();
+    FFVD_MARK(1);
 
     const double* LinvT = P.LinvT + (size_t)dh * Mp * Mp;
     const double* Linv = P.Linv + (size_t)dh * Mp * Mp;
@@ -534,6 +703,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         }
       }
       __syncthreads();          // everyone is done reading K from the tile
+      FFVD_MARK(2);
       if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
       // ---- per-row statistics (threads 0..BT-1)
       if (tid < 64) {
@@ -563,33 +733,31 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             } else if (MODE == MODE_COLLAPSED_P1) {
               const double delta = xn - xd;
               e = delta;                                   // b += F^T delta
-              jxq = -0.5 * delta * delta * invQ - 0.5 * log(Q);
+              jxq = -0.5 * delta * delta * invQ - 0.5 * logQd;
               jtr = -0.5 * sig2 * invQ;
               gq = 0.5 * sig2 * invQ + 0.5 * delta * delta * invQ - 0.5;   // explicit part of dJ/dlogQ
             } else {
               const double res = xn - (xd + su);
               e = res * invQ;
-              jxq = -0.5 * res * res * invQ - 0.5 * log(Q);
+              jxq = -0.5 * res * res * invQ - 0.5 * logQd;
               jtr = -0.5 * sig2 * invQ;
               gq = 0.5 * res * res * invQ - 0.5 + 0.5 * sig2 * invQ;
               if (MODE == MODE_UNCOLLAPSED) {
-                atomicAdd(gXs + (size_t)(t0 + r) * D + d, e);
-                atomicAdd(gXs + (size_t)(t0 + r + 1) * D + d, -e);
+                red_add(gXs + (size_t)(t0 + r) * D + d, e);
+                red_add(gXs + (size_t)(t0 + r + 1) * D + d, -e);
               }
             }
             gvd = -0.5 * kdiag * invQ;
             if (KIND == 1 && MODE == MODE_UNCOLLAPSED) {
-              for (int c = 0; c < D; ++c) atomicAdd(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
+              for (int c = 0; c < D; ++c) red_add(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
             }
           }
           sm.es[r] = e;
         }
         jxq = warp_sum(jxq); jtr = warp_sum(jtr); gq = warp_sum(gq); gvd = warp_sum(gvd);
         if (lane == 0) {
-          atomicAdd(sm.red + 0, jxq);
-          atomicAdd(sm.red + 1, jtr);
-          atomicAdd(sm.red + 2, gq);
-          atomicAdd(sm.red + 3, gvd);
+          double* rw = sm.red + 4 * warp;      // warps 0 and 1 only: private slots, summed at the flush
+          rw[0] = jxq; rw[1] = jtr; rw[2] = gq; rw[3] = gvd;
         }
       }
       // ---- emission term, once per (s, tile): dgp_model.py:248-250,264
@@ -608,29 +776,30 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             dy = res / Ry;
             rr = res * res - 1.0;
             if (MODE != MODE_FORWARD)
-              for (int c = 0; c < D; ++c) atomicAdd(gXs + (size_t)(t0 + r + 1) * D + c, dy * P.C[(size_t)c * Dy + y]);
+              for (int c = 0; c < D; ++c) red_add(gXs + (size_t)(t0 + r + 1) * D + c, dy * P.C[(size_t)c * Dy + y]);
           }
           if (MODE != MODE_FORWARD) {
             for (int c = 0; c < D; ++c) {
               const double xc1 = (r < nvalid) ? sm.xs[(r + 1) * FFVD_XLD + c] : 0.0;
               const double t = warp_sum(dy * xc1);
-              if (lane == 0) atomicAdd(P.gC + (size_t)c * Dy + y, t);
+              if (lane == 0) red_add(P.gC + (size_t)c * Dy + y, t);
             }
             const double sd = warp_sum(dy), sr = warp_sum(rr);
-            if (lane == 0) { atomicAdd(P.gd + y, sd); atomicAdd(P.gR + y, sr); }
+            if (lane == 0) { red_add(P.gd + y, sd); red_add(P.gR + y, sr); }
           }
         }
         ll = warp_sum(ll);
-        if (lane == 0) atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS, ll);
+        if (lane == 0) red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS, ll);
       }
       __syncthreads();          // A tile + es[] visible
+      FFVD_MARK(3);
     }
 
     if (MODE == MODE_FORWARD || MODE == MODE_COND) {
       // forward only: flush the scalar sums and move on
       if (MODE == MODE_FORWARD && tid == 0) {
-        atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0]);
-        atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1]);
+        red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0] + sm.red[4]);
+        red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1] + sm.red[5]);
       }
       continue;
     }
@@ -652,13 +821,16 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             t += __shfl_xor_sync(0xffffffffu, t, 4);
             t += __shfl_xor_sync(0xffffffffu, t, 8);
             t += __shfl_xor_sync(0xffffffffu, t, 16);
-            if (g == 0 && jb + c < M) atomicAdd(P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp + jb + c, t);
+            if (g == 0 && jb + c < M) red_add(P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp + jb + c, t);
           }
         }
       }
       // ---- S += A^T A
       double* Sd = P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp;
-      syrk_flush<RB, NW>(sm.tile, lda, Mp, Sd, sm.stage + warp * 4 * 40, warp, lane);
+#if FFVD_ABLATE != 2
+      syrk_flush<RB, NW>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
+#endif
+      FFVD_MARK(4);             // warp 0's own time: no barrier between the SYRK and the next contraction
     }
 
     if (MODE == MODE_UNCOLLAPSED) {
@@ -681,6 +853,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
                              [](double x, int, int) { return x; });
     }
 
+    FFVD_MARK(5);
     if (MODE == MODE_UNCOLLAPSED || MODE == MODE_COLLAPSED_P2) {
       if (MODE == MODE_COLLAPSED_P2) {
         // delta_r and dbar_r = sum_j k_rj w'_j (from the K tile still in shared memory)
@@ -693,10 +866,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             if (r < nvalid) {
               delta = sm.xs[(r + 1) * FFVD_XLD + d] - sm.xs[r * FFVD_XLD + d];
               const double gx = t - delta * invQ;
-              atomicAdd(gXs + (size_t)(t0 + r + 1) * D + d, gx);
-              atomicAdd(gXs + (size_t)(t0 + r) * D + d, -gx);
+              red_add(gXs + (size_t)(t0 + r + 1) * D + d, gx);
+              red_add(gXs + (size_t)(t0 + r) * D + d, -gx);
               if (KIND == 1)
-                for (int c = 0; c < D; ++c) atomicAdd(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
+                for (int c = 0; c < D; ++c) red_add(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
             }
             sm.es[r] = delta;
           }
@@ -714,7 +887,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             gvd = -0.5 * kdiag * invQ;
           }
           gvd = warp_sum(gvd);
-          if (lane == 0) atomicAdd(sm.red + 3, gvd);
+          if (lane == 0) sm.red[8 + warp] = gvd;
         }
         __syncthreads();
       }
@@ -756,21 +929,29 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
       }
       __syncthreads();
-      contract_W<KIND, RB, NW>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid);
+      FFVD_MARK(6);
+#ifdef FFVD_PHASE_TIMING
+#define FFVD_CW_TAIL , _phase_last
+#else
+#define FFVD_CW_TAIL
+#endif
+      if (Din + 1 <= 16) contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL);
+      else contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL);
+#undef FFVD_CW_TAIL
     }
 
     // ---- flush block-level scalars
     __syncthreads();
+    FFVD_MARK(7);
     if (tid < 32) {
       if (tid == 0) {
         if (MODE != MODE_COLLAPSED_P2) {
-          atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0]);
-          atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1]);
-          atomicAdd(P.gQ + d, sm.red[2]);
+          red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0] + sm.red[4]);
+          red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1] + sm.red[5]);
+          red_add(P.gQ + d, sm.red[2] + sm.red[6]);
         }
-        if (MODE != MODE_COLLAPSED_P1) atomicAdd(P.gv + d, sm.red[3] + sm.red[7]);
+        if (MODE != MODE_COLLAPSED_P1) red_add(P.gv + d, (sm.red[3] + sm.red[7]) + (sm.red[8] + sm.red[9]));
       }
-      if (KIND == 0 && MODE != MODE_COLLAPSED_P1 && tid < Din) atomicAdd(P.gl + (size_t)d * Din + tid, sm.red[8 + tid]);
     }
   }
 }

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
       double zv = 0.0;
       if (m < M) zv = (jd < Din) ? P.Z[(size_t)m * Din + jd] : (jd == Din ? 1.0 : 0.0);
       P.ZT[idx] = zv;
+      P.Zf[((size_t)(m >> 2) * 4 + (jd >> 3)) * 32 + (jd & 7) * 4 + (m & 3)] = zv;
     }
   }
   double* Lt = P.LinvT + (size_t)d * Mp * Mp;   // global scratch for L when it does not fit in smem
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) kzz_fill_kernel(const DevProblem* __restr
     double zv = 0.0;
     if (m < M) zv = (jd < Din) ? P.Z[(size_t)m * Din + jd] : (jd == Din ? 1.0 : 0.0);
     P.ZT[idx] = zv;
+    P.Zf[((size_t)(m >> 2) * 4 + (jd >> 3)) * 32 + (jd & 7) * 4 + (m & 3)] = zv;
   }
   if (idx >= (long long)Mp * Mp) return;
   const int m = (int)(idx / Mp), n = (int)(idx % Mp);
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256) collapsed_logdet_kernel(const DevProblem*
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int w = 0; w < 8; ++w) tot += red[w];
-    atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -tot);
+    red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -tot);
   }
 }
 
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(256) kzz_bwd_kernel(const DevProblem* __restri
       zb = 2.0 * exp(P.logv[d]) * wzz;
       vpart = 0.5 * z * zb;
     }
-    atomicAdd(P.gZ + (size_t)m * Din + jd, zb);
+    red_add(P.gZ + (size_t)m * Din + jd, zb);
   }
   if (KIND == 0) {
     // reduce lpart over the 8 rows of the block through shared memory, one atomic per jd
@@ -346,11 +348,11 @@ __global__ void __launch_bounds__(256) kzz_bwd_kernel(const DevProblem* __restri
       double t = 0.0;
 #pragma unroll
       for (int r = 0; r < 8; ++r) t += lsm[r][jd];
-      atomicAdd(P.gl + (size_t)d * Din + jd, t);
+      red_add(P.gl + (size_t)d * Din + jd, t);
     }
   }
   vpart = warp_sum(vpart);
-  if (jd == 0 && vpart != 0.0) atomicAdd(P.gv + d, vpart);
+  if (jd == 0 && vpart != 0.0) red_add(P.gv + d, vpart);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
     double t = 0.0;
     for (int i = tid; i < M; i += 32) t += log(H[(size_t)i * Mp + i]);
     t = warp_sum(t);
-    if (tid == 0) atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -t);
+    if (tid == 0) red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -t);
   }
   double* X = P.Hx + (size_t)b * Mp * Mp;
   double* XT = P.HxT + (size_t)b * Mp * Mp;
@@ -439,8 +441,8 @@ __global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __
   }
   __syncthreads();
   if (tid == 0) {
-    atomicAdd(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
-    atomicAdd(P.gQ + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
+    red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
+    red_add(P.gQ + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
   }
   // Mat' in place
   for (int idx = tid; idx < M * M; idx += 256) {

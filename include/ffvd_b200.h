@@ -93,6 +93,9 @@ int64_t ffvd_ctx_launch_count(ffvd_ctx* ctx);
  * tile-kernel launches recorded since the last reset (ring of 256); synchronises the stream.
  * bench.py derives the roofline figure from it. */
 int ffvd_ctx_fused_time(ffvd_ctx* ctx, int reset, double* total_ms, int64_t* count);
+/* Diagnostic: per-phase SM clock totals of the fused tile kernel (16 slots, summed over CTAs).
+ * Only in builds made with -DFFVD_PHASE_TIMING (tools/phase_timing.py); FFVD_E_UNSUPPORTED otherwise. */
+int ffvd_debug_phase_clocks(ffvd_ctx* ctx, int reset, uint64_t* out16);
 
 /* kernels_multi_output.py:202-214,246-247 / kernels.py:270-276  K(X, X2) -> out (N,N2).
  * X2 may be NULL (K(X,X)).  logv: () ; logl: (Din) for SE, NULL for Linear. */

@@ -1,8 +1,11 @@
 """Developer parity sweep: CUDA path (through the C ABI) vs the CPU oracle, per tensor.
-Run on a GPU box:  python tools/dev_check.py [quick]"""
+Run on a GPU box:  python tools/dev_check.py [quick|large|dev]   (dev: uses lib/libffvd_b200_dev.so)"""
 import copy
 import sys
 import os
+if len(sys.argv) > 1 and sys.argv[1] == "dev":
+    os.environ.setdefault("FFVD_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                        "ffvd_b200", "lib", "libffvd_b200_dev.so"))
 import time
 
 import numpy as np
@@ -54,6 +57,7 @@ def compare(a, b, tag, tol=1e-9):
 
 def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    devmin = len(sys.argv) > 1 and sys.argv[1] == "dev"      # -DFFVD_DEV_MINIMAL library: SE uncollapsed, Mp in {128,256,512}
     ok = True
     cases = []
     cases.append(("synthetic T=70 M=24 D=2 S=1", fixtures.synthetic_problem(T=70, M=24, D=2, S=1)))
@@ -76,8 +80,10 @@ def main():
             cases.append(("synthetic T=40 M=1000 D=2 S=1 (Mp=1024)", fixtures.synthetic_problem(T=40, M=1000, D=2, S=1)))
             cases.append(("synthetic T=30 M=1400 D=1 S=1 (Mp=1536)", fixtures.synthetic_problem(T=30, M=1400, D=1, S=1)))
             cases.append(("synthetic T=20 M=2048 D=1 S=1 (Mp=2048)", fixtures.synthetic_problem(T=20, M=2048, D=1, S=1)))
+    if devmin:
+        cases = [(t, p) for t, p in cases if p.kind == 0 and "Mp=384" not in t]
     for tag, prob in cases:
-        for collapsed in (False, True):
+        for collapsed in ((False,) if devmin else (False, True)):
             t = time.time()
             ref = O.nll_and_grads(prob, collapsed=collapsed)
             try:
