@@ -10,7 +10,13 @@
 #include <vector>
 
 #include "elementwise.cuh"
+#ifdef FFVD_SPLIT_BUILD
+#include "ffvd_common.cuh"
+#include "fused_modes.cuh"
+#else
 #include "fused.cuh"
+#endif
+#include "fused_table.cuh"
 #include "prep_post.cuh"
 #include "blocked_chol.cuh"
 
@@ -236,7 +242,7 @@ struct Layout {
   int nprob, nb, D, M, Mp, Din, Dy, nk;   // nk = kernels per problem (D, or 1 when shared)
   long long sumS;
   bool collapsed;
-  size_t off_ZT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
+  size_t off_ZT, off_ZTs, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
       off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, total;
   int nfac;                        // matrices in the blocked-factorisation pools: nprob * max(nk, nb)
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
@@ -253,7 +259,8 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   const size_t mm = (size_t)Mp * Mp * sizeof(double);
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.off_ZT = take((size_t)nprob * 64 * Mp * 8);          // Z~^T and its fragment-ordered copy
-  L.off_kscr = take((size_t)160 * 64 * Mp * 8);          // per-CTA K-tile scratch of the fused kernel
+  L.off_ZTs = take((size_t)nprob * nk * 32 * Mp * 8);
+  L.off_kscr = take((size_t)320 * 64 * Mp * 8);          // per-CTA K-tile scratch of the fused kernel (<= 2 CTAs / SM)
   L.off_Linv = take((size_t)nprob * nk * mm);
   L.off_LinvT = take((size_t)nprob * nk * mm);
   L.off_utmp = take((size_t)nprob * M * D * 8);
@@ -265,7 +272,7 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   L.off_Hx = take(collapsed ? (size_t)nprob * nb * mm : 0);
   L.off_HxT = take(collapsed ? (size_t)nprob * nb * mm : 0);
   L.off_cvec = take(collapsed ? (size_t)nprob * nb * Mp * 8 : 0);
-  L.off_wvec = take(collapsed ? (size_t)nprob * nb * Mp * 8 : 0);
+  L.off_wvec = take((size_t)nprob * nb * Mp * 8);        // uncollapsed: L^{-T} u ; collapsed: w'
   L.off_rs = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
   L.zero_begin = o;
   L.off_Sacc = take(need_acc ? (size_t)nprob * nb * mm : 0);
@@ -313,6 +320,7 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   const size_t mm = (size_t)L.Mp * L.Mp;
   P.ZT = (double*)(a + L.off_ZT) + (size_t)p * 64 * L.Mp;
   P.Zf = P.ZT + (size_t)32 * L.Mp;
+  P.ZTs = (double*)(a + L.off_ZTs) + (size_t)p * L.nk * 32 * L.Mp;
   P.Linv = (double*)(a + L.off_Linv) + (size_t)p * L.nk * mm;
   P.LinvT = (double*)(a + L.off_LinvT) + (size_t)p * L.nk * mm;
   P.Sacc = (double*)(a + L.off_Sacc) + (size_t)p * L.nb * mm;
@@ -339,8 +347,9 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch helpers
 // Tile configuration per padded M: RB row blocks (BT = 8*RB time steps per tile) and NW warps per CTA.
-// Overridable for experiments with FFVD_RB / FFVD_NW (only the combinations instantiated below exist).
-struct FusedCfg { int rb, nw; };
+// Tile configuration of the fused kernel for a padded inducing-point count.  Overridable for experiments with
+// FFVD_RB / FFVD_NW / FFVD_MINB (only the combinations instantiated below exist).
+struct FusedCfg { int rb, nw, minb; };
 // supported padded sizes: 128 * {1,2,3,4,6,8,12,16}
 static int pad_M(int M) {
   static const int sizes[] = {128, 256, 384, 512, 768, 1024, 1536, 2048};
@@ -353,33 +362,32 @@ static FusedCfg fused_cfg(int Mp) {
   const int ngw = Mp / 128;
   cfg.rb = (ngw <= 2) ? 8 : (ngw <= 4 ? 4 : (ngw <= 8 ? 2 : 1));
   cfg.nw = (ngw == 1) ? 16 : 8;
+  cfg.minb = 1;
   if (const char* e = getenv("FFVD_RB")) cfg.rb = atoi(e);
   if (const char* e = getenv("FFVD_NW")) cfg.nw = atoi(e);
+  if (const char* e = getenv("FFVD_MINB")) cfg.minb = atoi(e);
   return cfg;
 }
 
 template <int KIND, int MODE>
-static int launch_fused(ffvd_ctx* c, int Mp, const DevProblem* d_probs, int nprob, long long total_items) {
+static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs, int nprob, long long total_items) {
   const int ngw = Mp / 128;
   const FusedCfg cfg = fused_cfg(Mp);
-  void (*kern)(const DevProblem*, int, long long, double*) = nullptr;
-#define FFVD_PICK(RB_, NGW_, NW_) \
-  if (ngw == NGW_ && cfg.rb == RB_ && cfg.nw == NW_) kern = fused_kernel<KIND, RB_, NGW_, MODE, NW_>;
-#ifdef FFVD_DEV_MINIMAL
-  // kernel-development build (seconds instead of minutes): SE uncollapsed only, three tile shapes
-  if constexpr (KIND == 0 && MODE == MODE_UNCOLLAPSED) { FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 4, 8) }
+#ifdef FFVD_SPLIT_BUILD
+  ffvd_fused_fn kern = ffvd_fused_lookup(KIND, MODE, cfg.rb, ngw, cfg.nw, cfg.minb);    // instantiated in fused_inst.cu objects
 #else
-  FFVD_PICK(8, 1, 16) FFVD_PICK(8, 2, 8) FFVD_PICK(4, 3, 8) FFVD_PICK(4, 4, 8)
-  FFVD_PICK(2, 6, 8) FFVD_PICK(2, 8, 8) FFVD_PICK(1, 12, 8) FFVD_PICK(1, 16, 8)
-  if (KIND == 0 && MODE == MODE_UNCOLLAPSED) { FFVD_PICK(8, 1, 8) }
+  ffvd_fused_fn kern = ffvd_fused_pick<KIND, MODE>(cfg.rb, ngw, cfg.nw, cfg.minb);
 #endif
-#undef FFVD_PICK
-  if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_NW)");
+  if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_NW, FFVD_MINB)");
   const int RB = cfg.rb;
-  const size_t smem = fused_smem_bytes(RB, Mp, cfg.nw);
+  const size_t smem = fused_smem_bytes(RB, Mp, cfg.nw, (Din + 1 <= 16) ? 2 : 4);
   if ((int)smem > c->max_smem) return fail(FFVD_E_LIMIT, "fused kernel shared memory exceeds the device limit");
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long cap = (long long)c->num_sms;
+  int per_sm = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * cfg.nw, smem));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > cfg.minb) per_sm = cfg.minb;
+  const long long cap = (long long)c->num_sms * per_sm;      // persistent grid: every CTA resident
   long long grid = total_items < cap ? total_items : cap;
   if (grid < 1) return FFVD_OK;
   const int slot = (int)(c->ev_count % ffvd_ctx::kRing);
@@ -404,6 +412,7 @@ static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
 
 template <int KIND>
 static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter) {
+  if (KIND == 0) { zscale_kernel<<<dim3(L.nk, L.nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
   if (use_blocked(c, L.M, L.Mp)) {
     double* Lfac = (double*)(c->arena + L.off_Lfac);
     const size_t nel = (size_t)L.Mp * L.Mp > (size_t)32 * L.Mp ? (size_t)L.Mp * L.Mp : (size_t)32 * L.Mp;
@@ -596,12 +605,13 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   const dim3 gsym((unsigned)((size_t)M * M + 255) / 256, nb, nprob);
 
   if (no_grads && !collapsed) {
-    TRY((launch_fused<KIND, MODE_FORWARD>(c, Mp, c->d_probs, nprob, total_items)));
+    TRY((launch_fused<KIND, MODE_FORWARD>(c, Mp, Din, c->d_probs, nprob, total_items)));
   } else if (!collapsed) {
-    TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, c->d_probs, nprob, total_items)));
+    ltu_kernel<<<dim3(D, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, Din, c->d_probs, nprob, total_items)));
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 0); c->launches++;
   } else {
-    TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, c->d_probs, nprob, total_items)));
+    TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, Din, c->d_probs, nprob, total_items)));
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 1); c->launches++;
     if (use_blocked(c, M, Mp)) {
       collapsed_fill_kernel<<<dim3((unsigned)(((size_t)Mp * Mp + 255) / 256), nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
@@ -615,7 +625,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       collapsed_vec_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
       TRY(launch_bgemm(c, Hx, Wk, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Mat' L^{-1}
       TRY(launch_bgemm(c, Nmat, LinvT, Hx, Mp, 1.0, nz, idm, lmap, idm));     // N = L^{-T} Mat' L^{-1}
-      TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, c->d_probs, nprob, total_items)));
+      TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, Din, c->d_probs, nprob, total_items)));
       TRY(launch_bgemm(c, HxT, Wk, Sacc, Mp, 1.0, nz, idm, idm, idm));        // Mat' S
       symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 2); c->launches++;   // Sacc <- Gs
     } else {
@@ -820,8 +830,8 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
     P.U = utmp;
     CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
   }
-  if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, c->d_probs, 1, P.nitems)));
-  else TRY((launch_fused<1, MODE_COND>(c, P.Mp, c->d_probs, 1, P.nitems)));
+  if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
+  else TRY((launch_fused<1, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   int st = check_status(c, L);
   TRY(call.finish());
   return st;

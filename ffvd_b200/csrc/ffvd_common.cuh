@@ -25,6 +25,7 @@ struct DevProblem {
   // derived inputs (written by kzz_prep)
   double *ZT;          // [32][Mp]    Z~^T: transposed, zero padded inducing inputs, then a row of ones (m < M), zeros
   double *Zf;          // [Mp/4][4][32] the same matrix in DMMA B-fragment order: entry ((m>>2)*4 + (jd>>3))*32 + (jd&7)*4 + (m&3)
+  double *ZTs;         // [nk][32][Mp] SE: per-kernel scaled copy z~ = z/l (rows 0..Din-1) and row Din = -1/2 |z~_m|^2
   double *Linv;        // [D][Mp][Mp] L^{-1}  (lower), zero padded
   double *LinvT;       // [D][Mp][Mp] L^{-T}  (upper)
   // accumulators (zeroed before each evaluation)
@@ -63,32 +64,40 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// exp(x) for x <= ~0 (the SE kernel argument -r^2/2), branch free so that independent evaluations interleave:
+// exp(x) for x <= ~0 (the SE kernel argument -r^2/2), branch free, N independent evaluations advanced in lock step
+// so that the FP64 pipe always has N independent FMAs to issue (the pipe is narrow: two warps per scheduler cannot
+// hide its latency with one dependent Horner chain each).
 // x = n ln2 + r, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^n applied to the exponent bits.
-// <= 1 ulp from the correctly rounded result on [-700, 1e-9] (checked on the host against libm); x < -700 clamps
-// to exp(-700) ~ 1e-304, i.e. 0 at the scale of every quantity the kernels form.
+// <= 1 ulp from the correctly rounded result on [-700, 1e-9] (checked on the host against libm).  Valid for
+// x >= -1e6 (the low word of t must hold n); below -708 the result saturates near 1e-308, i.e. 0 at the scale of
+// every quantity the kernels form.
+template <int N>
+__device__ __forceinline__ void exp_nonpos_n(double (&x)[N]) {
+  double r[N], p[N];
+  int n[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double t = fma(x[i], 1.4426950408889634, 6755399441055744.0);
+    n[i] = max(__double2loint(t), -1022);      // x < -708: the scale saturates at 2^-1022 (result ~ 1e-308 ~ 0)
+    const double nd = t - 6755399441055744.0;
+    r[i] = fma(nd, -6.93147180369123816490e-01, x[i]);
+    r[i] = fma(nd, -1.90821492927058770002e-10, r[i]);
+    p[i] = fma(1.0 / 6227020800.0, r[i], 1.0 / 479001600.0);
+  }
+  const double cf[12] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+                         1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,           1.0,          1.0};
+#pragma unroll
+  for (int k = 0; k < 12; ++k)
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], cf[k]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = __hiloint2double(__double2hiint(p[i]) + (n[i] << 20), __double2loint(p[i]));
+}
+
 __device__ __forceinline__ double exp_nonpos(double x) {
-  x = fmax(x, -700.0);
-  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
-  const int n = __double2loint(t);
-  const double nd = t - 6755399441055744.0;
-  double r = fma(nd, -6.93147180369123816490e-01, x);
-  r = fma(nd, -1.90821492927058770002e-10, r);
-  double p = 1.0 / 6227020800.0;
-  p = fma(p, r, 1.0 / 479001600.0);
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  double a[1] = {x};
+  exp_nonpos_n<1>(a);
+  return a[0];
 }
 
 // Fire-and-forget FP64 add to GLOBAL memory.  atomicAdd() on a pointer whose address space the compiler cannot prove

@@ -26,96 +26,115 @@ __device__ unsigned long long g_phase_clocks[16];
 #define FFVD_MARK(i) do { } while (0)
 #endif
 
-#ifndef FFVD_ABLATE
-#define FFVD_ABLATE 0      // timing experiments only: 1 = no S REDs, 2 = no SYRK, 3 = no L^{-1} operand loads
-#endif
-
-enum { MODE_UNCOLLAPSED = 0, MODE_COLLAPSED_P1 = 1, MODE_COLLAPSED_P2 = 2, MODE_FORWARD = 3, MODE_COND = 4 };
+} // namespace ffvd
+#include "fused_modes.cuh"
+namespace ffvd {
 
 struct Smem {
   double* tile;     // BT x lda
   double* xs;       // (BT+1) x XLD : X~ rows t0..t0+BT  = [x_t, ctrl_t, 1, 0..]
   double* xsc;      // BT x XLD     : SE: x~ scaled by 1/l_j ; unused for Linear
   double* us;       // Mp           : u_d (uncollapsed) / w'_d (collapsed pass 2)
+  double* ws;       // Mp           : uncollapsed: w_d = L^{-T} u_d
   double* es;       // 64           : e_t (uncollapsed) / delta_t (collapsed)
-  double* rowpart;  // 2 x 8 x 64
+  double* rowpart;  // 2 x 8 x BT
   double* stage;    // NW warps x 8 x 40
-  double* part;     // 128 x 32: partial products of W [Z,1] per k slice (overlays xsc)
+  double* part;     // 128 x 8 NBM: partial products of W [Z,1] per k slice (overlays xsc / stage)
   double* small;    // 64: invl2[32], sil[32]
   double* xn2h;     // 64: SE: -1/2 |x~_r|^2 of the scaled rows
   double* sc;       // 8: per-item scalars v, Q, 1/Q, log Q
   double* red;      // 40: block-level reductions (smem atomics)
 };
 
-template <int RB>
-__host__ __device__ constexpr int bt_of() { return 8 * RB; }
-
-// xsc (SE: scaled x rows, used while the K tile is formed) and part (128 x 32 partial products of W [Z,1], used by the
-// last phase) share one region
-__host__ __device__ inline size_t fused_xsc_part_doubles(int BT) {
-  const size_t a = ((size_t)BT * FFVD_XLD + 1) & ~(size_t)1, b = 128 * 32;
-  return a > b ? a : b;
-}
-
-__host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp, int NW) {
-  const int BT = 8 * RB;
-  // every sub-array is rounded up to an even number of doubles so that all of them stay 16-byte aligned
-  size_t n = (size_t)BT * (Mp + 4) + (size_t)NW * 8 * 40 + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
-             fused_xsc_part_doubles(BT) + Mp + 64 + 2 * 8 * 64 + 64 + 64 + 8 + 40;
-  return n * sizeof(double);
-}
-
 // ---------------------------------------------------------------------------------------------
-// k(x_r, z_j) for the (rows 8*rb+g, cols jbase..jbase+3) owned by this lane.
-// SE follows the reference's expansion (kernels_multi_output.py:163-182): r^2 = |x~|^2 + |z~|^2 - 2 x~.z~ with
-// x~ = x/l, z~ = z/l, so the inner loop is one FMA per (element, input dim); exp through the branch-free exp_nonpos.
-template <int KIND, int RB>
-__device__ __forceinline__ void compute_k_group(double (&kv)[RB][4], const Smem& sm, const double* __restrict__ ZT,
-                                                int Mp, int Din, double v, int jbase, int g, int M, int nvalid, int row0) {
-  double s[RB][4];
+// K tile: k(x_r, z_j) for this warp's rows [row0, row0 + 8 RB) and column groups, written to the shared tile (and,
+// when SCR, to the CTA's L2 scratch copy that W = Kbar o K reads back).  Rows >= nvalid are NOT masked here (the
+// caller zeroes them in the rare partial tile); columns >= M get exact zeros through the per-column factor.
+// SE follows the reference's expansion (kernels_multi_output.py:163-182): -r^2/2 = x~.z~ - |x~|^2/2 - |z~|^2/2 with
+// x~ = x/l (sm.xsc, sm.xn2h) and z~ = z/l (ZTd rows 0..Din-1, row Din = -|z~|^2/2, zscale_kernel): one FMA per
+// (element, input dim); exp through the branch-free, lock-step exp_nonpos_n.  Linear: ZTd = Z~^T unscaled.
+// The ZTd rows stream from L2 through a 4-slot register ring (4 input dims ahead); the first rows of the next column
+// group are requested before the exp / store work of the current one.
+template <int KIND, int RB, int NGW, bool SCR>
+__device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __restrict__ ZTd, int Mp, int Din, double v,
+                                               int wc, int g, int q, int M, int row0, int lda, double* __restrict__ kscr) {
+  double2 ring[4][2], hz[2];
+  auto prologue = [&](int jb) {
 #pragma unroll
-  for (int rb = 0; rb < RB; ++rb)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) s[rb][c] = 0.0;
-  double zz[4] = {0.0, 0.0, 0.0, 0.0};
-  const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + g) * FFVD_XLD;
-  // one-step software pipeline on the (L1/L2-resident) Z^T loads
-  double2 n01 = __ldg(reinterpret_cast<const double2*>(ZT + jbase));
-  double2 n23 = __ldg(reinterpret_cast<const double2*>(ZT + jbase + 2));
-  for (int jd = 0; jd < Din; ++jd) {
-    const double2 z01 = n01, z23 = n23;
-    if (jd + 1 < Din) {
-      n01 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)(jd + 1) * Mp + jbase));
-      n23 = __ldg(reinterpret_cast<const double2*>(ZT + (size_t)(jd + 1) * Mp + jbase + 2));
-    }
-    double z[4] = {z01.x, z01.y, z23.x, z23.y};
-    if (KIND == 0) {
-      const double sil = sm.small[32 + jd];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        z[c] *= sil;
-        zz[c] = fma(z[c], z[c], zz[c]);
+    for (int u = 0; u < 4; ++u) {
+      ring[u][0] = ring[u][1] = make_double2(0.0, 0.0);
+      if (u < Din) {
+        ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)u * Mp + jb));
+        ring[u][1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)u * Mp + jb + 2));
       }
     }
-#pragma unroll
-    for (int rb = 0; rb < RB; ++rb) {
-      const double x = xsrc[8 * rb * FFVD_XLD + jd];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s[rb][c] = fma(x, z[c], s[rb][c]);
+    if (KIND == 0) {
+      hz[0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)Din * Mp + jb));
+      hz[1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)Din * Mp + jb + 2));
     }
-  }
-  if (KIND == 0) {
+  };
+  prologue(16 * group_index(wc, 0) + 4 * q);
+  const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + g) * FFVD_XLD;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) zz[c] *= -0.5;
-  }
+  for (int ng = 0; ng < NGW; ++ng) {
+    const int jb = 16 * group_index(wc, ng) + 4 * q;
+    double s[RB][4];
+    {
+      const double h[4] = {hz[0].x, hz[0].y, hz[1].x, hz[1].y};
 #pragma unroll
-  for (int rb = 0; rb < RB; ++rb) {
-    const double hx = (KIND == 0) ? sm.xn2h[row0 + 8 * rb + g] : 0.0;
+      for (int rb = 0; rb < RB; ++rb) {
+        const double hx = (KIND == 0) ? sm.xn2h[row0 + 8 * rb + g] : 0.0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      double k = (KIND == 0) ? v * exp_nonpos(s[rb][c] + (hx + zz[c])) : v * s[rb][c];
-      if (jbase + c >= M || row0 + 8 * rb + g >= nvalid) k = 0.0;
-      kv[rb][c] = k;
+        for (int c = 0; c < 4; ++c) s[rb][c] = (KIND == 0) ? hx + h[c] : 0.0;
+      }
+    }
+    for (int j0 = 0; j0 < Din; j0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jd = j0 + u;
+        if (jd < Din) {
+          const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
+          if (jd + 4 < Din) {
+            ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + 4) * Mp + jb));
+            ring[u][1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + 4) * Mp + jb + 2));
+          }
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb) {
+            const double x = xsrc[8 * rb * FFVD_XLD + jd];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[rb][c] = fma(x, z[c], s[rb][c]);
+          }
+        }
+      }
+    }
+    if (ng + 1 < NGW) prologue(16 * group_index(wc, ng + 1) + 4 * q);
+    double vc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) vc[c] = (jb + c < M) ? v : 0.0;
+    // exp in lock-step batches of RBB rows x 4 columns
+    constexpr int RBB = RB >= 2 ? 2 : 1;
+#pragma unroll
+    for (int rb0 = 0; rb0 < RB; rb0 += RBB) {
+      double kv[RBB * 4];
+#pragma unroll
+      for (int i = 0; i < RBB; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kv[4 * i + c] = s[rb0 + i][c];
+      if (KIND == 0) exp_nonpos_n<RBB * 4>(kv);
+#pragma unroll
+      for (int i = 0; i < RBB; ++i) {
+        const int row = row0 + 8 * (rb0 + i) + g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kv[4 * i + c] *= vc[c];
+        double* p = sm.tile + row * lda + jb;
+        *reinterpret_cast<double2*>(p) = make_double2(kv[4 * i], kv[4 * i + 1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
+        if (SCR) {
+          double* sp = kscr + (size_t)row * Mp + jb;
+          *reinterpret_cast<double2*>(sp) = make_double2(kv[4 * i], kv[4 * i + 1]);
+          *reinterpret_cast<double2*>(sp + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
+        }
+      }
     }
   }
 }
@@ -440,6 +459,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
   constexpr int KLEN = 128 * NGW / KS;         // columns of W per slice
   constexpr int TRIPS = KLEN / 16;
   constexpr int PF = 2;
+  constexpr int PW = 8 * NBM;                  // row stride of part
   static_assert(KS * BT <= 128, "part holds 128 rows");
   if (warp < 8) {
     const int rg = warp % RG, ks = warp / RG;
@@ -484,7 +504,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 #pragma unroll
       for (int nb = 0; nb < NBM; ++nb)
         if (nb < nbx)
-          *reinterpret_cast<double2*>(sm.part + (size_t)(ks * BT + 8 * (RPW * rg + r) + g) * 32 + 8 * nb + 2 * q) =
+          *reinterpret_cast<double2*>(sm.part + (size_t)(ks * BT + 8 * (RPW * rg + r) + g) * PW + 8 * nb + 2 * q) =
               make_double2(c[r][nb][0], c[r][nb][1]);
   }
   FFVD_MARK(9);
@@ -498,8 +518,8 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
       double wz = 0.0, rs = 0.0;
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        wz += sm.part[(size_t)(k * BT + r) * 32 + lane];
-        rs += sm.part[(size_t)(k * BT + r) * 32 + Din];
+        if (lane < PW) wz += sm.part[(size_t)(k * BT + r) * PW + lane];
+        rs += sm.part[(size_t)(k * BT + r) * PW + Din];
       }
       if (lane < Din) {
         const double x = sm.xs[r * FFVD_XLD + lane];
@@ -525,8 +545,10 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 // NW warps per CTA (8 or 16).  Warp w owns the column groups of "column warp" wc = w & 7 and the
 // row blocks [wr*RBW, (wr+1)*RBW) with wr = w >> 3, RBW = RB / (NW/8): 16 warps share one tile and
 // double the latency-hiding capacity of the SM without shrinking the tile.
-template <int KIND, int RB, int NGW, int MODE, int NW>
-__global__ void __launch_bounds__(32 * NW, 1)
+// MINB = CTAs per SM the kernel is built for (register cap 65536 / (32 NW MINB)): two co-resident CTAs let one CTA's
+// tensor-pipe phases run under the other's K-tile / statistics / flush phases.
+template <int KIND, int RB, int NGW, int MODE, int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB)
 fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_items, double* __restrict__ kscr_base) {
   extern __shared__ __align__(16) double smem_raw[];
   constexpr int BT = 8 * RB;
@@ -567,12 +589,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     {
       double* p = smem_raw;
       sm.tile = p; p += (size_t)BT * lda;
-      sm.stage = p; p += NW * 8 * 40;
       sm.xs = p; p += ((BT + 1) * FFVD_XLD + 1) & ~1;
-      sm.xsc = p; sm.part = p; p += fused_xsc_part_doubles(BT);
+      sm.xsc = p; sm.part = p; sm.stage = p; p += fused_xsc_part_doubles(BT, NW, (Din + 1 <= 16) ? 2 : 4);
       sm.us = p; p += Mp;
+      sm.ws = p; p += Mp;
       sm.es = p; p += 64;
-      sm.rowpart = p; p += 2 * 8 * 64;
+      sm.rowpart = p; p += 2 * 8 * BT;
       sm.small = p; p += 64;
       sm.xn2h = p; p += 64;
       sm.sc = p; p += 8;
@@ -617,9 +639,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         else if (MODE == MODE_COLLAPSED_P2) u = P.wvec[((size_t)s * D + d) * Mp + j];
       }
       sm.us[j] = u;
+      if (MODE == MODE_UNCOLLAPSED) sm.ws[j] = P.wvec[(size_t)d * Mp + j];
     }
     __syncthreads();
-    const double v = sm.sc[0], Q = sm.sc[1], invQ = sm.sc[2], logQd = sm.sc[3];
+    const double v = sm.sc[0], invQ = sm.sc[2], logQd = sm.sc[3];
     if (KIND == 0) {
       for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
         const int r = idx >> 5, c = idx & 31;
@@ -639,26 +662,13 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
     FFVD_MARK(0);
 
-    // ---- P1: K tile -> shared
-    {
-#pragma unroll
-      for (int ng = 0; ng < NGW; ++ng) {
-        double kv[RBW][4];
-        const int jb = 16 * group_index(wc, ng) + 4 * q;
-        compute_k_group<KIND, RBW>(kv, sm, P.ZT, Mp, Din, v, jb, g, M, nvalid, row0);
-#pragma unroll
-        for (int rb = 0; rb < RBW; ++rb) {
-          double* p = sm.tile + (row0 + 8 * rb + g) * lda + jb;
-          *reinterpret_cast<double2*>(p) = make_double2(kv[rb][0], kv[rb][1]);
-          *reinterpret_cast<double2*>(p + 2) = make_double2(kv[rb][2], kv[rb][3]);
-          if (KIND == 0 && MODE == MODE_UNCOLLAPSED) {
-            // keep a copy of the K tile in this CTA's L2-resident scratch: it is needed again for W = Kbar o K
-            double* s = kscr + (size_t)(row0 + 8 * rb + g) * Mp + jb;
-            *reinterpret_cast<double2*>(s) = make_double2(kv[rb][0], kv[rb][1]);
-            *reinterpret_cast<double2*>(s + 2) = make_double2(kv[rb][2], kv[rb][3]);
-          }
-        }
-      }
+    // ---- P1: K tile -> shared (SE uncollapsed: also to this CTA's L2-resident scratch, needed again for W = Kbar o K)
+    compute_k_tile<KIND, RBW, NGW, (KIND == 0 && MODE == MODE_UNCOLLAPSED)>(
+        sm, (KIND == 0) ? P.ZTs + (size_t)dh * 32 * Mp : P.ZT, Mp, Din, v, wc, g, q, M, row0, lda, kscr);
+    if (nvalid < BT) {
+      // partial last tile of a sample: rows >= nvalid must be inert (exact zeros)
+      __syncthreads();
+      for (int idx = tid; idx < (BT - nvalid) * Mp; idx += NTH) sm.tile[(nvalid + idx / Mp) * lda + idx % Mp] = 0.0;
     }
     __syncthreads();
     FFVD_MARK(1);
@@ -697,8 +707,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
           sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 1);
           sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 2);
           if (q == 0) {
-            sm.rowpart[(0 * 8 + wc) * 64 + row0 + 8 * rb + g] = su[rb];
-            sm.rowpart[(1 * 8 + wc) * 64 + row0 + 8 * rb + g] = sa[rb];
+            sm.rowpart[(0 * 8 + wc) * BT + row0 + 8 * rb + g] = su[rb];
+            sm.rowpart[(1 * 8 + wc) * BT + row0 + 8 * rb + g] = sa[rb];
           }
         }
       }
@@ -715,8 +725,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             double su = 0.0, sa = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-              su += sm.rowpart[(0 * 8 + w) * 64 + r];
-              sa += sm.rowpart[(1 * 8 + w) * 64 + r];
+              su += sm.rowpart[(0 * 8 + w) * BT + r];
+              sa += sm.rowpart[(1 * 8 + w) * BT + r];
             }
             const double xd = sm.xs[r * FFVD_XLD + d], xn = sm.xs[(r + 1) * FFVD_XLD + d];
             double kdiag = v;
@@ -834,19 +844,23 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
 
     if (MODE == MODE_UNCOLLAPSED) {
-      // ---- P4: Kbar = Abar L^{-1},  abar_rj = e_r u_j + a_rj / Q  formed on the fly
+      // ---- P4: Kbar = Abar L^{-1} with abar_r = e_r u + a_r / Q.  By linearity Kbar = (A L^{-1})/Q + e w^T with
+      //      w = L^{-T} u (ltu_kernel, once per evaluation), so the contraction reads A unmodified.
+      tile_gemm<RBW, NGW, -1>(acc, wtile, lda, Linv, Mp, wc, g, q,
+                              [](double x, int, int) { return x; });
       double er[RBW];
 #pragma unroll
-      for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g] * Q;      // residual = e * Q
-      const double* us = sm.us;
-      tile_gemm<RBW, NGW, -1>(acc, wtile, lda, Linv, Mp, wc, g, q,
-                              [&](double x, int rb, int k) { return fma(er[rb], us[k], x); });
+      for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g];
 #pragma unroll
-      for (int ng = 0; ng < NGW; ++ng)
+      for (int ng = 0; ng < NGW; ++ng) {
+        const int jb = 16 * group_index(wc, ng) + 4 * q;
 #pragma unroll
-        for (int rb = 0; rb < RBW; ++rb)
+        for (int c = 0; c < 4; ++c) {
+          const double w = sm.ws[jb + c];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[ng][rb][c] *= invQ;
+          for (int rb = 0; rb < RBW; ++rb) acc[ng][rb][c] = fma(acc[ng][rb][c], invQ, er[rb] * w);
+        }
+      }
     } else if (MODE == MODE_COLLAPSED_P2) {
       // ---- Kbar = K N + delta w'^T ; also dbar_r = k_r . w'
       tile_gemm<RBW, NGW, 0>(acc, wtile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, g, q,

@@ -392,6 +392,42 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
   tri_inverse(H, Mp, M, X, XT, Mp, sh + Mp);
 }
 
+// SE: per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded) and, in row Din, -1/2 |z~_m|^2 -- the
+// column half of the reference's expansion of the scaled squared distance (kernels_multi_output.py:163-182).
+// grid (nk, nprob); block 256.
+__global__ void __launch_bounds__(256) zscale_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  const int d = blockIdx.x, M = P.M, Mp = P.Mp, Din = P.Din;
+  double* out = P.ZTs + (size_t)d * 32 * Mp;
+  for (int m = threadIdx.x; m < Mp; m += blockDim.x) {
+    double a = 0.0;
+    for (int jd = 0; jd < Din; ++jd) {
+      double z = 0.0;
+      if (m < M) z = P.Z[(size_t)m * Din + jd] * exp(-P.logl[(size_t)d * Din + jd]);
+      out[(size_t)jd * Mp + m] = z;
+      a = fma(z, z, a);
+    }
+    out[(size_t)Din * Mp + m] = -0.5 * a;
+  }
+}
+
+// Uncollapsed: w_d = L_d^{-T} u_d, so that the fused kernel can form Kbar = (A L^{-1})/Q + e w^T without touching the
+// A operand of its second contraction.  grid (D, nprob); block 256 (warp per row of the upper-triangular L^{-T}).
+__global__ void __launch_bounds__(256) ltu_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  const int d = blockIdx.x, M = P.M, Mp = P.Mp, D = P.D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double* LT = P.LinvT + (size_t)d * P.hs * Mp * Mp;
+  double* w = P.wvec + (size_t)d * Mp;
+  for (int m = warp; m < Mp; m += 8) {
+    double t = 0.0;
+    if (m < M)
+      for (int n = (m & ~31) + lane; n < M; n += 32) t = fma(LT[(size_t)m * Mp + n], P.U[(size_t)n * D + d], t);
+    t = warp_sum(t);
+    if (lane == 0) w[m] = t;
+  }
+}
+
 // After Hinv = L_H^{-T} L_H^{-1} is in Wk[b]:  c = Hinv b/Q ; w' = L^{-T} c / Q ; quad; dJ/dlogQ;
 // then Wk[b] <- Mat' = (I - Hinv - c c^T)/Q.     grid (S*D, nprob); block 256.
 __global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __restrict__ probs) {
