@@ -107,11 +107,15 @@ __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v));
 }
 
-// 16-byte read-only load that does not allocate in L1: the L^{-1} / L^{-T} operand streams are used once per tile,
-// keeping them out of L1 leaves it to the small reused arrays (Z~^T, Zf).
+// 16-byte read-only load for the L^{-1} / L^{-T} operand streams: no L1 allocation (each element is used once per
+// tile) and an L2 evict-last policy -- the D matrices (8 MB at C3) are re-read by every tile for the whole kernel while
+// X / x-bar (hundreds of MB) stream through the same L2; without the hint the streams kept evicting them and the
+// kernel re-fetched them from HBM ~700 times (ncu: 6.4 GB of DRAM reads against 0.8 GB of X + x-bar).
 __device__ __forceinline__ double2 ldg_stream2(const double* p) {
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   double2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
 }
 

@@ -563,7 +563,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
   long long _phase_last = clock64();
 #endif
   for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-    // ---- decode item -> (problem, d, s, tile); d is the slowest index inside a problem
+    // ---- decode item -> (problem, s, tile, d)
     int pi = 0;
     {
       int lo = 0, hi = nprob - 1;
@@ -575,9 +575,13 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
     const DevProblem& P = probs[pi];
     const long long li = item - P.item_begin;
-    const int tile_i = (int)(li % P.ntiles);
-    const int s = (int)((li / P.ntiles) % P.S);
-    const int d = (int)(li / ((long long)P.ntiles * P.S));
+    // d is the FASTEST index: the D items of one (sample, tile) run on neighbouring CTAs at the same time, so the
+    // x tile is fetched from HBM once and the D contributions to its x-bar rows meet in L2 (ordering d slowest re-read
+    // X and re-wrote x-bar once per output dim: 8x the algorithmic DRAM bytes at C3, ncu round-1 capture)
+    const int d = (int)(li % P.D);
+    const long long st = li / P.D;
+    const int tile_i = (int)(st % P.ntiles);
+    const int s = (int)(st / P.ntiles);
     const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, Mp = P.Mp, nc = P.nc;
     const int lda = Mp + 4;
     const int t0 = tile_i * BT;
