@@ -267,6 +267,12 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax.item()) / K
+    # per-rank device time of the fused kernel (diagnostic: shows which GPU of the box set the max)
+    per_rank_fused = [fused_ms / max(fused_n, 1)]
+    if world > 1:
+        tl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([per_rank_fused[0]], dtype=torch.float64, device=dev))
+        per_rank_fused = [float(t.item()) for t in tl]
     units = S * T * D * world
     value = units / (ms_per_step * 1e-3)
     nll_check = float(out["nll"].mean().item())
@@ -337,6 +343,7 @@ def main():
                          "peak_source": "measured live: cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json holds no FP64 figure); DMMA issue peak 37.15 TF (tools/probe)",
                          "algorithmic_flops_per_unit": algorithmic_flops_per_unit(M, Din), "fused_ms_per_launch": fused_ms / max(fused_n, 1),
                          "fused_share_of_step": (fused_ms / max(fused_n, 1)) / ms_per_step,
+                         "fused_ms_per_rank": per_rank_fused,
                          "hbm_gbs_measured": peaks.get("hbm_gbs")},
             "clocks": clocks,
             "nll_mean": nll_check,

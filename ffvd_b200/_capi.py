@@ -77,6 +77,7 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_kernel_Kdiag.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.ffvd_kernel_pre_cal.argtypes = [vp, ci, vp, vp, vp, cd, vp]
     lib.ffvd_conditional.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, vp, vp]
+    lib.ffvd_collapse_u_mean.argtypes = [vp, ci, ctypes.POINTER(_Problem), cd, vp, vp]
     lib.ffvd_logdensity_norm_diag.argtypes = [vp, vp, vp, vp, ci, vp]
     lib.ffvd_nll_grads_uncollapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
     lib.ffvd_nll_grads_collapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
@@ -85,7 +86,8 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_adam_update.argtypes = [vp, vp, vp, vp, vp, cd, cd, cd, cd, cll]
     for name in ("ffvd_ctx_create", "ffvd_ctx_destroy", "ffvd_ctx_synchronize", "ffvd_kernel_K", "ffvd_kernel_Kdiag",
                  "ffvd_kernel_pre_cal", "ffvd_conditional", "ffvd_logdensity_norm_diag", "ffvd_nll_grads_uncollapsed",
-                 "ffvd_nll_grads_collapsed", "ffvd_nll_grads_batched", "ffvd_sghmc_update", "ffvd_adam_update"):
+                 "ffvd_nll_grads_collapsed", "ffvd_nll_grads_batched", "ffvd_sghmc_update", "ffvd_adam_update",
+                 "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks"):
         getattr(lib, name).restype = ci
     _lib = lib
     return lib
@@ -207,6 +209,16 @@ class Context:
         finally:
             b.release()
         return mean_out, var_out
+
+    def collapse_u_mean(self, kind: int, problem: dict, U_mean_out, LHinvT_out=None, jitter: float = 1e-5):
+        b = _Borrow()
+        try:
+            P = _Problem()
+            self._fill(b, P, _PROBLEM_FIELDS, problem)
+            _check(self._lib.ffvd_collapse_u_mean(self._h, kind, ctypes.byref(P), float(jitter), b.ptr(U_mean_out), b.ptr(LHinvT_out)))
+        finally:
+            b.release()
+        return U_mean_out, LHinvT_out
 
     def logdensity_norm_diag(self, y, ymean, Rchols, vec, out):
         b = _Borrow()

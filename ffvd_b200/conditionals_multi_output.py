@@ -24,25 +24,81 @@ def _stack_hypers(kern, ref):
     return kind, logv, logl
 
 
+def _q_sqrt_first_output(q_sqrt, ref, R):
+    """The reference passes the whole q_sqrt to every per-kernel `base_conditional` call (f is M x 1 there), lets
+    TF broadcast it, and keeps `[:, :, 0]` of the stacked result (cmo:112-120, 317-322): every output ends up with
+    the FIRST factor / the first column of scales.  Reproduced literally."""
+    q = to_lib(ref, as_f64(q_sqrt))
+    if q.ndim == 3:
+        q0 = q[0:1]
+        return q0.contiguous() if is_torch(q0) else np.ascontiguousarray(q0)
+    if q.ndim == 2:
+        if is_torch(q):
+            return q[:, 0:1].expand(q.shape[0], R).contiguous()
+        return np.ascontiguousarray(np.repeat(q[:, 0:1], R, axis=1))
+    raise ValueError("Bad dimension for q_sqrt: %s" % str(q.ndim))            # cmo:57-59
+
+
 def conditional(Xnew, X, kern, f, *, full_cov=False, q_sqrt=None, white=False, return_Lm=False):
     """`conditionals_multi_output.py:73-120`: mean (N,D), var (N,D) of D independent GPs with
     per-output kernels `kern[kk]`, inducing inputs X (M,Din), q(u) means f (M,D).  The hot path
-    uses white=True, full_cov=False, q_sqrt=None; full_cov / q_sqrt are prediction-only options
-     and raise NotImplementedError.  `return_Lm=True` reproduces the reference's
-    ValueError."""
+    uses white=True, full_cov=False, q_sqrt=None; `q_sqrt` ((D,M,M) factors or (M,D) scales) adds the
+    q(u) covariance term with the reference's first-output broadcasting; `full_cov=True`
+    is not built (the driver runs with full_cov=False, FFVD_Main.py:267).  `return_Lm=True` reproduces the
+    reference's ValueError."""
     if return_Lm:
         raise ValueError("too many values to unpack (expected 2)")      # cmo:115, reference quirk Q8
-    if full_cov or q_sqrt is not None:
-        raise NotImplementedError("full_cov / q_sqrt belong to the prediction path (SURVEY 8f)")
+    if full_cov:
+        raise NotImplementedError("full_cov=True (N x N covariances) is not built; FFVD_Main.py:267 sets full_cov=False")
+    if q_sqrt is not None and not white:
+        raise NotImplementedError("q_sqrt with white=False is not built")
     Xnew, X, f = as_f64(Xnew), as_f64(X), as_f64(f)
     X = to_lib(Xnew, X); f = to_lib(Xnew, f)
     kind, logv, logl = _stack_hypers(kern, Xnew)
     Xs = Xnew[..., : kern[0].input_dim]
     Xs = Xs.contiguous() if is_torch(Xs) else np.ascontiguousarray(Xs)
+    q = None if q_sqrt is None else _q_sqrt_first_output(q_sqrt, Xnew, len(kern))
     mean = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
     var = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
-    context_for(Xnew).conditional(kind, False, Xs, X, logv, logl, f, None, white, False, JITTER, mean, var)
+    context_for(Xnew).conditional(kind, False, Xs, X, logv, logl, f, q, white, False, JITTER, mean, var)
     return mean, var
+
+
+def conditional_after_kernel_precalculation(Lm_inverse_seq, Xnew, Z, kern, f, *, full_cov=False, q_sqrt=None, white=False,
+                                            return_Lm=False):
+    """`conditionals_multi_output.py:306-387`: the prediction-time conditional.  `Lm_inverse_seq` (the list from
+    `kernel_pre_cal`) is accepted for signature parity; the fused path refactorises K(Z,Z)+1e-5 I on the device,
+    which is the same matrix.  Only white=True is built: the reference's own non-white branch multiplies by L^{-1}
+    twice and prints 'May have some problems with the non-white case' (cmo:359-362)."""
+    if not white:
+        raise NotImplementedError("conditional_after_kernel_precalculation: white=False is marked broken in the reference (cmo:359-362)")
+    if return_Lm:
+        raise ValueError("too many values to unpack (expected 2)")      # cmo:317, same unpack as Q8
+    return conditional(Xnew, Z, kern, f, full_cov=full_cov, q_sqrt=q_sqrt, white=True)
+
+
+def collapse_u_mean_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q):
+    """`conditionals_multi_output.py:206-227`: the optimal collapsed q(u).  Returns (U_mean, Lm_inverse_dd_seq) with
+    the reference's shapes: U_mean (1,M,D) (= tf.transpose of the (D,M,1) stack; callers take `[0]`,
+    base_model.py:249-250) and the (D,M,M) stack of chol(H_d)^{-T}.  `Lm_inverse_seq` is accepted for signature
+    parity (recomputed on the device)."""
+    X = as_f64(X)
+    D = X.shape[1]
+    T = X.shape[0] - 1
+    M = Z.shape[0]
+    Xc = to_lib(X, as_f64(X_combine))
+    ctrl = Xc[:, D:]
+    ctrl = ctrl.contiguous() if is_torch(ctrl) else np.ascontiguousarray(ctrl)
+    kind, logv, logl = _stack_hypers(kern, X)
+    zeros = lambda *s: to_lib(X, np.zeros(s))
+    Qv = to_lib(X, Q)
+    logQ = Qv.log() if is_torch(Qv) else np.log(Qv)
+    prob = dict(X=X, Z=to_lib(X, as_f64(Z)), U=zeros(M, D), logv=logv, logl=logl, logQ=logQ, C=zeros(D, 1),
+                d=zeros(1), logR=zeros(1, 1), Y=zeros(T, 1), ctrl=ctrl if ctrl.shape[1] > 0 else None)
+    U_mean = empty_like_lib(X, (M, D))
+    Linv = empty_like_lib(X, (D, M, M))
+    context_for(X).collapse_u_mean(kind, prob, U_mean, Linv, jitter=JITTER)
+    return U_mean[None, :, :], Linv
 
 
 def kernel_pre_cal(X, kern):

@@ -48,6 +48,9 @@ struct ffvd_ctx {
   DevProblem* d_probs = nullptr;
   OutPtrs* d_outs = nullptr;
   double* kscr = nullptr;      // points into the arena (set by ensure_arena)
+  // pools of the last collapsed evaluation (read by ffvd_collapse_u_mean right after it)
+  size_t last_off_cvec = 0, last_off_HxT = 0;
+  int last_Mp = 0, last_nb = 0;
   int probs_cap = 0;
   int* h_status = nullptr;     // pinned
   size_t h_status_cap = 0;
@@ -591,6 +594,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     O.g_logQ = t.glogQ.d; O.g_C = t.gC.d; O.g_d = t.gd.d; O.g_logR = t.glogR.d;
   }
   const long long total_items = item;
+  c->last_off_cvec = L.off_cvec; c->last_off_HxT = L.off_HxT; c->last_Mp = Mp; c->last_nb = nb;
   CUDA_TRY(cudaMemcpyAsync(c->d_probs, hp.data(), sizeof(DevProblem) * nprob, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->d_outs, ho.data(), sizeof(OutPtrs) * nprob, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
@@ -668,6 +672,52 @@ extern "C" int ffvd_nll_grads_collapsed(ffvd_ctx* c, int kind, const ffvd_proble
   if (kind == FFVD_KERNEL_LINEAR) return run_nll<1>(c, 1, 1, p, flags, jitter, o);
   return fail(FFVD_E_BADARG, "unknown kernel kind");
 }
+// (S,D,Mp) -> U_mean (S,M,D) and (S,D,Mp,Mp) -> LHinvT (S,D,M,M)
+__global__ void extract_collapsed_kernel(const double* __restrict__ cvec, const double* __restrict__ HxT, double* __restrict__ Umean,
+                                         double* __restrict__ LHinvT, int S, int D, int M, int Mp) {
+  const size_t n1 = (size_t)S * M * D, n2 = LHinvT ? (size_t)S * D * M * M : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int d = (int)(i % D), m = (int)((i / D) % M), s = (int)(i / ((size_t)D * M));
+      Umean[i] = cvec[((size_t)s * D + d) * Mp + m];
+    } else {
+      const size_t j = i - n1;
+      const int c0 = (int)(j % M), r0 = (int)((j / M) % M);
+      const size_t b = j / ((size_t)M * M);
+      LHinvT[j] = HxT[b * Mp * Mp + (size_t)r0 * Mp + c0];
+    }
+  }
+}
+
+extern "C" int ffvd_collapse_u_mean(ffvd_ctx* c, int kind, const ffvd_problem* p, double jitter, DLManagedTensor* U_mean_out,
+                                    DLManagedTensor* LHinvT_out) {
+  if (!c || !p || !U_mean_out) return fail(FFVD_E_BADARG, "null argument");
+  ffvd_outputs o;
+  memset(&o, 0, sizeof o);
+  // collapsed forward pass: S = F^T F, b = F^T delta, H = S/Q + I, chol(H), c = H^{-1} b / Q  (left in the context's pools)
+  int st;
+  if (kind == FFVD_KERNEL_SE) st = run_nll<0>(c, 1, 1, p, FFVD_FLAG_NO_GRADS, jitter, &o);
+  else if (kind == FFVD_KERNEL_LINEAR) st = run_nll<1>(c, 1, 1, p, FFVD_FLAG_NO_GRADS, jitter, &o);
+  else return fail(FFVD_E_BADARG, "unknown kernel kind");
+  if (st != FFVD_OK) return st;
+  Call call(c);
+  Tens tX, tZ, tu, tl;
+  TRY(call.import(p->X, false, tX, "X"));
+  TRY(call.import(p->Z, false, tZ, "Z"));
+  TRY(call.import(U_mean_out, true, tu, "U_mean_out"));
+  TRY(call.import(LHinvT_out, true, tl, "LHinvT_out", true));
+  const int S = tX.ndim == 3 ? (int)tX.shape[0] : 1, D = (int)tX.shape[tX.ndim - 1], M = (int)tZ.shape[0];
+  if (tu.numel != (size_t)S * M * D) return fail(FFVD_E_SHAPE, "U_mean_out must be (S,M,D) [(M,D) for 2-d X]");
+  if (tl.present && tl.numel != (size_t)S * D * M * M) return fail(FFVD_E_SHAPE, "LHinvT_out must be (S,D,M,M)");
+  // NOTE: staging X / Z again for host tensors is wasteful but harmless; the pools were written by run_nll above
+  extract_collapsed_kernel<<<grid1d((size_t)S * M * D + (tl.present ? (size_t)S * D * M * M : 0)), 256, 0, c->stream>>>(
+      (const double*)(c->arena + c->last_off_cvec), (const double*)(c->arena + c->last_off_HxT), tu.d, tl.present ? tl.d : nullptr, S, D, M,
+      c->last_Mp);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return call.finish();
+}
+
 extern "C" int ffvd_nll_grads_batched(ffvd_ctx* c, int kind, int collapsed, int nprob, const ffvd_problem* p, int flags,
                                       double jitter, const ffvd_outputs* o) {
   if (kind == FFVD_KERNEL_SE) return run_nll<0>(c, collapsed, nprob, p, flags, jitter, o);
@@ -731,12 +781,12 @@ extern "C" int ffvd_kernel_Kdiag(ffvd_ctx* c, int kind, DLManagedTensor* X, DLMa
 
 // shared prep for kernel_pre_cal / conditional: one DevProblem with only the Z-side fields.
 static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, const Tens& tl, int nk, int R, double jitter,
-                       Layout& L, DevProblem& P) {
+                       Layout& L, DevProblem& P, bool need_scratch = false) {
   const int M = (int)tZ.shape[0], Din = (int)tZ.shape[1];
   if (Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
   const int Mp = pad_M(M);
   if (Mp < 0) return fail(FFVD_E_LIMIT, "M > 2048 is not supported by this build");
-  L = make_layout(1, nk, nk, R, M, Mp, Din, 1, 1, false, false);
+  L = make_layout(1, need_scratch ? R : nk, nk, R, M, Mp, Din, 1, 1, false, need_scratch);
   TRY(ensure_arena(c, L));
   memset(&P, 0, sizeof P);
   P.Z = tZ.d; P.logv = tv.d; P.logl = tl.d;
@@ -796,10 +846,13 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
                                 DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
                                 int white, int full_cov, double jitter, DLManagedTensor* mean_out, DLManagedTensor* var_out) {
   if (!c) return fail(FFVD_E_BADARG, "ctx is null");
-  if (q_sqrt || full_cov) return fail(FFVD_E_UNSUPPORTED, "conditional: q_sqrt / full_cov are prediction-only options not built yet");
+  if (full_cov) return fail(FFVD_E_UNSUPPORTED, "conditional: full_cov=True (N x N covariances) is not built; the reference driver "
+                                                "runs with full_cov=False (FFVD_Main.py:267)");
+  if (q_sqrt && !white) return fail(FFVD_E_UNSUPPORTED, "conditional: q_sqrt with white=False is not built");
   CUDA_TRY(cudaSetDevice(c->device));
   Call call(c);
-  Tens tX, tZ, tv, tl, tf, tm, tvar;
+  Tens tX, tZ, tv, tl, tf, tm, tvar, tq;
+  TRY(call.import(q_sqrt, false, tq, "q_sqrt", true));
   TRY(call.import(Xnew, false, tX, "Xnew"));
   TRY(call.import(Z, false, tZ, "Z"));
   TRY(call.import(logv, false, tv, "logv"));
@@ -816,12 +869,30 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
   if (tm.numel != (size_t)N * R || tvar.numel != (size_t)N * R) return fail(FFVD_E_SHAPE, "mean/var must be (N,R)");
   if (N == 0) return call.finish();
   Layout L; DevProblem P;
-  TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P));
+  TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P, tq.present && tq.ndim == 3));
   const int RB = rb_of(P.Mp), BT = 8 * RB;
   P.hs = shared_kernel ? 0 : 1;
   P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;
   P.ntiles = (N + BT - 1) / BT; P.item_begin = 0; P.nitems = (long long)R * P.ntiles;
   P.cond_mean = tm.d; P.cond_var = tvar.d;
+  if (tq.present) {
+    if (tq.ndim == 2) {                       // (M,R) per-point scales, conditionals_multi_output.py:51-52
+      if (tq.shape[0] != M || tq.shape[1] != R) return fail(FFVD_E_SHAPE, "2-d q_sqrt must be (M,R)");
+      P.qmode = 2; P.nq = R; P.qmat = tq.d;
+    } else if (tq.ndim == 3) {                // (R,M,M) or (1,M,M) factors, :53-62
+      if (tq.shape[1] != M || tq.shape[2] != M || (tq.shape[0] != R && tq.shape[0] != 1))
+        return fail(FFVD_E_SHAPE, "3-d q_sqrt must be (R,M,M) or (1,M,M)");
+      P.qmode = 3; P.nq = (int)tq.shape[0];
+      double* qpad = (double*)(c->arena + L.off_Wk);      // zero padded (nq,Mp,Mp) copies
+      CUDA_TRY(cudaMemsetAsync(qpad, 0, (size_t)P.nq * P.Mp * P.Mp * 8, c->stream));
+      for (int i = 0; i < P.nq; ++i)
+        CUDA_TRY(cudaMemcpy2DAsync(qpad + (size_t)i * P.Mp * P.Mp, (size_t)P.Mp * 8, tq.d + (size_t)i * M * M, (size_t)M * 8,
+                                   (size_t)M * 8, M, cudaMemcpyDeviceToDevice, c->stream));
+      P.qmat = qpad;
+    } else {
+      return fail(FFVD_E_SHAPE, "Bad dimension for q_sqrt");       // conditionals_multi_output.py:57-59
+    }
+  }
   double* utmp = (double*)(c->arena + L.off_utmp);
   P.U = tf.d;
   CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));

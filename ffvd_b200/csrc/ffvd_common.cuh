@@ -49,6 +49,9 @@ struct DevProblem {
   double *rs;          // [nb][Mp] row sums of Wz
   int *status;         // [D] 0 ok, else 1-based failing pivot
   double *cond_mean, *cond_var;   // conditional(): (N,R) outputs
+  const double *qmat;  // conditional() with q_sqrt: qmode 3 -> [nq][Mp][Mp] zero padded factors (var += |Q^T a|^2);
+                       //                            qmode 2 -> [M][R] per-point scales      (var += sum (q_m a_m)^2)
+  int qmode, nq;       // nq = 1: one factor shared by all outputs (the reference's [:, :, 0] indexing), else R
   int S, T, D, Din, nc, Dy, M, Mp;
   int Dx;              // columns of X (== D for the nll paths, == Din for conditional())
   int xrows;           // valid rows of X per sample (T+1 for nll, N for conditional())

@@ -37,7 +37,7 @@ struct Smem {
   double* us;       // Mp           : u_d (uncollapsed) / w'_d (collapsed pass 2)
   double* ws;       // Mp           : uncollapsed: w_d = L^{-T} u_d
   double* es;       // 64           : e_t (uncollapsed) / delta_t (collapsed)
-  double* rowpart;  // 2 x 8 x BT
+  double* rowpart;  // 3 x 8 x BT
   double* stage;    // NW warps x 8 x 40
   double* part;     // 128 x 8 NBM: partial products of W [Z,1] per k slice (overlays xsc / stage)
   double* small;    // 64: invl2[32], sil[32]
@@ -598,7 +598,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       sm.us = p; p += Mp;
       sm.ws = p; p += Mp;
       sm.es = p; p += 64;
-      sm.rowpart = p; p += 2 * 8 * BT;
+      sm.rowpart = p; p += 3 * 8 * BT;
       sm.small = p; p += 64;
       sm.xn2h = p; p += 64;
       sm.sc = p; p += 8;
@@ -644,6 +644,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
       sm.us[j] = u;
       if (MODE == MODE_UNCOLLAPSED) sm.ws[j] = P.wvec[(size_t)d * Mp + j];
+      if (MODE == MODE_COND) sm.ws[j] = (P.qmode == 2 && j < M) ? P.qmat[(size_t)j * D + d] : 0.0;
     }
     __syncthreads();
     const double v = sm.sc[0], invQ = sm.sc[2], logQd = sm.sc[3];
@@ -688,19 +689,24 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
                               [](double x, int, int) { return x; });
       // row partial sums: a.u and a.a
       {
-        double su[RBW], sa[RBW];
+        double su[RBW], sa[RBW], sq[RBW];
 #pragma unroll
-        for (int rb = 0; rb < RBW; ++rb) su[rb] = sa[rb] = 0.0;
+        for (int rb = 0; rb < RBW; ++rb) su[rb] = sa[rb] = sq[rb] = 0.0;
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
           const int jb = 16 * group_index(wc, ng) + 4 * q;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const double u = sm.us[jb + c];
+            const double qs = (MODE == MODE_COND) ? sm.ws[jb + c] : 0.0;     // q_sqrt given as (M,R) scales
 #pragma unroll
             for (int rb = 0; rb < RBW; ++rb) {
               su[rb] = fma(acc[ng][rb][c], u, su[rb]);
               sa[rb] = fma(acc[ng][rb][c], acc[ng][rb][c], sa[rb]);
+              if (MODE == MODE_COND) {
+                const double t = acc[ng][rb][c] * qs;
+                sq[rb] = fma(t, t, sq[rb]);
+              }
             }
           }
         }
@@ -710,9 +716,14 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
           su[rb] += __shfl_xor_sync(0xffffffffu, su[rb], 2);
           sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 1);
           sa[rb] += __shfl_xor_sync(0xffffffffu, sa[rb], 2);
+          if (MODE == MODE_COND) {
+            sq[rb] += __shfl_xor_sync(0xffffffffu, sq[rb], 1);
+            sq[rb] += __shfl_xor_sync(0xffffffffu, sq[rb], 2);
+          }
           if (q == 0) {
             sm.rowpart[(0 * 8 + wc) * BT + row0 + 8 * rb + g] = su[rb];
             sm.rowpart[(1 * 8 + wc) * BT + row0 + 8 * rb + g] = sa[rb];
+            if (MODE == MODE_COND) sm.rowpart[(2 * 8 + wc) * BT + row0 + 8 * rb + g] = sq[rb];
           }
         }
       }
@@ -741,9 +752,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             }
             const double sig2 = kdiag - sa;
             if (MODE == MODE_COND) {
-              // conditionals_multi_output.py:41,48 : fvar = Knn - sum A^2 ; fmean = A^T f
+              // conditionals_multi_output.py:41,48 : fvar = Knn - sum A^2 ; fmean = A^T f ; :50-52 q_sqrt (M,R) term
+              double sq = 0.0;
+#pragma unroll
+              for (int w = 0; w < 8; ++w) sq += sm.rowpart[(2 * 8 + w) * BT + r];
               P.cond_mean[(size_t)(t0 + r) * D + d] = su;
-              P.cond_var[(size_t)(t0 + r) * D + d] = sig2;
+              P.cond_var[(size_t)(t0 + r) * D + d] = sig2 + sq;
             } else if (MODE == MODE_COLLAPSED_P1) {
               const double delta = xn - xd;
               e = delta;                                   // b += F^T delta
@@ -809,6 +823,36 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       FFVD_MARK(3);
     }
 
+    if (MODE == MODE_COND && P.qmode == 3) {
+      // conditionals_multi_output.py:53-62 (q_sqrt R x M x M): fvar += sum_m (Q^T a_t)_m^2, a second contraction of the A
+      // tile (still in registers) with the dense zero-padded factor
+      store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
+      __syncthreads();
+      tile_gemm<RBW, NGW, 0>(acc, wtile, lda, P.qmat + (size_t)(P.nq == 1 ? 0 : d) * Mp * Mp, Mp, wc, g, q,
+                             [](double x, int, int) { return x; });
+      double sq[RBW];
+#pragma unroll
+      for (int rb = 0; rb < RBW; ++rb) sq[rb] = 0.0;
+#pragma unroll
+      for (int ng = 0; ng < NGW; ++ng)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int rb = 0; rb < RBW; ++rb) sq[rb] = fma(acc[ng][rb][c], acc[ng][rb][c], sq[rb]);
+#pragma unroll
+      for (int rb = 0; rb < RBW; ++rb) {
+        sq[rb] += __shfl_xor_sync(0xffffffffu, sq[rb], 1);
+        sq[rb] += __shfl_xor_sync(0xffffffffu, sq[rb], 2);
+        if (q == 0) sm.rowpart[(2 * 8 + wc) * BT + row0 + 8 * rb + g] = sq[rb];
+      }
+      __syncthreads();
+      if (tid < nvalid) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm.rowpart[(2 * 8 + w) * BT + tid];
+        P.cond_var[(size_t)(t0 + tid) * D + d] += t;      // written by this same thread above
+      }
+    }
     if (MODE == MODE_FORWARD || MODE == MODE_COND) {
       // forward only: flush the scalar sums and move on
       if (MODE == MODE_FORWARD && tid == 0) {

@@ -112,11 +112,23 @@ int ffvd_kernel_pre_cal(ffvd_ctx*, int kind, DLManagedTensor* Z, DLManagedTensor
 
 /* conditionals_multi_output.py:73-120 (list of D kernels, f (M,D)) and, with
  * shared_kernel=1, conditionals.py:69-107 (one kernel for all R columns of f; logv (), logl (Din)).
- * mean_out, var_out (N,R).  Supported: full_cov=0, q_sqrt=NULL, white in {0,1}. */
+ * Also the prediction form conditional_after_kernel_precalculation (cmo:306-387): the factors are
+ * recomputed on the device, so Lm_inverse_seq is not an input.
+ * mean_out, var_out (N,R).  q_sqrt (nullable): (M,R) per-point scales (cmo:51-52) or (R,M,M) /
+ * (1,M,M) factors (cmo:53-62; (1,M,M) = one factor for every output, which is what the
+ * reference's [:, :, 0] indexing computes); requires white=1.  full_cov=1 is not built. */
 int ffvd_conditional(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
                      DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f,
                      DLManagedTensor* q_sqrt, int white, int full_cov, double jitter,
                      DLManagedTensor* mean_out, DLManagedTensor* var_out);
+
+/* conditionals_multi_output.py:206-227 collapse_u_mean_after_kernel_precalculation: the optimal
+ * collapsed q(u).  Per sample s and output d: F = K(Xc,Z) L^{-T}, H = F^T F / Q_d + I,
+ * U_mean_out[s,:,d] = H^{-1} F^T (x_{1:T,d} - x_{0:T-1,d}) / Q_d   (S,M,D) [(M,D) for 2-d X],
+ * LHinvT_out[s,d] = chol(H)^{-T} (upper)   (S,D,M,M), nullable.
+ * Only X, Z, logv, logl, logQ, ctrl of the problem matter (the others must still be valid tensors). */
+int ffvd_collapse_u_mean(ffvd_ctx*, int kind, const ffvd_problem* p, double jitter,
+                         DLManagedTensor* U_mean_out, DLManagedTensor* LHinvT_out);
 
 /* likelihoods.py:96-111 (vec=1 -> out (N)) and :89-93 (vec=0 -> out (N,Dy)); no -0.5 log 2pi. */
 int ffvd_logdensity_norm_diag(ffvd_ctx*, DLManagedTensor* y, DLManagedTensor* ymean,

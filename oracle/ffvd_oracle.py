@@ -220,6 +220,68 @@ def collapse_u_mean_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z,
     return U_mean[:, :, 0].T, torch.stack(Linv_dd)
 
 
+def base_conditional_after_kernel_precalculation(Kmn, Lm_inverse_seq_kk, Knn, f, *, full_cov=False, q_sqrt=None, white=False):
+    """`conditionals_multi_output.py:324-387`, op for op (including the doubled L^{-1} of its non-white branch and TF's
+    batch broadcasting of a (R',M,M) q_sqrt against the (num_func,M,N) tiled A)."""
+    num_func = f.shape[1]
+    A = Lm_inverse_seq_kk.T @ Kmn
+    if full_cov:
+        fvar = Knn - A.T @ A
+        fvar = fvar[None, :, :].repeat(num_func, 1, 1)
+    else:
+        fvar = Knn - torch.sum(torch.square(A), 0)
+        fvar = fvar[None, :].repeat(num_func, 1)
+    if not white:
+        A = Lm_inverse_seq_kk.T @ A
+    fmean = A.T @ f
+    if q_sqrt is not None:
+        if q_sqrt.dim() == 2:
+            LTA = A * q_sqrt.T.unsqueeze(2)
+        elif q_sqrt.dim() == 3:
+            A_tiled = A.unsqueeze(0).repeat(num_func, 1, 1)
+            LTA = q_sqrt.transpose(-1, -2) @ A_tiled                 # broadcasts (R',M,M) x (1,M,N) -> (R',M,N)
+        else:
+            raise ValueError("Bad dimension for q_sqrt: %s" % str(q_sqrt.dim()))
+        if full_cov:
+            fvar = fvar + LTA.transpose(-1, -2) @ LTA
+        else:
+            fvar = fvar + torch.sum(torch.square(LTA), 1)
+    if not full_cov:
+        fvar = fvar.T
+    return fmean, fvar
+
+
+def conditional_after_kernel_precalculation(Lm_inverse_seq, Xnew, Z, kern, f, *, full_cov=False, q_sqrt=None, white=False):
+    """`conditionals_multi_output.py:306-322`; the final `[:, :, 0]` keeps output 0's q_sqrt term for every kernel
+    (SURVEY Q9)."""
+    f_mu, f_var = [], []
+    for kk in range(len(kern)):
+        Kmn = kern[kk].K(Z, Xnew)
+        Knn = kern[kk].K(Xnew) if full_cov else kern[kk].Kdiag(Xnew)
+        mu, var = base_conditional_after_kernel_precalculation(Kmn, Lm_inverse_seq[kk], Knn, f[:, kk][:, None], full_cov=full_cov,
+                                                               q_sqrt=q_sqrt, white=white)
+        f_mu.append(mu)
+        f_var.append(var)
+    return torch.stack(f_mu)[:, :, 0].T, torch.stack(f_var)[:, :, 0].T
+
+
+def rollout(Lm_inverse_seq, x_last, ctrl_future, Z, kern, U_val, q_sqrt, Q, noise):
+    """The prediction roll-out of `base_model.py:283-310` for one posterior sample: x_{t+1} = x_t + f(x_t, c_t) +
+    eps_t sqrt(var_t + Q), eps_t = noise[t] (the reference draws tf.random.normal; injected here).  Returns the stacked
+    states (L,D) and their predictive variances var_t + Q (L,D)."""
+    x_t = x_last[None, :]
+    xs, vs = [], []
+    for t in range(noise.shape[0]):
+        xc = torch.cat((x_t, ctrl_future[t][None, :]), dim=1) if ctrl_future.shape[1] > 0 else x_t
+        mu, var = conditional_after_kernel_precalculation(Lm_inverse_seq, xc, Z, kern, U_val, white=True, full_cov=False, q_sqrt=q_sqrt)
+        mu = mu + x_t
+        x_next = mu + noise[t][None, :] * torch.sqrt(var + Q)
+        xs.append(x_next[0])
+        vs.append((var + Q)[0])
+        x_t = x_next
+    return torch.stack(xs), torch.stack(vs)
+
+
 def collapse_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q, batch_size, Y_N):
     """`conditionals_multi_output.py:230-257`: the three collapsed-bound terms."""
     term1 = 0.0

@@ -376,3 +376,73 @@ def test_full_size_properties(env):
     from oracle import ffvd_oracle as O
     q = copy.copy(prob); q.X = prob.X[0, :129]; q.Y = prob.Y[:128]; q.ctrl = prob.ctrl[:128]
     check(O.nll_and_grads(q, collapsed=False), run_cuda(env, q, False), what="prefix")
+
+
+# ---- "next" row, SURVEY 8(f) rank 2: collapsed q(u) and the prediction-time conditional ---------------------------
+@pytest.mark.parametrize("name", ("ballbeam/4", "actuator/0", "gas_furnace/0"))
+def test_collapse_u_mean_and_predictive_conditional(env, name):
+    """collapse_u_mean_after_kernel_precalculation (cmo:206-227) and conditional_after_kernel_precalculation with its
+    q_sqrt term (cmo:306-387) against the op-for-op oracle, including the reference's first-output broadcasting of
+    q_sqrt."""
+    import torch as th
+    from oracle import ffvd_oracle as O
+    from ffvd_b200 import conditionals_multi_output as cmo
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    prob = env["byname"][name]
+    T, D = prob.Y.shape[0], prob.X.shape[1]
+    Din = prob.Z.shape[1]
+    kerns = [SquaredExponential(Din, variance=np.exp(prob.logv[k]), lengthscales=np.exp(prob.logl[k]), ARD=True) for k in range(D)]
+    ok = O._make_kernels(th.as_tensor(prob.logv), th.as_tensor(prob.logl), 0, Din)
+    Xc = np.concatenate([prob.X[:T], prob.ctrl], axis=1)
+    Q = np.exp(prob.logQ)
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    Linv_o = O.kernel_pre_cal(th.as_tensor(prob.Z), ok)
+    rU, rL = O.collapse_u_mean_after_kernel_precalculation(Linv_o, th.as_tensor(Xc), th.as_tensor(prob.X), th.as_tensor(prob.Z), ok,
+                                                           th.as_tensor(Q))
+    U_mean, Lseq = cmo.collapse_u_mean_after_kernel_precalculation(None, t(Xc), t(prob.X), t(prob.Z), kerns, t(Q))
+    assert tuple(U_mean.shape) == (1, prob.Z.shape[0], D)             # tf.transpose of the (D,M,1) stack
+    assert_close(rU.numpy(), U_mean[0].cpu().numpy(), TOL)
+    assert_close(rL.numpy(), Lseq.cpu().numpy(), TOL)
+    # prediction-time conditional at a few new inputs, q(u) = N(U_mean, H^{-1})
+    rng = np.random.default_rng(3)
+    Xn = Xc[rng.integers(0, T, 37)] + 0.05 * rng.standard_normal((37, Din))
+    rmu, rvar = O.conditional_after_kernel_precalculation(Linv_o, th.as_tensor(Xn), th.as_tensor(prob.Z), ok, rU, white=True, q_sqrt=rL)
+    mu, var = cmo.conditional_after_kernel_precalculation(None, t(Xn), t(prob.Z), kerns, U_mean[0], white=True, q_sqrt=Lseq)
+    assert_close(rmu.numpy(), mu.cpu().numpy(), TOL)
+    # the variance is a difference of O(v) terms: tolerance relative to max Kdiag (as for the LinearK variances)
+    scale = float(np.max(np.exp(prob.logv)))
+    assert np.max(np.abs(rvar.numpy() - var.cpu().numpy())) <= TOL * scale
+    # NumPy (host) tensors go through the same C ABI with explicit staging copies
+    mu_h, var_h = cmo.conditional_after_kernel_precalculation(None, Xn, prob.Z, kerns, U_mean[0].cpu().numpy(), white=True,
+                                                              q_sqrt=Lseq.cpu().numpy())
+    assert_close(mu.cpu().numpy(), mu_h, 1e-13)
+    assert np.max(np.abs(var.cpu().numpy() - var_h)) <= 1e-13 * scale
+    with pytest.raises(NotImplementedError):
+        cmo.conditional_after_kernel_precalculation(None, t(Xn), t(prob.Z), kerns, U_mean[0], white=False)
+
+
+def test_single_kernel_conditional_q_sqrt(env):
+    """conditionals.conditional (one kernel, f (M,R)) with q_sqrt given as (R,M,M) factors and as (M,R) scales
+    (conditionals.py:46-58): one factor per column of f."""
+    import torch as th
+    from oracle import ffvd_oracle as O
+    from ffvd_b200 import conditionals
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    rng = np.random.default_rng(11)
+    M, R, N, Din = 60, 3, 41, 4
+    Z = rng.standard_normal((M, Din)) * 1.5
+    Xn = rng.standard_normal((N, Din))
+    f = rng.standard_normal((M, R))
+    q3 = np.tril(rng.standard_normal((R, M, M))) * 0.2
+    q2 = rng.uniform(0.1, 1.0, (M, R))
+    ls = rng.uniform(1.0, 3.0, Din)
+    kern = SquaredExponential(Din, variance=0.7, lengthscales=ls, ARD=True)
+    ok = O.SquaredExponential(Din, variance=0.7, lengthscales=ls, ARD=True)
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    for q in (q3, q2):
+        rmu, rvar = O.conditional(th.as_tensor(Xn), th.as_tensor(Z), ok, th.as_tensor(f), white=True, q_sqrt=th.as_tensor(q))
+        mu, var = conditionals.conditional(t(Xn), t(Z), kern, t(f), white=True, q_sqrt=t(q))
+        assert_close(rmu.numpy(), mu.cpu().numpy(), TOL)
+        assert_close(rvar.numpy(), var.cpu().numpy(), TOL)
+    with pytest.raises(ValueError):
+        conditionals.conditional(t(Xn), t(Z), kern, t(f), white=True, q_sqrt=t(q2[:, 0]))
