@@ -1,7 +1,8 @@
 """Mirror of the hot-path part of `vfegpssm/base_model.py`: the adaptive SG-HMC update
 (`generate_update_step`, :143-179), its schedule (`sghmc_step`, :915-933), `get_minibatch`
-(:188-194) and the Adam step (`train_hypers`, :944-950).  Prediction / particle-Gibbs methods of
-the reference class are out of scope."""
+(:188-194), the Adam step (`train_hypers`, :944-950) and the posterior roll-out / results file of
+`collect_samples_formal` (:197-522).  The particle-Gibbs methods of the reference class are out of scope
+(SURVEY 2.1)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
@@ -99,3 +100,107 @@ class BaseModel(object):
             m, v = self.adam_state[name]
             self.ctx.adam_update(th, out["g_" + name], m, v, lr, 0.9, 0.999, 1e-8, self.adam_step)
         return out
+
+    # ---- base_model.py:197-522
+    def collect_samples_formal(self, num, spacing, control_inputs, test_len, sghmc_var_len=0, U_collapse=False, Y_test=None,
+                               Y_train_std=1., save_path_file=None, Y_train=None, case='C1', ll_seq=[0.], running_time_seq=[0.],
+                               PG_num=None, synthetic_data_function_plot=False, data_uu=None, noise=None):
+        """Posterior roll-out, `base_model.py:197-522`: for each of `num` posterior samples (advanced by `spacing`
+        SG-HMC sample updates when anything is sampled, :226-232), start from the last latent state and iterate
+        x_{t+1} = x_t + f(x_t, c_t) + eps sqrt(var + Q) for `test_len` steps (:283-310) with the prediction-time
+        conditional (q(u) = the collapsed optimum when `U_collapse`, :241-252); then y = x C + d, RMSE over the
+        first 30 test steps (:330-347) and the `_results.npz` file with the reference's keys (:488-517).
+        `noise` (num, test_len, D) replaces the reference's unseeded tf.random.normal draws.
+        When nothing is SG-HMC sampled every posterior sample shares its parameters and the `num` roll-outs advance
+        together as one N = num conditional per step."""
+        import torch
+        from . import conditionals_multi_output as cmo
+        if synthetic_data_function_plot:
+            raise NotImplementedError("synthetic_data_function_plot is a plotting aid of the reference (base_model.py:262-278)")
+        dev = self.device
+        t64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
+        X = self.params["X"]
+        if X.dim() != 2:
+            raise NotImplementedError("roll-out of a batched-sample model: pick one trajectory")
+        D = X.shape[1]
+        kern = self.kernels[-1]
+        ctrl_all = t64(control_inputs) if control_inputs is not None else torch.zeros((0, 0), dtype=torch.float64, device=dev)
+        n_ctrl = ctrl_all.shape[1] if ctrl_all.dim() == 2 else 0
+        T_train = int(np.asarray(Y_train).shape[0]) if Y_train is not None else self.X_N - 1
+        L = int(test_len)                                           # prediction_length = test_len + pre_index - 1, pre_index = 1
+        if noise is None:
+            noise = torch.randn((num, L, D), dtype=torch.float64, device=dev)
+        else:
+            noise = t64(noise)
+        Qv = self.log_Q.exp()
+        self.fit_x = X.clone()
+
+        def posterior_qu():
+            if U_collapse:
+                xc = torch.cat((X[:self.X_N - 1], ctrl_all[:self.X_N - 1]), dim=1) if n_ctrl > 0 else X[:-1]
+                U_val, Lseq = cmo.collapse_u_mean_after_kernel_precalculation(None, xc.contiguous(), X, self.params["Z"], kern, Qv)
+                return U_val[0], Lseq
+            return self.params["U"], None
+
+        def roll(x_t, U_val, q_sqrt, eps):
+            """x_t (n,D), eps (n,L,D) -> states (n,L,D), variances (n,L,D)"""
+            xs, vs = [], []
+            for t in range(L):
+                if n_ctrl > 0:
+                    c = ctrl_all[t + T_train][None, :].expand(x_t.shape[0], n_ctrl)
+                    xc = torch.cat((x_t, c), dim=1).contiguous()
+                else:
+                    xc = x_t.contiguous()
+                mu, var = cmo.conditional_after_kernel_precalculation(None, xc, self.params["Z"], kern, U_val, white=True,
+                                                                      full_cov=False, q_sqrt=q_sqrt)
+                x_next = mu + x_t + eps[:, t] * torch.sqrt(var + Qv)
+                xs.append(x_next)
+                vs.append(var + Qv)
+                x_t = x_next
+            return torch.stack(xs, dim=1), torch.stack(vs, dim=1)
+
+        mc_posterior_samples = [[] for _ in range(sghmc_var_len)]
+        if sghmc_var_len == 0:
+            U_val, q_sqrt = posterior_qu()
+            x0 = X[-1][None, :].expand(num, D).contiguous()
+            predict_x_whole, predict_x_var_whole = roll(x0, U_val, q_sqrt, noise)
+        else:
+            px, pv = [], []
+            for i in range(num):
+                for _ in range(spacing):
+                    self._run_update(False)
+                for j, name in enumerate(self.vars[:sghmc_var_len]):
+                    mc_posterior_samples[j].append(self.params[name].cpu().numpy().copy())
+                U_val, q_sqrt = posterior_qu()
+                a, b = roll(X[-1][None, :].contiguous(), U_val, q_sqrt, noise[i:i + 1])
+                px.append(a[0]); pv.append(b[0])
+            predict_x_whole, predict_x_var_whole = torch.stack(px), torch.stack(pv)
+
+        predict_x_whole = predict_x_whole.cpu().numpy()
+        predict_x_var_whole = predict_x_var_whole.cpu().numpy()
+        CC_val = self.params["C"].cpu().numpy()
+        DD_val = self.params["d"].cpu().numpy()
+        log_R_cholesky = self.params["logR"].cpu().numpy()
+        fit_x_value = self.fit_x.cpu().numpy()[1:]
+        self.predict_y = (np.mean(np.einsum('ijk,kl->ijl', predict_x_whole, CC_val), axis=0) + DD_val[None, :]).reshape((-1))
+        self.predict_y_var = (np.mean(np.einsum('ijk,kl->ijl', predict_x_var_whole, CC_val ** 2), axis=0)).reshape((-1)) \
+            + np.exp(2 * log_R_cholesky).reshape(-1)
+        self.fit_y = (np.matmul(fit_x_value, CC_val) + DD_val).reshape((-1))
+        self.predict_x, self.predict_x_var = predict_x_whole, predict_x_var_whole
+        self.RMSE_val = None
+        if Y_test is not None:
+            Y_test = np.asarray(Y_test)
+            n30 = min(30, self.predict_y.shape[0])
+            self.RMSE_val = float(np.sqrt(np.mean((Y_test[:30].reshape((-1))[:n30] - self.predict_y[:n30]) ** 2)) * Y_train_std)
+        if save_path_file is not None:
+            k_log_lengthscales = [np.asarray(k.loglengthscales.cpu().numpy() if hasattr(k.loglengthscales, "cpu") else k.loglengthscales)
+                                  for k in kern] if self.kind == 0 else []
+            k_log_variances = [np.asarray(k.logvariance.cpu().numpy() if hasattr(k.logvariance, "cpu") else k.logvariance) for k in kern]
+            np.savez_compressed(save_path_file + '_results.npz', y_train_vfe=self.fit_y, y_test_vfe=self.predict_y,
+                                v_test_vfe_var=self.predict_y_var, Y_test_data=Y_test, Y_train_data=Y_train, Y_train_std=Y_train_std,
+                                CC_val=CC_val, DD_val=DD_val, log_R_cholesky=log_R_cholesky, log_QQ=self.log_Q.cpu().numpy(),
+                                Z_val=self.params["Z"].cpu().numpy(), U_val=self.params["U"].cpu().numpy(), X_val=fit_x_value,
+                                k_lengthscales=k_log_lengthscales, k_log_variances=k_log_variances, case=case, ll_seq=ll_seq,
+                                running_time_seq=running_time_seq, PG_num=PG_num,
+                                mc_posterior_samples=np.asarray(mc_posterior_samples, dtype=object) if sghmc_var_len else [])
+        return self.predict_y, self.predict_y_var

@@ -446,3 +446,80 @@ def test_single_kernel_conditional_q_sqrt(env):
         assert_close(rvar.numpy(), var.cpu().numpy(), TOL)
     with pytest.raises(ValueError):
         conditionals.conditional(t(Xn), t(Z), kern, t(f), white=True, q_sqrt=t(q2[:, 0]))
+
+
+# ---- "next" rows, SURVEY 8(f) ranks 2-3: posterior roll-out, results file and the outer training loop ----------------
+def _model_from_problem(env, prob, case_val, iterations=1, extra_ctrl=None):
+    from ffvd_b200 import models
+    ctrl = prob.ctrl if extra_ctrl is None else np.concatenate([prob.ctrl, extra_ctrl], axis=0)
+    args = dict(CC=prob.C, DD=prob.d, QQ_chol=np.exp(0.5 * prob.logQ), RR_chol=np.exp(prob.logR), lengthscales=np.exp(prob.logl),
+                variance=np.exp(prob.logv), UU_ini=prob.U, XX_0_ini=prob.X[0], x_initialization=prob.X[1:], ZZ=prob.Z)
+    m = models.configure(models.RegressionModel("normal"), args, ctrl, case_val, iterations=iterations, window_size=64)
+    return m, ctrl
+
+
+@pytest.mark.parametrize("case_val", (4, 2))
+def test_rollout_and_results_file(env, case_val, tmp_path):
+    """collect_samples_formal (base_model.py:197-522) against the oracle's restatement of the roll-out with the same
+    injected noise: case 4 (collapsed q(u), all samples share parameters -> batched roll-out) and case 2 (U, kernel
+    hypers SG-HMC sampled -> per-sample roll-out after `spacing` sample updates)."""
+    import torch as th
+    from oracle import ffvd_oracle as O
+    prob = env["byname"]["drive/0"]
+    T, D = prob.Y.shape[0], prob.X.shape[1]
+    rng = np.random.default_rng(5)
+    L, num = 12, 3
+    future = rng.standard_normal((L + 2, prob.ctrl.shape[1]))
+    m, ctrl = _model_from_problem(env, prob, case_val, iterations=0, extra_ctrl=future)
+    model = m.fit(prob.Y, kernel_type="SquaredExponential")
+    noise = rng.standard_normal((num, L, D))
+    spacing = 0 if case_val == 2 else 5          # spacing 0: the sampled variables stay at their initial values
+    base = str(tmp_path / "run")
+    py, pv = model.collect_samples_formal(num, spacing, ctrl, L, sghmc_var_len=len(model.vars), U_collapse=(case_val == 4),
+                                          Y_test=rng.standard_normal((40, 1)), Y_train_std=2.0, save_path_file=base, Y_train=prob.Y,
+                                          case="C%d" % case_val, noise=noise)
+    # oracle
+    tt = th.as_tensor
+    ok = O._make_kernels(tt(prob.logv), tt(prob.logl), 0, prob.Z.shape[1])
+    Linv = O.kernel_pre_cal(tt(prob.Z), ok)
+    Q = tt(np.exp(prob.logQ))
+    if case_val == 4:
+        Xc = tt(np.concatenate([prob.X[:T], prob.ctrl], axis=1))
+        U_val, q_sqrt = O.collapse_u_mean_after_kernel_precalculation(Linv, Xc, tt(prob.X), tt(prob.Z), ok, Q)
+    else:
+        U_val, q_sqrt = tt(prob.U), None
+    xs, vs = zip(*[O.rollout(Linv, tt(prob.X[-1]), tt(ctrl[T:T + L]), tt(prob.Z), ok, U_val, q_sqrt, Q, tt(noise[i])) for i in range(num)])
+    xs, vs = th.stack(xs).numpy(), th.stack(vs).numpy()
+    # twelve sequential steps amplify rounding differences slightly: 1e-8 on the trajectories
+    assert_close(xs, model.predict_x, 1e-8)
+    assert_close(vs, model.predict_x_var, 1e-8)
+    ref_y = (np.mean(np.einsum('ijk,kl->ijl', xs, prob.C), axis=0) + prob.d[None, :]).reshape(-1)
+    assert_close(ref_y, py, 1e-8)
+    ref_v = np.mean(np.einsum('ijk,kl->ijl', vs, prob.C ** 2), axis=0).reshape(-1) + np.exp(2 * prob.logR).reshape(-1)
+    assert_close(ref_v, pv, 1e-8)
+    res = np.load(base + "_results.npz", allow_pickle=True)
+    for key in ("y_train_vfe", "y_test_vfe", "v_test_vfe_var", "Y_test_data", "Y_train_data", "Y_train_std", "CC_val", "DD_val",
+                "log_R_cholesky", "log_QQ", "Z_val", "U_val", "X_val", "k_lengthscales", "k_log_variances", "case", "ll_seq",
+                "running_time_seq", "PG_num", "mc_posterior_samples"):
+        assert key in res.files, key                      # base_model.py:512-517
+    assert_close((prob.X[1:] @ prob.C + prob.d).reshape(-1), res["y_train_vfe"], 1e-13)
+    assert model.RMSE_val is not None and np.isfinite(model.RMSE_val)
+
+
+def test_outer_training_loop(env):
+    """Model._fit (models.py:142-168): each iteration = sghmc_step (21 evaluations; a no-op update set in case 4) +
+    one Adam step on the trainable set.  The default case 4 must lower the collapsed nll."""
+    prob = env["byname"]["actuator/0"]
+    m, _ = _model_from_problem(env, prob, 4, iterations=5)
+    model = m.fit(prob.Y, kernel_type="SquaredExponential")          # 2 * iterations = 10 outer iterations
+    assert model.vars == [] and set(model.trainable) == {"X", "Z", "logv", "logl", "logQ", "C", "d", "logR"}
+    assert model.adam_step == 10 and m.global_step == 10
+    nll_end = float(model.nll)
+    m0, _ = _model_from_problem(env, prob, 4, iterations=0)
+    nll_start = float(m0.fit(prob.Y).nll)
+    assert np.isfinite(nll_end) and nll_end < nll_start
+    # case 2 samples {logv, logl, U} and keeps a window of snapshots
+    m2, _ = _model_from_problem(env, prob, 2, iterations=1)
+    model2 = m2.fit(prob.Y)
+    assert model2.vars == ["logv", "logl", "U"] and len(model2.window) == 2
+    assert np.isfinite(float(model2.nll))

@@ -56,3 +56,31 @@ def test_shard_helpers():
             assert max(b[1] - b[0] for b in blocks) - min(b[1] - b[0] for b in blocks) <= 1
             rr = sorted(sum((distributed.round_robin(n, r, w) for r in range(w)), []))
             assert rr == list(range(n))
+
+
+def test_create_dataset_and_case_table(tmp_path):
+    """datasets.create_dataset restates FFVD_Main.py:134-171 (checked against the oracle-side fixture loader on a
+    synthetic file in the reference's gas_furnace.csv layout) and CASE_TABLE restates :273-324."""
+    from ffvd_b200 import datasets
+    from oracle import fixtures
+    rng = np.random.default_rng(0)
+    raw = np.column_stack([rng.standard_normal(60) * 3 + 1, rng.standard_normal(60) * 2 - 5])
+    with open(tmp_path / "gas_furnace.csv", "w") as f:
+        f.write("u,y\n" + "\n".join("%.17g,%.17g" % (a, b) for a, b in raw))
+    Ytr, Yte, ctrl, ystd, ymean, cmean, cstd = datasets.create_dataset("gas_furnace/", str(tmp_path))
+    rYtr, rYte, rctrl = fixtures.create_dataset("gas_furnace", str(tmp_path))
+    assert np.array_equal(Ytr, rYtr) and np.array_equal(Yte, rYte) and np.array_equal(ctrl, rctrl)
+    assert Ytr.shape == (30, 1) and Yte.shape == (30, 1) and ctrl.shape == (60, 1)
+    assert abs(np.mean(Ytr)) < 1e-12 and abs(np.std(Ytr) - 1) < 1e-12 and abs(np.mean(ctrl)) < 1e-12
+    assert np.isclose(ystd, np.std(raw[:30, 1])) and np.isclose(ymean, np.mean(raw[:30, 1]))
+    with pytest.raises(ValueError):
+        datasets.create_dataset("nope/", str(tmp_path))
+    expect = {1: [], 2: ["logv", "logl", "U"], 3: ["logv", "logl", "U", "Z"], 4: [], 5: ["logv", "logl"], 6: [], 7: ["U", "X"]}
+    for case_val, (ko, uo, zo, uc, pg) in datasets.CASE_TABLE.items():
+        assert sghmc_variable_names(_capi.KERNEL_SE, case_val, ko, True, uo, uc, zo) == expect[case_val]
+        assert pg == (case_val == 6)
+    f = dict(C_val=np.ones((1, 4)), d_val=np.zeros(1), Q_sqrt_ini=np.ones(4), R_chol_val=np.ones((1, 1)), kernel_lengthscales=np.ones((4, 5)),
+             kernel_variance=np.ones(4), Umu_ini=np.zeros((4, 100)), qx1_mu_ini=np.zeros(4), x_samples_training=np.zeros((30, 7, 4)),
+             Z_val=np.zeros((100, 5)))
+    a = datasets.arguments_from_factnonlin(f)
+    assert a["CC"].shape == (4, 1) and a["UU_ini"].shape == (100, 4) and a["x_initialization"].shape == (30, 4)
