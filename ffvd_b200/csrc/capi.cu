@@ -403,6 +403,15 @@ static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs,
   return FFVD_OK;
 }
 static int rb_of(int Mp) { return fused_cfg(Mp).rb; }
+// output dims per block of the work-item order: keep the operand matrices of one block (16 Mp^2 bytes per dim) within
+// ~16 MB of L2.  FFVD_DBLK overrides (experiments).
+static int dblk_of(int Mp, int D) {
+  int b = (int)((size_t)16 * 1024 * 1024 / ((size_t)16 * Mp * Mp));
+  if (const char* e = getenv("FFVD_DBLK")) b = atoi(e);
+  if (b < 1) b = 1;
+  if (b > D) b = D;
+  return b;
+}
 
 static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X, double* XT, int* status, int nbatch,
                                  int M, int Mp);
@@ -578,6 +587,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     P.dvec = t.d.d; P.logR = t.logR.d; P.Y = t.Y.d; P.ctrl = t.ctrl.d;
     P.S = t.S; P.T = t.T; P.D = D; P.Din = Din; P.nc = t.nc; P.Dy = Dy; P.M = M; P.Mp = Mp; P.Dx = D; P.xrows = t.T + 1; P.hs = 1;
     P.ntiles = (t.T + BT - 1) / BT;
+    P.dblk = dblk_of(Mp, D);
     P.item_begin = item;
     P.nitems = (long long)D * t.S * P.ntiles;
     item += P.nitems;
@@ -873,7 +883,7 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
   const int RB = rb_of(P.Mp), BT = 8 * RB;
   P.hs = shared_kernel ? 0 : 1;
   P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;
-  P.ntiles = (N + BT - 1) / BT; P.item_begin = 0; P.nitems = (long long)R * P.ntiles;
+  P.ntiles = (N + BT - 1) / BT; P.dblk = dblk_of(P.Mp, R); P.item_begin = 0; P.nitems = (long long)R * P.ntiles;
   P.cond_mean = tm.d; P.cond_var = tvar.d;
   if (tq.present) {
     if (tq.ndim == 2) {                       // (M,R) per-point scales, conditionals_multi_output.py:51-52

@@ -57,6 +57,7 @@ struct DevProblem {
   int xrows;           // valid rows of X per sample (T+1 for nll, N for conditional())
   int hs;              // hyper-parameter / Linv stride per output dim: 1 = list of D kernels, 0 = one shared kernel
   int ntiles;          // tiles per sample
+  int dblk;            // output dims per block of the work-item order (see fused_kernel)
   long long item_begin;   // first work item of this problem (prefix sum)
   long long nitems;       // D * S * ntiles
 };

@@ -575,13 +575,25 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
     const DevProblem& P = probs[pi];
     const long long li = item - P.item_begin;
-    // d is the FASTEST index: the D items of one (sample, tile) run on neighbouring CTAs at the same time, so the
-    // x tile is fetched from HBM once and the D contributions to its x-bar rows meet in L2 (ordering d slowest re-read
-    // X and re-wrote x-bar once per output dim: 8x the algorithmic DRAM bytes at C3, ncu round-1 capture)
-    const int d = (int)(li % P.D);
-    const long long st = li / P.D;
-    const int tile_i = (int)(st % P.ntiles);
-    const int s = (int)(st / P.ntiles);
+    // Work-item order inside a problem: blocks of `dblk` output dims (slowest), then (sample, tile), then d inside the
+    // block (fastest).  The dblk items of one (sample, tile) run on neighbouring CTAs at the same time, so the x tile
+    // is fetched from HBM once per block and its x-bar contributions meet in L2 (d slowest re-read X and re-wrote
+    // x-bar once per output dim: 8x the algorithmic DRAM bytes at C3); dblk is chosen by the host so that the L^{-1}
+    // / L^{-T} operands of one block (dblk * 16 Mp^2 bytes, streamed by every tile) stay a small part of L2.
+    int d, tile_i, s;
+    {
+      const int DB = P.dblk;
+      const long long per_blk = (long long)P.S * P.ntiles * DB;
+      const int nfull = P.D / DB;
+      const long long blk = li / per_blk;
+      long long rem = li - blk * per_blk;
+      int bs = DB, d0 = (int)blk * DB;
+      if (blk >= nfull) { rem = li - (long long)nfull * per_blk; bs = P.D - nfull * DB; d0 = nfull * DB; }
+      d = d0 + (int)(rem % bs);
+      const long long st = rem / bs;
+      tile_i = (int)(st % P.ntiles);
+      s = (int)(st / P.ntiles);
+    }
     const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, Mp = P.Mp, nc = P.nc;
     const int lda = Mp + 4;
     const int t0 = tile_i * BT;

@@ -134,6 +134,16 @@ def test_ragged_shapes(env, T, M, D, S, collapsed):
     check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="T%d M%d" % (T, M))
 
 
+@pytest.mark.parametrize("T,M,D,n_ctrl", [(70, 40, 16, 1), (90, 200, 12, 3), (33, 130, 14, 1), (40, 60, 20, 11), (50, 500, 16, 1)])
+@pytest.mark.parametrize("collapsed,kind", ((False, 0), (True, 0), (False, 1)))
+def test_wide_inputs(env, T, M, D, n_ctrl, collapsed, kind):
+    """Din = 15 / 16 (the boundary between two and four 8-column blocks of [X,1] / [Z,1] in the W back-propagation), 17
+    (the C5 shape: D = 16 + one control) and 31 (the build's limit)."""
+    from oracle import fixtures, ffvd_oracle as O
+    prob = fixtures.synthetic_problem(T=T, M=M, D=D, S=1, n_ctrl=n_ctrl, seed=7 * T + M, kind=kind)
+    check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="Din%d M%d" % (D + n_ctrl, M))
+
+
 def test_no_control_inputs_and_multi_output_y(env):
     from oracle import fixtures, ffvd_oracle as O
     prob = fixtures.synthetic_problem(T=50, M=20, D=3, S=1, n_ctrl=0, Dy=2)
