@@ -598,7 +598,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       CUDA_TRY(cudaMallocAsync((void**)&t.gx_scratch, t.X.numel * 8, c->stream));
       P.gX = t.gx_scratch;
     }
-    if (P.gX) CUDA_TRY(cudaMemsetAsync(P.gX, 0, t.X.numel * 8, c->stream));
+    if (P.gX && nprob <= 4) CUDA_TRY(cudaMemsetAsync(P.gX, 0, t.X.numel * 8, c->stream));
     OutPtrs& O = ho[p];
     O.nll = t.nll.d; O.terms = t.terms.d; O.g_Z = t.gZ.d; O.g_U = t.gU.d; O.g_logv = t.glogv.d; O.g_logl = t.glogl.d;
     O.g_logQ = t.glogQ.d; O.g_C = t.gC.d; O.g_d = t.gd.d; O.g_logR = t.glogR.d;
@@ -608,6 +608,11 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   CUDA_TRY(cudaMemcpyAsync(c->d_probs, hp.data(), sizeof(DevProblem) * nprob, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->d_outs, ho.data(), sizeof(OutPtrs) * nprob, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
+  if (nprob > 4) {           // many small problems: one launch instead of nprob memsets
+    size_t maxn = 0;
+    for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
+    zero_gx_kernel<<<dim3(grid1d(maxn, 256, 64), nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+  }
 
   TRY(launch_prep<KIND>(c, L, jitter));
   const int nz = nprob * nb;

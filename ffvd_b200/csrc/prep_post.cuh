@@ -411,6 +411,14 @@ __global__ void __launch_bounds__(256) zscale_kernel(const DevProblem* __restric
   }
 }
 
+// x-bar <- 0 for every problem of a batch.  grid (blocks, nprob); block 256.
+__global__ void zero_gx_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  if (!P.gX) return;
+  const size_t n = (size_t)P.S * (P.T + 1) * P.D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) P.gX[i] = 0.0;
+}
+
 // Uncollapsed: w_d = L_d^{-T} u_d, so that the fused kernel can form Kbar = (A L^{-1})/Q + e w^T without touching the
 // A operand of its second contraction.  grid (D, nprob); block 256 (warp per row of the upper-triangular L^{-T}).
 __global__ void __launch_bounds__(256) ltu_kernel(const DevProblem* __restrict__ probs) {

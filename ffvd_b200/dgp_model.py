@@ -157,10 +157,16 @@ class DGPSSM(BaseModel):
         """One evaluation of nll (dgp_model.py:248-297) and all its gradients (base_model.py:148)."""
         if self._out is None:
             self._out = self._alloc_outputs()
-        prob = dict(self.params)
-        prob.update(self.data)
-        prob.setdefault("logl", None)
-        self.ctx.nll_grads(self.kind, self.U_collapse, prob, self._out, flags=self.flags | flags_extra, jitter=1e-5)
+            self._prepared = {}
+        call = self._prepared.get(flags_extra)
+        if call is None:
+            # tensors are bound once (they are only ever updated in place); 21 evaluations per sghmc_step re-use the binding
+            prob = dict(self.params)
+            prob.update(self.data)
+            prob.setdefault("logl", None)
+            call = self.ctx.prepare_nll_grads(self.kind, self.U_collapse, prob, self._out, flags=self.flags | flags_extra, jitter=1e-5)
+            self._prepared[flags_extra] = call
+        call.run()
         return self._out
 
     @property
