@@ -664,7 +664,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   if (!no_grads) {
     size_t maxn = 0;
     for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
-    scale_gx_kernel<<<dim3(grid1d(maxn), nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    scale_gx_kernel<<<dim3(grid1d(maxn), nprob), 256, 0, c->stream>>>(c->d_probs, flags); c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
   for (auto& t : pt)

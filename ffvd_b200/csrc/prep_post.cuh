@@ -524,17 +524,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
   const int tid = threadIdx.x, nth = blockDim.x;
   const int M = P.M, Mp = P.Mp, D = P.D, Din = P.Din, Dy = P.Dy, S = P.S, T = P.T;
   const double sc = -1.0 / (double)T;
-  const double npri = (flags & 2) ? 1.0 : (double)S;
+  const bool shared_priors = (flags & 16) == 0, x0_prior = (flags & 32) == 0;
+  const double npri = !shared_priors ? 0.0 : ((flags & 2) ? 1.0 : (double)S);
   const bool zprior = (flags & 1) != 0;
   const double log005 = log(0.05);
-  const double pz = zprior ? -0.5 * block_sum_sq(P.Z, M * Din, 0.0, &red) : 0.0;
+  double pz = zprior ? -0.5 * block_sum_sq(P.Z, M * Din, 0.0, &red) : 0.0;
   double ph = -0.5 * block_sum_sq(P.logv, D, log005, &red);
   if (KIND == 0) ph += -0.5 * block_sum_sq(P.logl, D * Din, 0.0, &red);
-  const double pu = collapsed ? 0.0 : -0.5 * block_sum_sq(P.U, M * D, 0.0, &red);
-  const double hyp = -0.5 * (block_sum_sq(P.logQ, D, 0.0, &red) + block_sum_sq(P.C, D * Dy, 0.0, &red) +
-                             block_sum_sq(P.dvec, Dy, 0.0, &red) + block_sum_sq(P.logR, Dy * Dy, 0.0, &red));
+  double pu = collapsed ? 0.0 : -0.5 * block_sum_sq(P.U, M * D, 0.0, &red);
+  double hyp = -0.5 * (block_sum_sq(P.logQ, D, 0.0, &red) + block_sum_sq(P.C, D * Dy, 0.0, &red) +
+                       block_sum_sq(P.dvec, Dy, 0.0, &red) + block_sum_sq(P.logR, Dy * Dy, 0.0, &red));
+  if (!shared_priors) pz = ph = pu = hyp = 0.0;
   for (int s = 0; s < S; ++s) {
-    const double px0 = -0.5 * block_sum_sq(P.X + (size_t)s * (T + 1) * D, D, 0.0, &red);
+    const double px0 = x0_prior ? -0.5 * block_sum_sq(P.X + (size_t)s * (T + 1) * D, D, 0.0, &red) : 0.0;
     if (tid == 0) {
       const double* r = P.terms_raw + (size_t)s * FFVD_NTERMS_RAW;
       double t[6];
@@ -563,14 +565,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
 }
 
 // g_X = -(raw - [t==0] X_0)/T, in place.   grid (blocks, nprob)
-__global__ void scale_gx_kernel(const DevProblem* __restrict__ probs) {
+__global__ void scale_gx_kernel(const DevProblem* __restrict__ probs, int flags) {
   const DevProblem& P = probs[blockIdx.y];
   const size_t per = (size_t)(P.T + 1) * P.D, n = per * P.S;
   const double sc = -1.0 / (double)P.T;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i % per;
     double v = P.gX[i];
-    if (r < (size_t)P.D) v -= P.X[i];
+    if (r < (size_t)P.D && !(flags & 32)) v -= P.X[i];
     P.gX[i] = sc * v;
   }
 }

@@ -1,7 +1,10 @@
 """Multi-GPU plumbing: one process per GPU, samples (or whole chains) sharded across ranks with
 no data-path collective; a single all-reduce of the packed shared-parameter gradients and the
 scalar objective per evaluation.  `torch.distributed` (NCCL on GPUs, gloo in the
-CPU tests) is the transport; x-bar never leaves its owner."""
+CPU tests) is the transport; x-bar never leaves its owner.
+
+When there are fewer trajectories than GPUs (one long chain), `time_block` / `evaluate_time_sharded` shard T instead
+(SURVEY 8e): contiguous blocks of transitions with a one-row halo, uncollapsed form."""
 from __future__ import annotations
 
 from typing import Dict, List, Sequence, Tuple
@@ -46,3 +49,78 @@ def allreduce_shared(outputs: Dict[str, object], group=None, names: Sequence[str
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     unpack(flat, outputs, present)
     return outputs
+
+
+# ---- time sharding of ONE trajectory (S < number of GPUs) -----------------------------------------------------------
+def time_block(problem: Dict[str, object], rank: int, world: int) -> Tuple[Dict[str, object], int, int]:
+    """The block of transitions [a, b) owned by `rank`, as an ordinary problem: X rows a..b (b - a + 1 rows: the last
+    one is the halo row x_b owned by the next rank), Y and ctrl rows a..b-1; everything else shared.
+    Works on NumPy arrays and torch tensors (views, no copies of the parameters)."""
+    X = problem["X"]
+    if X.ndim != 2:
+        raise ValueError("time sharding is for one trajectory: X must be (T+1, D)")
+    T = X.shape[0] - 1
+    a, b = shard_range(T, rank, world)
+    blk = dict(problem)
+    blk["X"] = X[a:b + 1]
+    blk["Y"] = problem["Y"][a:b]
+    if problem.get("ctrl") is not None:
+        blk["ctrl"] = problem["ctrl"][a:b]
+    return blk, a, b
+
+
+def time_block_flags(rank: int) -> int:
+    """Block 0 carries the shared-parameter priors and the x_0 prior; the other blocks drop both."""
+    from . import _capi
+    return 0 if rank == 0 else (_capi.FLAG_NO_SHARED_PRIORS | _capi.FLAG_NO_X0_PRIOR)
+
+
+def evaluate_time_sharded(evaluate, problem: Dict[str, object], outputs: Dict[str, object], rank: int, world: int, group=None):
+    """nll and gradients of ONE trajectory whose T transitions are split over `world` ranks (uncollapsed form).
+
+    `evaluate(block_problem, block_outputs, extra_flags)` runs the ordinary single-GPU evaluation on a block (the CUDA
+    path: `ctx.nll_grads(kind, False, blk, out, flags=base | extra_flags)`).  `outputs` holds this rank's tensors:
+    `g_X` with the block's b - a + 1 rows, `nll` (1,), `terms` (1,6) and the shared-parameter gradients.  After the
+    call: nll / terms / shared gradients are the FULL-trajectory values on every rank (one packed all-reduce);
+    g_X rows a..b-1 (plus row b on the last rank) are final on their owner -- the halo row's contribution was sent
+    to the next rank and the first row received the previous rank's (one all-gather of D doubles per rank).
+    Every block evaluates with its own T_b in the 1/T normalisation (dgp_model.py:264-297), so everything is
+    rescaled by T_b / T before the reduction."""
+    import torch
+    import torch.distributed as dist
+    T = problem["X"].shape[0] - 1
+    blk, a, b = time_block(problem, rank, world)
+    evaluate(blk, outputs, time_block_flags(rank))
+    scale = float(b - a) / float(T)
+    for k, v in outputs.items():
+        if v is not None:
+            v.mul_(scale)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return outputs
+    names = ("nll", "terms") + SHARED
+    flat, present = pack(outputs, names)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    unpack(flat, outputs, present)
+    gX = outputs.get("g_X")
+    if gX is not None:
+        last = gX[-1].clone().contiguous()                 # contribution of this block to the halo row x_b
+        rows = [torch.empty_like(last) for _ in range(world)]
+        dist.all_gather(rows, last, group=group)
+        if rank > 0:
+            gX[0].add_(rows[rank - 1])                     # row a = halo row of the previous block
+    return outputs
+
+
+def exchange_halo_row(X_block, rank: int, world: int, group=None):
+    """After the owners updated their rows (SG-HMC / Adam), refresh every block's halo row x_b from the next rank's
+    first row (one all-gather of D doubles per rank)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return X_block
+    first = X_block[0].clone().contiguous()
+    rows = [torch.empty_like(first) for _ in range(world)]
+    dist.all_gather(rows, first, group=group)
+    if rank + 1 < world:
+        X_block[-1].copy_(rows[rank + 1])
+    return X_block

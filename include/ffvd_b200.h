@@ -59,6 +59,10 @@ typedef struct DLManagedTensor {
 #define FFVD_FLAG_PRIOR_ONCE      2   /* count shared-parameter priors once instead of S times  */
 #define FFVD_FLAG_NO_GRADS        4   /* forward only: nll + terms                               */
 #define FFVD_FLAG_ASYNC           8   /* do not synchronise to read back the Cholesky status     */
+/* time-sharded evaluation of ONE trajectory (ffvd_b200/distributed.py: a block of consecutive transitions per GPU):
+ * every block is an ordinary problem whose nll / gradients are then rescaled by T_block / T_total by the caller */
+#define FFVD_FLAG_NO_SHARED_PRIORS 16 /* drop the priors on Z, U, kernel hypers, logQ, C, d, logR (blocks other than the first) */
+#define FFVD_FLAG_NO_X0_PRIOR      32 /* drop -1/2 |X_0|^2 (dgp_model.py:252): the block does not start at t = 0 */
 
 typedef struct ffvd_ctx ffvd_ctx;
 

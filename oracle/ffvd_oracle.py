@@ -394,7 +394,7 @@ def _priors(p, kind, prior_type, include_U):
 
 
 def nll_terms(p: Dict[str, torch.Tensor], Y, ctrl, *, collapsed: bool, kind: int = 0,
-              prior_type: str = "normal"):
+              prior_type: str = "normal", shared_priors: bool = True, x0_prior: bool = True):
     """Scalar nll and its named terms for ONE trajectory, `dgp_model.py:248-297`.
 
     Full batch: batch_placeholder = [0, X_N] (base_model.py:194) so batch_size == Y_N == T.
@@ -411,6 +411,10 @@ def nll_terms(p: Dict[str, torch.Tensor], Y, ctrl, *, collapsed: bool, kind: int
     log_lik = logdensity_norm_diag(Y[0:T], y_mean, Rchols[0])              # dgp_model.py:250
     prior_x_0 = -torch.sum(torch.square(X[0])) / 2.0                        # :252
     prior_Z, prior_hyper, prior_U, hyp = _priors(p, kind, prior_type, include_U=not collapsed)
+    if not shared_priors:          # time-sharded evaluation: blocks after the first (FFVD_FLAG_NO_SHARED_PRIORS)
+        prior_Z = prior_hyper = prior_U = hyp = torch.zeros((), dtype=DT)
+    if not x0_prior:               # blocks that do not start at t = 0 (FFVD_FLAG_NO_X0_PRIOR)
+        prior_x_0 = torch.zeros((), dtype=DT)
     nll_log_likelihood = -torch.sum(log_lik) / Tf                           # :264
     Xc = torch.cat((X[0:T], ctrl[0:T]), dim=1) if Din > D else X[0:T]       # :269 / :340
     out = {}
@@ -439,7 +443,7 @@ def nll_terms(p: Dict[str, torch.Tensor], Y, ctrl, *, collapsed: bool, kind: int
 TERM_NAMES = ("prior", "loglik", "xq", "trace", "term1", "term2")
 
 
-def nll_and_grads(prob: Problem, *, collapsed: bool) -> Dict[str, np.ndarray]:
+def nll_and_grads(prob: Problem, *, collapsed: bool, shared_priors: bool = True, x0_prior: bool = True) -> Dict[str, np.ndarray]:
     """nll, the six terms and d nll / d{X,Z,U,logv,logl,logQ,C,d,logR} by autograd
     (the stand-in for `tf.gradients`, base_model.py:148 / `adam.minimize`, dgp_model.py:305).
 
@@ -462,7 +466,8 @@ def nll_and_grads(prob: Problem, *, collapsed: bool) -> Dict[str, np.ndarray]:
             v = getattr(prob, k)
             if v is not None:
                 p[k] = _t(v, True)
-        out = nll_terms(p, Y, ctrl, collapsed=collapsed, kind=prob.kind, prior_type=prob.prior_type)
+        out = nll_terms(p, Y, ctrl, collapsed=collapsed, kind=prob.kind, prior_type=prob.prior_type, shared_priors=shared_priors,
+                        x0_prior=x0_prior)
         names = list(p.keys())
         grads = torch.autograd.grad(out["nll"], [p[k] for k in names], allow_unused=True)
         nlls[s] = out["nll"].item()

@@ -533,3 +533,60 @@ def test_outer_training_loop(env):
     model2 = m2.fit(prob.Y)
     assert model2.vars == ["logv", "logl", "U"] and len(model2.window) == 2
     assert np.isfinite(float(model2.nll))
+
+
+def test_time_blocks_reassemble_full_trajectory(env):
+    """Time sharding (SURVEY 8e, S < #GPUs): two blocks of one trajectory evaluated with FFVD_FLAG_NO_SHARED_PRIORS /
+    FFVD_FLAG_NO_X0_PRIOR on the second, rescaled by T_b / T and stitched at the halo row, equal the full evaluation
+    (the collective itself is covered by the gloo test; here the CUDA path produces the blocks)."""
+    from oracle import fixtures
+    from ffvd_b200 import distributed
+    torch, ctx = env["torch"], env["ctx"]
+    prob = fixtures.synthetic_problem(T=157, M=70, D=3, S=1)
+    p = dev_problem(env, prob)
+    full = alloc_out(env, p)
+    ctx.nll_grads(0, False, p, full)
+    T = prob.Y.shape[0]
+    acc = {k: torch.zeros_like(v) for k, v in full.items() if k != "g_X"}
+    gX = torch.zeros_like(full["g_X"])
+    for rank in range(3):
+        blk, a, b = distributed.time_block(p, rank, 3)
+        blk = {k: (v.contiguous() if v is not None else None) for k, v in blk.items()}
+        o = alloc_out(env, blk)
+        ctx.nll_grads(0, False, blk, o, flags=env["ffvd"].FLAG_PRIOR_Z_NORMAL | distributed.time_block_flags(rank))
+        sc = (b - a) / T
+        for k in acc:
+            acc[k] += sc * o[k]
+        gX[a:b + 1] += sc * o["g_X"]
+    torch.cuda.synchronize()
+    for k in acc:
+        assert_close(full[k].cpu().numpy(), acc[k].cpu().numpy(), 1e-11, k)
+    assert_close(full["g_X"].cpu().numpy(), gX.cpu().numpy(), 1e-11, "g_X")
+
+
+def test_prepared_call_sees_in_place_updates(env):
+    """Context.prepare_nll_grads binds tensors once; re-running after an in-place parameter update must give the same
+    result as a fresh (unbound) call -- single problem and batch."""
+    from oracle import fixtures
+    torch, ctx = env["torch"], env["ctx"]
+    probs = [fixtures.synthetic_problem(T=90 + 10 * i, M=33, D=2, S=1, seed=i) for i in range(6)]
+    Ps = [dev_problem(env, q) for q in probs]
+    Os = [alloc_out(env, p) for p in Ps]
+    call = ctx.prepare_nll_grads(0, True, Ps, Os)
+    call.run()
+    for p in Ps:
+        p["X"].mul_(0.9); p["Z"].add_(0.01)
+    call.run()
+    torch.cuda.synchronize()
+    fresh = [alloc_out(env, p) for p in Ps]
+    ctx.nll_grads_batched(0, True, Ps, fresh)
+    torch.cuda.synchronize()
+    for a, b in zip(Os, fresh):
+        for k in a:
+            assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-10, k)      # FP64 RED order differs from run to run
+    call.close()
+    one = ctx.prepare_nll_grads(0, False, Ps[0], Os[0])
+    one.run(); torch.cuda.synchronize()
+    ref = alloc_out(env, Ps[0]); ctx.nll_grads(0, False, Ps[0], ref); torch.cuda.synchronize()
+    for k in ref:
+        assert_close(ref[k].cpu().numpy(), Os[0][k].cpu().numpy(), 1e-10, k)
