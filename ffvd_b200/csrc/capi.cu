@@ -245,7 +245,7 @@ struct Layout {
   int nprob, nb, D, M, Mp, Din, Dy, nk;   // nk = kernels per problem (D, or 1 when shared)
   long long sumS;
   bool collapsed;
-  size_t off_ZT, off_ZTs, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
+  size_t off_ZT, off_ZTs, off_hyp, off_hq, off_UT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
       off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, total;
   int nfac;                        // matrices in the blocked-factorisation pools: nprob * max(nk, nb)
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
@@ -263,6 +263,9 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.off_ZT = take((size_t)nprob * 64 * Mp * 8);          // Z~^T and its fragment-ordered copy
   L.off_ZTs = take((size_t)nprob * nk * 32 * Mp * 8);
+  L.off_hyp = take((size_t)nprob * nk * 72 * 8);
+  L.off_hq = take((size_t)nprob * D * 4 * 8);
+  L.off_UT = take((size_t)nprob * D * Mp * 8);
   L.off_kscr = take((size_t)320 * 64 * Mp * 8);          // per-CTA K-tile scratch of the fused kernel (<= 2 CTAs / SM)
   L.off_Linv = take((size_t)nprob * nk * mm);
   L.off_LinvT = take((size_t)nprob * nk * mm);
@@ -324,6 +327,9 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   P.ZT = (double*)(a + L.off_ZT) + (size_t)p * 64 * L.Mp;
   P.Zf = P.ZT + (size_t)32 * L.Mp;
   P.ZTs = (double*)(a + L.off_ZTs) + (size_t)p * L.nk * 32 * L.Mp;
+  P.hyp = (double*)(a + L.off_hyp) + (size_t)p * L.nk * 72;
+  P.hq = (double*)(a + L.off_hq) + (size_t)p * L.D * 4;
+  P.UT = (double*)(a + L.off_UT) + (size_t)p * L.D * L.Mp;
   P.Linv = (double*)(a + L.off_Linv) + (size_t)p * L.nk * mm;
   P.LinvT = (double*)(a + L.off_LinvT) + (size_t)p * L.nk * mm;
   P.Sacc = (double*)(a + L.off_Sacc) + (size_t)p * L.nb * mm;
@@ -383,7 +389,7 @@ static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs,
 #endif
   if (!kern) return fail(FFVD_E_BADARG, "no fused kernel instantiated for this (Mp, FFVD_RB, FFVD_NW, FFVD_MINB)");
   const int RB = cfg.rb;
-  const size_t smem = fused_smem_bytes(RB, Mp, cfg.nw, (Din + 1 <= 16) ? 2 : 4);
+  const size_t smem = fused_smem_bytes(RB, Mp, cfg.nw, (Din + 1 + 7) / 8);
   if ((int)smem > c->max_smem) return fail(FFVD_E_LIMIT, "fused kernel shared memory exceeds the device limit");
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -424,6 +430,7 @@ static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
 
 template <int KIND>
 static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter) {
+  hyper_kernel<<<dim3(L.nk > L.D ? L.nk : L.D, L.nprob), 128, 0, c->stream>>>(c->d_probs, KIND, L.nk); c->launches++;
   if (KIND == 0) { zscale_kernel<<<dim3(L.nk, L.nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
   if (use_blocked(c, L.M, L.Mp)) {
     double* Lfac = (double*)(c->arena + L.off_Lfac);
@@ -916,6 +923,8 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
     P.U = utmp;
     CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
   }
+  // U (possibly un-whitened) was bound after setup_zside ran the prep kernels: refresh U^T
+  hyper_kernel<<<dim3(nk > R ? nk : R, 1), 128, 0, c->stream>>>(c->d_probs, kind, nk); c->launches++;
   if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   else TRY((launch_fused<1, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   int st = check_status(c, L);

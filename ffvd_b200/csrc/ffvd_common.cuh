@@ -26,6 +26,9 @@ struct DevProblem {
   double *ZT;          // [32][Mp]    Z~^T: transposed, zero padded inducing inputs, then a row of ones (m < M), zeros
   double *Zf;          // [Mp/4][4][32] the same matrix in DMMA B-fragment order: entry ((m>>2)*4 + (jd>>3))*32 + (jd&7)*4 + (m&3)
   double *ZTs;         // [nk][32][Mp] SE: per-kernel scaled copy z~ = z/l (rows 0..Din-1) and row Din = -1/2 |z~_m|^2
+  double *hyp;         // [nk][72]   per kernel: 1/l^2 [0..31], 1/l [32..63], v [64]           (hyper_kernel)
+  double *hq;          // [D][4]     per output dim: Q, 1/Q, log Q                              (hyper_kernel)
+  double *UT;          // [D][Mp]    U transposed, zero padded (coalesced staging of u_d)       (hyper_kernel)
   double *Linv;        // [D][Mp][Mp] L^{-1}  (lower), zero padded
   double *LinvT;       // [D][Mp][Mp] L^{-T}  (upper)
   // accumulators (zeroed before each evaluation)

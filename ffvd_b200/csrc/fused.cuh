@@ -53,15 +53,17 @@ struct Smem {
 // SE follows the reference's expansion (kernels_multi_output.py:163-182): -r^2/2 = x~.z~ - |x~|^2/2 - |z~|^2/2 with
 // x~ = x/l (sm.xsc, sm.xn2h) and z~ = z/l (ZTd rows 0..Din-1, row Din = -|z~|^2/2, zscale_kernel): one FMA per
 // (element, input dim); exp through the branch-free, lock-step exp_nonpos_n.  Linear: ZTd = Z~^T unscaled.
-// The ZTd rows stream from L2 through a 4-slot register ring (4 input dims ahead); the first rows of the next column
+// The ZTd rows stream from L2 through a 4- or 8-slot register ring (that many input dims ahead); the first rows of the next column
 // group are requested before the exp / store work of the current one.
 template <int KIND, int RB, int NGW, bool SCR>
 __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __restrict__ ZTd, int Mp, int Din, double v,
                                                int wc, int g, int q, int M, int row0, int lda, double* __restrict__ kscr) {
-  double2 ring[4][2], hz[2];
+  // ring depth in input dims: one step is 4 RB FMAs per lane, so fewer rows per warp need a deeper ring to cover L2 latency
+  constexpr int RING = RB >= 8 ? 4 : 8;
+  double2 ring[RING][2], hz[2];
   auto prologue = [&](int jb) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < RING; ++u) {
       ring[u][0] = ring[u][1] = make_double2(0.0, 0.0);
       if (u < Din) {
         ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)u * Mp + jb));
@@ -88,15 +90,15 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
         for (int c = 0; c < 4; ++c) s[rb][c] = (KIND == 0) ? hx + h[c] : 0.0;
       }
     }
-    for (int j0 = 0; j0 < Din; j0 += 4) {
+    for (int j0 = 0; j0 < Din; j0 += RING) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < RING; ++u) {
         const int jd = j0 + u;
         if (jd < Din) {
           const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
-          if (jd + 4 < Din) {
-            ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + 4) * Mp + jb));
-            ring[u][1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + 4) * Mp + jb + 2));
+          if (jd + RING < Din) {
+            ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + RING) * Mp + jb));
+            ring[u][1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + RING) * Mp + jb + 2));
           }
 #pragma unroll
           for (int rb = 0; rb < RB; ++rb) {
@@ -349,7 +351,8 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
 // SE: W = kbar*k;  Linear: W = kbar (the factor v is applied here).
 // Both products run on the tensor pipe with every global operand (Z~ fragments, the Z values of the epilogue)
 // requested ahead of its use, and all reductions end in fire-and-forget global REDs.
-// NBM = compile-time bound on the 8-column blocks of [Xc,1] / [Z,1] (2 for Din <= 15, else 4).
+// NBM = number of 8-column blocks of [Xc,1] / [Z,1] = ceil((Din+1)/8), exact: a predicated-off DMMA for an unused block
+// would still occupy the tensor pipe.
 template <int KIND, int RB, int NGW, int NW, int NBM>
 __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevProblem& P, int d, double v, double* gXs,
                                            int t0, int nvalid, int warp, int lane, int tid
@@ -359,7 +362,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
                                            ) {
   const int g = lane >> 2, q = lane & 3;
   const int Din = P.Din, M = P.M, Mp = P.Mp, D = P.D;
-  const int nbx = (Din + 1 + 7) >> 3;           // n-blocks covering Din+1 columns (<= NBM)
+  constexpr int nbx = NBM;                      // n-blocks covering Din+1 columns
   constexpr int BT = 8 * RB;
   const double* tile = sm.tile;
   // ---- W^T X~ : 8 warps own m-blocks w, w+8, ...  (NW == 16: warps 8..15, concurrently with W Z~ on warps 0..7)
@@ -559,6 +562,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
   const int wc = warp & 7, row0 = (warp >> 3) * 8 * RBW;
   double* kscr = kscr_base + (size_t)blockIdx.x * BT * probs[0].Mp;     // per-CTA K-tile scratch (BT x Mp)
 
+  __shared__ DevProblem sP;
+  int cur_pi = -1;
 #ifdef FFVD_PHASE_TIMING
   long long _phase_last = clock64();
 #endif
@@ -573,7 +578,17 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
       pi = lo;
     }
-    const DevProblem& P = probs[pi];
+    // The problem descriptor lives in shared memory: its ~40 fields are read all over the item, and as global loads
+    // each first use per phase was a dependent L2 round trip in front of the phase's own loads.
+    if (pi != cur_pi) {
+      __syncthreads();          // nobody still reads the previous descriptor
+      const int* src = reinterpret_cast<const int*>(probs + pi);
+      int* dst = reinterpret_cast<int*>(&sP);
+      for (int i = tid; i < (int)(sizeof(DevProblem) / sizeof(int)); i += NTH) dst[i] = src[i];
+      cur_pi = pi;
+      __syncthreads();
+    }
+    const DevProblem& P = sP;
     const long long li = item - P.item_begin;
     // Work-item order inside a problem: blocks of `dblk` output dims (slowest), then (sample, tile), then d inside the
     // block (fastest).  The dblk items of one (sample, tile) run on neighbouring CTAs at the same time, so the x tile
@@ -606,7 +621,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       double* p = smem_raw;
       sm.tile = p; p += (size_t)BT * lda;
       sm.xs = p; p += ((BT + 1) * FFVD_XLD + 1) & ~1;
-      sm.xsc = p; sm.part = p; sm.stage = p; p += fused_xsc_part_doubles(BT, NW, (Din + 1 <= 16) ? 2 : 4);
+      sm.xsc = p; sm.part = p; sm.stage = p; p += fused_xsc_part_doubles(BT, NW, (Din + 1 + 7) >> 3);
       sm.us = p; p += Mp;
       sm.ws = p; p += Mp;
       sm.es = p; p += 64;
@@ -619,64 +634,69 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     const int dh = d * P.hs;
 
     __syncthreads();   // previous item fully done with shared memory
-    // ---- P0: stage the x tile and per-d vectors
+    // ---- P0: stage the x tile and per-d vectors.  The per-evaluation scalars (1/l, 1/l^2, v, Q, ...) and U^T come
+    //      precomputed from hyper_kernel; the scaled rows x~ = x/l and -1/2 |x~|^2 are formed in the same pass as the
+    //      raw rows: two CTA barriers instead of three.
+    const double* hyp = P.hyp + (size_t)dh * 72;
     if (tid < 64) {
-      double il2 = 0.0, sil = 0.0;
-      if (KIND == 0 && tid < 32 && tid < Din) {
-        const double ll = P.logl[(size_t)dh * Din + tid];
-        il2 = exp(-2.0 * ll);
-        sil = exp(-ll);
-      }
-      if (tid < 32) { sm.small[tid] = il2; sm.small[32 + tid] = sil; }
+      if (tid < 32) { sm.small[tid] = hyp[tid]; sm.small[32 + tid] = hyp[32 + tid]; }
       if (tid < 40) sm.red[tid] = 0.0;
-      if (tid == 40) sm.sc[0] = exp(P.logv[dh]);
-      if (tid == 41) {
-        const double lq = (MODE == MODE_COND) ? 0.0 : P.logQ[d];
-        const double Qv = exp(lq);
-        sm.sc[1] = Qv; sm.sc[2] = 1.0 / Qv; sm.sc[3] = lq;
-      }
+      if (tid == 40) sm.sc[0] = hyp[64];
+      if (tid >= 41 && tid < 44) sm.sc[tid - 40] = P.hq[(size_t)d * 4 + (tid - 41)];
     }
-    for (int idx = tid; idx < (BT + 1) * FFVD_XCOLS; idx += NTH) {
-      const int r = idx >> 5, c = idx & 31;
-      const int t = t0 + r;
-      double val = 0.0;
-      if (t < P.xrows) {
-        if (c < Dx) val = Xs[(size_t)t * Dx + c];
-        else if (c < Din) val = (t < T) ? P.ctrl[(size_t)t * nc + (c - Dx)] : 0.0;
+    {
+      const double silc = (KIND == 0 && lane < Din) ? hyp[32 + lane] : 0.0;
+      // all global loads of the tile are issued before the first one is consumed (a load -> store loop pays one
+      // L2 / HBM latency per trip: ~5k clk per work item at C3)
+      constexpr int NIT = ((BT + 1) * FFVD_XCOLS + NTH - 1) / NTH;
+      double xv[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * NTH;
+        const int r = idx >> 5, c = idx & 31;          // c == lane: NTH is a multiple of 32
+        const int t = t0 + r;
+        const double* src = nullptr;
+        if (r <= nvalid && r <= BT && t < P.xrows) {   // rows above nvalid stay zero (row nvalid is x_{t+1} of the last valid row)
+          if (c < Dx) src = Xs + (size_t)t * Dx + c;
+          else if (c < Din && t < T) src = P.ctrl + (size_t)t * nc + (c - Dx);
+        }
+        xv[it] = src ? __ldg(src) : 0.0;
       }
-      if (c == Din) val = (r < nvalid) ? 1.0 : 0.0;
-      if (r > nvalid && c < Din) val = 0.0;   // keep padded rows inert (row nvalid is x_{t+1} of the last valid row)
-      sm.xs[r * FFVD_XLD + c] = val;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * NTH;
+        const int r = idx >> 5, c = idx & 31;
+        if (r <= BT) {
+          const double sv = xv[it] * silc;             // 0 for c >= Din
+          sm.xs[r * FFVD_XLD + c] = (c == Din) ? ((r < nvalid) ? 1.0 : 0.0) : xv[it];
+          if (KIND == 0 && r < BT) sm.xsc[r * FFVD_XLD + c] = sv;
+        }
+      }
+      if (KIND == 0 && tid >= NTH - BT) {
+        // -1/2 |x~_r|^2, one thread per row, straight from global memory (the same lines the loop above just
+        // requested: L1 hits) so that it needs no barrier of its own; same rounded products as xsc
+        const int r = tid - (NTH - BT), t = t0 + r;
+        double a = 0.0;
+        if (r <= nvalid && t < P.xrows) {
+          for (int c = 0; c < Din; ++c) {
+            const double x = (c < Dx) ? Xs[(size_t)t * Dx + c] : ((t < T) ? P.ctrl[(size_t)t * nc + (c - Dx)] : 0.0);
+            const double sv = x * hyp[32 + c];
+            a = fma(sv, sv, a);
+          }
+        }
+        sm.xn2h[r] = -0.5 * a;
+      }
     }
     for (int j = tid; j < Mp; j += NTH) {
       double u = 0.0;
-      if (j < M) {
-        if (MODE == MODE_UNCOLLAPSED || MODE == MODE_FORWARD || MODE == MODE_COND) u = P.U[(size_t)j * D + d];
-        else if (MODE == MODE_COLLAPSED_P2) u = P.wvec[((size_t)s * D + d) * Mp + j];
-      }
+      if (MODE == MODE_UNCOLLAPSED || MODE == MODE_FORWARD || MODE == MODE_COND) u = P.UT[(size_t)d * Mp + j];
+      else if (MODE == MODE_COLLAPSED_P2) u = (j < M) ? P.wvec[((size_t)s * D + d) * Mp + j] : 0.0;
       sm.us[j] = u;
       if (MODE == MODE_UNCOLLAPSED) sm.ws[j] = P.wvec[(size_t)d * Mp + j];
       if (MODE == MODE_COND) sm.ws[j] = (P.qmode == 2 && j < M) ? P.qmat[(size_t)j * D + d] : 0.0;
     }
     __syncthreads();
     const double v = sm.sc[0], invQ = sm.sc[2], logQd = sm.sc[3];
-    if (KIND == 0) {
-      for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
-        const int r = idx >> 5, c = idx & 31;
-        sm.xsc[r * FFVD_XLD + c] = (c < Din) ? sm.xs[r * FFVD_XLD + c] * sm.small[32 + c] : 0.0;
-      }
-      if (tid >= NTH - BT) {
-        // -1/2 |x~_r|^2 from the same rounded products the tile code reads
-        const int r = tid - (NTH - BT);
-        double a = 0.0;
-        for (int c = 0; c < Din; ++c) {
-          const double t = sm.xs[r * FFVD_XLD + c] * sm.small[32 + c];
-          a = fma(t, t, a);
-        }
-        sm.xn2h[r] = -0.5 * a;
-      }
-      __syncthreads();
-    }
     FFVD_MARK(0);
 
     // ---- P1: K tile -> shared (SE uncollapsed: also to this CTA's L2-resident scratch, needed again for W = Kbar o K)
@@ -1009,8 +1029,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 #else
 #define FFVD_CW_TAIL
 #endif
-      if (Din + 1 <= 16) contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL);
-      else contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL);
+      switch ((Din + 1 + 7) >> 3) {
+        case 1: contract_W<KIND, RB, NGW, NW, 1>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 2: contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 3: contract_W<KIND, RB, NGW, NW, 3>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        default: contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+      }
 #undef FFVD_CW_TAIL
     }
 

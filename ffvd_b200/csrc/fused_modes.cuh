@@ -21,7 +21,7 @@ __host__ __device__ inline size_t fused_xsc_part_doubles(int BT, int NW, int nbm
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
-// nbm = 2 when Din + 1 <= 16 (the [Xc,1] / [Z,1] operands fit two 8-column blocks), else 4
+// nbm = ceil((Din + 1) / 8): 8-column blocks of the [Xc,1] / [Z,1] operands
 __host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp, int NW, int nbm) {
   const int BT = 8 * RB;
   // every sub-array is rounded up to an even number of doubles so that all of them stay 16-byte aligned

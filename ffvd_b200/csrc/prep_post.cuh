@@ -411,6 +411,37 @@ __global__ void __launch_bounds__(256) zscale_kernel(const DevProblem* __restric
   }
 }
 
+// Per-evaluation scalars the tile kernel would otherwise re-derive (with FP64 exp calls) in every work item:
+// hyp[k] = {1/l_j^2, 1/l_j, v} per kernel, hq[d] = {Q, 1/Q, log Q} per output dim, UT = U^T zero padded.
+// grid (max(nk, D), nprob); block 128.
+__global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int nk) {
+  const DevProblem& P = probs[blockIdx.y];
+  const int k = blockIdx.x, t = threadIdx.x, Din = P.Din, D = P.D, M = P.M, Mp = P.Mp;
+  if (k < nk) {
+    double* h = P.hyp + (size_t)k * 72;
+    if (t < 32) {
+      double il2 = 0.0, sil = 0.0;
+      if (kind == 0 && t < Din) {
+        const double ll = P.logl[(size_t)k * Din + t];
+        il2 = exp(-2.0 * ll);
+        sil = exp(-ll);
+      }
+      h[t] = il2; h[32 + t] = sil;
+    }
+    if (t == 32) h[64] = exp(P.logv[k]);
+  }
+  if (k < D) {
+    if (t == 33) {
+      const double lq = P.logQ ? P.logQ[k] : 0.0;
+      const double Qv = exp(lq);
+      double* q = P.hq + (size_t)k * 4;
+      q[0] = Qv; q[1] = 1.0 / Qv; q[2] = lq; q[3] = 0.0;
+    }
+    if (P.U)
+      for (int j = t; j < Mp; j += blockDim.x) P.UT[(size_t)k * Mp + j] = (j < M) ? P.U[(size_t)j * D + k] : 0.0;
+  }
+}
+
 // x-bar <- 0 for every problem of a batch.  grid (blocks, nprob); block 256.
 __global__ void zero_gx_kernel(const DevProblem* __restrict__ probs) {
   const DevProblem& P = probs[blockIdx.y];
