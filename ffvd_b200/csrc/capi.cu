@@ -974,8 +974,12 @@ extern "C" int ffvd_sghmc_update(ffvd_ctx* c, DLManagedTensor* theta, DLManagedT
   if (n) {
     const double eps_scaled = epsilon / sqrt(X_N);
     const int grid = grid1d(n, 256, c->num_sms * 8);
-    if (burn_in) sghmc_kernel<1><<<grid, 256, 0, c->stream>>>(tt.d, tg.d, tn.d, txi.d, tgg.d, tg2.d, tp.d, n, epsilon, mdecay, eps_scaled);
-    else sghmc_kernel<0><<<grid, 256, 0, c->stream>>>(tt.d, tg.d, tn.d, txi.d, tgg.d, tg2.d, tp.d, n, epsilon, mdecay, eps_scaled);
+    const uintptr_t al = (uintptr_t)tt.d | (uintptr_t)tg.d | (uintptr_t)tn.d | (uintptr_t)txi.d | (uintptr_t)tgg.d | (uintptr_t)tg2.d | (uintptr_t)tp.d;
+    const bool vec = (al & 15) == 0;
+#define FFVD_SGHMC(B, V) sghmc_kernel<B, V><<<grid, 256, 0, c->stream>>>(tt.d, tg.d, tn.d, txi.d, tgg.d, tg2.d, tp.d, n, epsilon, mdecay, eps_scaled)
+    if (burn_in) { if (vec) FFVD_SGHMC(1, 1); else FFVD_SGHMC(1, 0); }
+    else { if (vec) FFVD_SGHMC(0, 1); else FFVD_SGHMC(0, 0); }
+#undef FFVD_SGHMC
     c->launches++;
   }
   return call.finish();
@@ -998,7 +1002,9 @@ extern "C" int ffvd_adam_update(ffvd_ctx* c, DLManagedTensor* theta, DLManagedTe
     if (s.host == tt.host || s.host == tm.host || s.host == tv.host) s.is_out = true;
   if (n) {
     const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
-    adam_kernel<<<grid1d(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(tt.d, tg.d, tm.d, tv.d, n, lr_t, beta1, beta2, eps);
+    const bool vec = ((((uintptr_t)tt.d | (uintptr_t)tg.d | (uintptr_t)tm.d | (uintptr_t)tv.d)) & 15) == 0;
+    if (vec) adam_kernel<1><<<grid1d(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(tt.d, tg.d, tm.d, tv.d, n, lr_t, beta1, beta2, eps);
+    else adam_kernel<0><<<grid1d(n, 256, c->num_sms * 8), 256, 0, c->stream>>>(tt.d, tg.d, tm.d, tv.d, n, lr_t, beta1, beta2, eps);
     c->launches++;
   }
   return call.finish();

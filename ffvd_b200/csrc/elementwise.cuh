@@ -61,7 +61,24 @@ __global__ void logdensity_diag_kernel(const double* __restrict__ y, const doubl
 
 // base_model.py:150-179: adaptive SG-HMC, Jacobi semantics (all right-hand sides read pre-step state).
 // 12 streams/element in burn-in (7 reads + 5 writes = 96 B), 7 in sampling (5 R + 2 W = 56 B).
-template <int BURN_IN>
+__device__ __forceinline__ void sghmc_one(double& th, double gr, double nz, double& xio, double& go, double& g2o, double& po,
+                                          int burn_in, double eps2, double mdecay, double ns) {
+  const double Minv = 1.0 / (sqrt(g2o + 1e-16) + 1e-16);                 // :160 (old g2)
+  const double sigma = sqrt(fmax(ns * Minv, 1e-16));                      // :169-170
+  const double pt = po - eps2 * Minv * gr - mdecay * po + nz * sigma;     // :172
+  if (burn_in) {
+    const double r = 1.0 / (xio + 1.0);                                   // :156
+    const double gn = (1.0 - r) * go + r * gr;                            // :157
+    const double g2n = (1.0 - r) * g2o + r * gr * gr;                     // :158
+    xio = 1.0 + xio * (1.0 - go * go / (g2o + 1e-16));                    // :159
+    go = gn; g2o = g2n;
+  }
+  po = pt;
+  th = th + pt;                                                           // :173
+}
+
+// 16-byte accesses, two elements per thread and trip (VEC = 1; all pointers 16-byte aligned), scalar tail / fallback (VEC = 0).
+template <int BURN_IN, int VEC>
 __global__ void __launch_bounds__(256) sghmc_kernel(double* __restrict__ theta, const double* __restrict__ grad,
                                                     const double* __restrict__ noise, double* __restrict__ xi,
                                                     double* __restrict__ g, double* __restrict__ g2,
@@ -69,33 +86,58 @@ __global__ void __launch_bounds__(256) sghmc_kernel(double* __restrict__ theta, 
                                                     double eps_scaled) {
   const double eps2 = eps * eps;
   const double ns = 2.0 * eps_scaled * eps_scaled * mdecay;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const double gr = grad[i], g2o = g2[i], po = p[i], th = theta[i], nz = noise[i];
-    const double Minv = 1.0 / (sqrt(g2o + 1e-16) + 1e-16);                 // :160 (old g2)
-    const double sigma = sqrt(fmax(ns * Minv, 1e-16));                      // :169-170
-    const double pt = po - eps2 * Minv * gr - mdecay * po + nz * sigma;     // :172
-    if (BURN_IN) {
-      const double xio = xi[i], go = g[i];
-      const double r = 1.0 / (xio + 1.0);                                   // :156
-      g[i] = (1.0 - r) * go + r * gr;                                       // :157
-      g2[i] = (1.0 - r) * g2o + r * gr * gr;                                // :158
-      xi[i] = 1.0 + xio * (1.0 - go * go / (g2o + 1e-16));                  // :159
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    const size_t n2 = n / 2;
+    for (size_t i = i0; i < n2; i += stride) {
+      double2 th = reinterpret_cast<double2*>(theta)[i], po = reinterpret_cast<double2*>(p)[i], g2o = reinterpret_cast<double2*>(g2)[i];
+      const double2 gr = reinterpret_cast<const double2*>(grad)[i], nz = reinterpret_cast<const double2*>(noise)[i];
+      double2 xio = make_double2(0.0, 0.0), go = make_double2(0.0, 0.0);
+      if (BURN_IN) { xio = reinterpret_cast<double2*>(xi)[i]; go = reinterpret_cast<double2*>(g)[i]; }
+      sghmc_one(th.x, gr.x, nz.x, xio.x, go.x, g2o.x, po.x, BURN_IN, eps2, mdecay, ns);
+      sghmc_one(th.y, gr.y, nz.y, xio.y, go.y, g2o.y, po.y, BURN_IN, eps2, mdecay, ns);
+      if (BURN_IN) {
+        reinterpret_cast<double2*>(g)[i] = go; reinterpret_cast<double2*>(g2)[i] = g2o; reinterpret_cast<double2*>(xi)[i] = xio;
+      }
+      reinterpret_cast<double2*>(p)[i] = po;
+      reinterpret_cast<double2*>(theta)[i] = th;
     }
-    p[i] = pt;
-    theta[i] = th + pt;                                                     // :173
+  }
+  for (size_t i = (VEC ? 2 * (n / 2) : 0) + i0; i < n; i += stride) {
+    double th = theta[i], po = p[i], g2o = g2[i], xio = BURN_IN ? xi[i] : 0.0, go = BURN_IN ? g[i] : 0.0;
+    sghmc_one(th, grad[i], noise[i], xio, go, g2o, po, BURN_IN, eps2, mdecay, ns);
+    if (BURN_IN) { g[i] = go; g2[i] = g2o; xi[i] = xio; }
+    p[i] = po;
+    theta[i] = th;
   }
 }
 
-// TF1 AdamOptimizer apply (dgp_model.py:303-305): epsilon-hat form
+// TF1 AdamOptimizer apply (dgp_model.py:303-305): epsilon-hat form.  HBM-bound: 4 reads + 3 writes = 56 B / element;
+// VEC = 1 uses 16-byte accesses (all pointers 16-byte aligned), VEC = 0 is the scalar fallback / tail.
+__device__ __forceinline__ void adam_one(double& th, double gr, double& m, double& v, double lr_t, double b1, double b2, double eps) {
+  m = b1 * m + (1.0 - b1) * gr;
+  v = b2 * v + (1.0 - b2) * gr * gr;
+  th = th - lr_t * m / (sqrt(v) + eps);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256) adam_kernel(double* __restrict__ theta, const double* __restrict__ grad,
                                                    double* __restrict__ m, double* __restrict__ v, size_t n,
                                                    double lr_t, double b1, double b2, double eps) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const double gr = grad[i];
-    const double mt = b1 * m[i] + (1.0 - b1) * gr;
-    const double vt = b2 * v[i] + (1.0 - b2) * gr * gr;
-    m[i] = mt; v[i] = vt;
-    theta[i] = theta[i] - lr_t * mt / (sqrt(vt) + eps);
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    for (size_t i = i0; i < n / 2; i += stride) {
+      double2 th = reinterpret_cast<double2*>(theta)[i], mm = reinterpret_cast<double2*>(m)[i], vv = reinterpret_cast<double2*>(v)[i];
+      const double2 gr = reinterpret_cast<const double2*>(grad)[i];
+      adam_one(th.x, gr.x, mm.x, vv.x, lr_t, b1, b2, eps);
+      adam_one(th.y, gr.y, mm.y, vv.y, lr_t, b1, b2, eps);
+      reinterpret_cast<double2*>(m)[i] = mm; reinterpret_cast<double2*>(v)[i] = vv; reinterpret_cast<double2*>(theta)[i] = th;
+    }
+  }
+  for (size_t i = (VEC ? 2 * (n / 2) : 0) + i0; i < n; i += stride) {
+    double th = theta[i], mm = m[i], vv = v[i];
+    adam_one(th, grad[i], mm, vv, lr_t, b1, b2, eps);
+    m[i] = mm; v[i] = vv; theta[i] = th;
   }
 }
 
