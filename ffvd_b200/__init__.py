@@ -7,7 +7,7 @@ hand-written CUDA through the C ABI in include/ffvd_b200.h (ffvd_b200/_capi.py);
 CPU fallback.
 """
 from ._capi import (Context, FFVDError, NotPositiveDefinite, KERNEL_SE, KERNEL_LINEAR, FLAG_PRIOR_Z_NORMAL,
-                    FLAG_PRIOR_ONCE, FLAG_NO_GRADS, FLAG_ASYNC, FLAG_NO_SHARED_PRIORS, FLAG_NO_X0_PRIOR, LIB_PATH, load_library)
+                    FLAG_PRIOR_ONCE, FLAG_NO_GRADS, FLAG_ASYNC, FLAG_NO_SHARED_PRIORS, FLAG_NO_X0_PRIOR, FLAG_REUSE_KZZ, LIB_PATH, load_library)
 
 __all__ = ["Context", "FFVDError", "NotPositiveDefinite", "KERNEL_SE", "KERNEL_LINEAR", "FLAG_PRIOR_Z_NORMAL",
-           "FLAG_PRIOR_ONCE", "FLAG_NO_GRADS", "FLAG_ASYNC", "FLAG_NO_SHARED_PRIORS", "FLAG_NO_X0_PRIOR", "LIB_PATH", "load_library"]
+           "FLAG_PRIOR_ONCE", "FLAG_NO_GRADS", "FLAG_ASYNC", "FLAG_NO_SHARED_PRIORS", "FLAG_NO_X0_PRIOR", "FLAG_REUSE_KZZ", "LIB_PATH", "load_library"]

@@ -21,6 +21,7 @@ FLAG_PRIOR_Z_NORMAL = 1
 FLAG_PRIOR_ONCE = 2
 FLAG_NO_SHARED_PRIORS = 16
 FLAG_NO_X0_PRIOR = 32
+FLAG_REUSE_KZZ = 64
 FLAG_NO_GRADS = 4
 FLAG_ASYNC = 8
 

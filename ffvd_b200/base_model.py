@@ -44,7 +44,11 @@ class BaseModel(object):
         """One `session.run(burn_in_op | sample_op)`: a full nll+gradient evaluation followed by the
         elementwise update of every sampled variable (Jacobi semantics)."""
         import torch
-        out = self.evaluate()
+        from . import _capi
+        # Z and the kernel hyper-parameters are fixed across the 21 evaluations of a step unless they are sampled: the
+        # Cholesky factors of K(Z,Z) are then reused (FFVD_FLAG_REUSE_KZZ)
+        out = self.evaluate(_capi.FLAG_REUSE_KZZ if getattr(self, "_kzz_clean", False) else 0)
+        self._kzz_clean = not any(n in ("Z", "logv", "logl") for n in self.vars)
         for name in self.vars:
             th = self.params[name]
             st = self.sghmc_state[name]
@@ -53,6 +57,11 @@ class BaseModel(object):
             self.ctx.sghmc_update(th, out["g_" + name], nz.contiguous(), st["xi"], st["g"], st["g2"], st["p"],
                                   self.epsilon, self.mdecay, float(self.X_N), burn_in)
         return out
+
+    def invalidate_kzz(self):
+        """Call after changing Z or the kernel hyper-parameters from outside this class (the SG-HMC loop otherwise
+        re-uses the Cholesky factors of K(Z,Z) between evaluations that cannot have moved them)."""
+        self._kzz_clean = False
 
     def get_minibatch(self, global_step=1):
         # base_model.py:188-194: always the full batch; decayed Adam learning rate
@@ -84,6 +93,7 @@ class BaseModel(object):
         import torch
         _, lr = self.get_minibatch(self.global_step)
         saved = {}
+        self._kzz_clean = False                       # the window feed and the Adam step may move Z / hyper-parameters
         if self.window:
             i = np.random.randint(len(self.window)) if window_index is None else window_index
             for name, val in self.window[i].items():

@@ -49,6 +49,9 @@ struct ffvd_ctx {
   OutPtrs* d_outs = nullptr;
   double* kscr = nullptr;      // points into the arena (set by ensure_arena)
   // pools of the last collapsed evaluation (read by ffvd_collapse_u_mean right after it)
+  // Kzz factors of the last full preparation (FFVD_FLAG_REUSE_KZZ)
+  bool kzz_valid = false;
+  std::vector<long long> kzz_key;
   size_t last_off_cvec = 0, last_off_HxT = 0;
   int last_Mp = 0, last_nb = 0;
   int probs_cap = 0;
@@ -304,6 +307,7 @@ static int ensure_arena(ffvd_ctx* c, const Layout& L) {
   if (key != c->arena_key) {
     CUDA_TRY(cudaMemsetAsync(c->arena, 0, L.total, c->stream));   // padding of Linv etc. must be zero
     c->arena_key = key;
+    c->kzz_valid = false;
   }
   c->kscr = (double*)(c->arena + L.off_kscr);
   if (c->probs_cap < L.nprob) {
@@ -429,8 +433,15 @@ static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
 }
 
 template <int KIND>
-static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter) {
+static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse = false, long long ident = 0) {
   hyper_kernel<<<dim3(L.nk > L.D ? L.nk : L.D, L.nprob), 128, 0, c->stream>>>(c->d_probs, KIND, L.nk); c->launches++;
+  long long jbits;
+  memcpy(&jbits, &jitter, sizeof jbits);
+  std::vector<long long> key = c->arena_key;
+  key.push_back(KIND); key.push_back(jbits); key.push_back(ident);
+  if (reuse && c->kzz_valid && key == c->kzz_key) return FFVD_OK;     // factors of the previous call are still in the arena
+  c->kzz_valid = true;
+  c->kzz_key = key;
   if (KIND == 0) { zscale_kernel<<<dim3(L.nk, L.nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
   if (use_blocked(c, L.M, L.Mp)) {
     double* Lfac = (double*)(c->arena + L.off_Lfac);
@@ -621,7 +632,10 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     zero_gx_kernel<<<dim3(grid1d(maxn, 256, 64), nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
   }
 
-  TRY(launch_prep<KIND>(c, L, jitter));
+  long long ident = 1469598103934665603LL;      // FNV-1a over the addresses of Z / logv / logl of every problem: the factors in
+  for (auto& t : pt)                             // the arena belong to exactly these tensors
+    for (const double* q : {t.Z.d, t.logv.d, t.logl.d}) ident = (ident ^ (long long)(uintptr_t)q) * 1099511628211LL;
+  TRY(launch_prep<KIND>(c, L, jitter, (flags & FFVD_FLAG_REUSE_KZZ) != 0, ident));
   const int nz = nprob * nb;
   const BatchMap idm = {1, 1, 1};                // z -> z
   const BatchMap lmap = {nb, D, D};              // z -> (z / nb) * D + z % D
@@ -820,6 +834,7 @@ static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, co
   if (kind == FFVD_KERNEL_SE) TRY(launch_prep<0>(c, L, jitter));
   else if (kind == FFVD_KERNEL_LINEAR) TRY(launch_prep<1>(c, L, jitter));
   else return fail(FFVD_E_BADARG, "unknown kernel kind");
+  c->kzz_valid = false;           // operator-level calls do not take part in FFVD_FLAG_REUSE_KZZ
   return FFVD_OK;
 }
 

@@ -59,6 +59,11 @@ typedef struct DLManagedTensor {
 #define FFVD_FLAG_PRIOR_ONCE      2   /* count shared-parameter priors once instead of S times  */
 #define FFVD_FLAG_NO_GRADS        4   /* forward only: nll + terms                               */
 #define FFVD_FLAG_ASYNC           8   /* do not synchronise to read back the Cholesky status     */
+/* The caller asserts that Z, logv, logl, the kernel kind, the jitter and every shape are unchanged since the previous
+ * ffvd_nll_grads_* call on this context: K(Z,Z)'s Cholesky factor, L^{-1}, L^{-T} and the scaled inducing inputs are
+ * reused instead of recomputed (SG-HMC chains that sample only X / U evaluate 21 times per outer iteration with fixed Z
+ * and hyper-parameters, base_model.py:915-933).  Ignored when the context holds no factors for these shapes. */
+#define FFVD_FLAG_REUSE_KZZ       64
 /* time-sharded evaluation of ONE trajectory (ffvd_b200/distributed.py: a block of consecutive transitions per GPU):
  * every block is an ordinary problem whose nll / gradients are then rescaled by T_block / T_total by the caller */
 #define FFVD_FLAG_NO_SHARED_PRIORS 16 /* drop the priors on Z, U, kernel hypers, logQ, C, d, logR (blocks other than the first) */

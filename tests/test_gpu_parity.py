@@ -590,3 +590,48 @@ def test_prepared_call_sees_in_place_updates(env):
     ref = alloc_out(env, Ps[0]); ctx.nll_grads(0, False, Ps[0], ref); torch.cuda.synchronize()
     for k in ref:
         assert_close(ref[k].cpu().numpy(), Os[0][k].cpu().numpy(), 1e-10, k)
+
+
+def test_kzz_reuse_flag(env):
+    """FFVD_FLAG_REUSE_KZZ: with Z and the kernel hyper-parameters unchanged, skipping the Cholesky preparation gives the
+    same results; a changed Z pointer / shape falls back to a full preparation; a case-7 SG-HMC step (X, U sampled) with
+    reuse equals the same step without it."""
+    from oracle import fixtures
+    torch, ctx, F = env["torch"], env["ctx"], env["ffvd"]
+    prob = fixtures.synthetic_problem(T=120, M=90, D=3, S=2)
+    p = dev_problem(env, prob)
+    a, b = alloc_out(env, p), alloc_out(env, p)
+    ctx.nll_grads(0, False, p, a)
+    p["X"].mul_(0.97); p["U"].add_(0.05)                       # not Z / hypers
+    ctx.nll_grads(0, False, p, a, flags=F.FLAG_PRIOR_Z_NORMAL | F.FLAG_REUSE_KZZ)
+    ctx.nll_grads(0, False, p, b)
+    torch.cuda.synchronize()
+    for k in a:
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-10, k)
+    # a different Z tensor (new address) must not reuse the old factors even if the flag is set
+    p2 = dict(p); p2["Z"] = (p["Z"] * 1.1).contiguous()
+    ctx.nll_grads(0, False, p2, a, flags=F.FLAG_PRIOR_Z_NORMAL | F.FLAG_REUSE_KZZ)
+    ctx.nll_grads(0, False, p2, b)
+    torch.cuda.synchronize()
+    for k in a:
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-10, k)
+    # end to end: one case-7 sghmc_step with and without the reuse
+    fx = env["byname"]["drive/0"]
+    res = []
+    for reuse in (True, False):
+        m, _ = _model_from_problem(env, fx, 7, iterations=0)
+        model = m.fit(fx.Y)
+        rng = np.random.default_rng(9)
+        noises = [{n: rng.standard_normal(tuple(model.params[n].shape)) for n in model.vars} for _ in range(21)]
+        if not reuse:
+            model.invalidate_kzz()
+            orig = model._run_update
+            def no_reuse(burn_in, noise=None, _o=orig, _m=model):
+                _m.invalidate_kzz()
+                return _o(burn_in, noise)
+            model._run_update = no_reuse
+        model.sghmc_step(noise_fn=lambda k: noises[k])
+        res.append({n: model.params[n].cpu().numpy().copy() for n in model.vars})
+    assert sorted(res[0]) == ["U", "X"]
+    for n in res[0]:
+        assert_close(res[1][n], res[0][n], 1e-9, n)

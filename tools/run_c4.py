@@ -1,5 +1,5 @@
 """BASELINE config 4: all 95 Factnonlin_ini warm starts as ONE batched nll+gradient call (for ncu launch lists).
-usage: python tools/run_c4.py [collapsed] [reps]"""
+usage: python tools/run_c4.py [collapsed|x] [reps] [reuse]   (reuse: FFVD_FLAG_REUSE_KZZ, Z / hyper-parameters fixed)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -21,6 +21,8 @@ for prob in packed["problems"]:
         o["g_" + k] = torch.empty_like(p[k])
     Ps.append(p); Os.append(o)
 FL = ffvd_b200.FLAG_PRIOR_Z_NORMAL | ffvd_b200.FLAG_ASYNC
+if len(sys.argv) > 3 and sys.argv[3] == "reuse":
+    FL |= ffvd_b200.FLAG_REUSE_KZZ
 call = ctx.prepare_nll_grads(0, collapsed, Ps, Os, flags=FL)
 for _ in range(2):
     call.run()
@@ -36,4 +38,5 @@ for _ in range(reps):
     call.run()
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / reps * 1e3
+print("flags=%d " % FL, end="")
 print("95 chains, collapsed=%d: %.3f ms per batched evaluation (device), %.3f ms wall" % (collapsed, e0.elapsed_time(e1) / reps, wall))
