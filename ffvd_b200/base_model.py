@@ -45,6 +45,10 @@ class BaseModel(object):
         elementwise update of every sampled variable (Jacobi semantics)."""
         import torch
         from . import _capi
+        if not self.vars:
+            # cases 1, 4, 6: nothing is SG-HMC sampled, burn_in_op / sample_op are empty lists and session.run([]) evaluates
+            # nothing (SURVEY Q3) -- no nll evaluation here either
+            return None
         # Z and the kernel hyper-parameters are fixed across the 21 evaluations of a step unless they are sampled: the
         # Cholesky factors of K(Z,Z) are then reused (FFVD_FLAG_REUSE_KZZ)
         out = self.evaluate(_capi.FLAG_REUSE_KZZ if getattr(self, "_kzz_clean", False) else 0)

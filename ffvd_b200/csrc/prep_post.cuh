@@ -74,8 +74,56 @@ __device__ void tri_inverse(const double* L, int ldl, int M, double* X, double* 
   __syncthreads();
 }
 
+// Fast path for matrices small enough that L AND its inverse fit in shared memory (M <= ~116): X = L^{-1} by forward
+// substitution with ONE THREAD PER COLUMN (columns j and M-1-j paired for balance) -- no barrier and no global-memory
+// round trip inside the substitution (the generic routine above reads the rows of X it has just written back from
+// global memory, ~1 us per row step).  L: M x ldl shared; Xs: M x ldx shared (ldx even keeps the diagonal-stride reads of
+// neighbouring columns conflict free); dinv: M doubles.  Then X / X^T are written to the zero-padded global buffers.
+__device__ void tri_inverse_smem(const double* L, int ldl, int M, double* Xs, int ldx, double* dinv, double* X, double* XT, int Mp) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int i = tid; i < M; i += nth) dinv[i] = 1.0 / L[(size_t)i * ldl + i];
+  __syncthreads();
+  for (int t = tid; t < (M + 1) / 2; t += nth) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int j = half ? (M - 1 - t) : t;
+      if (half && j == t) break;
+      Xs[(size_t)j * ldx + j] = dinv[j];
+      for (int i = j + 1; i < M; ++i) {
+        const double* Li = L + (size_t)i * ldl;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = j;
+        for (; k + 3 < i; k += 4) {
+          s0 = fma(Li[k], Xs[(size_t)k * ldx + j], s0);
+          s1 = fma(Li[k + 1], Xs[(size_t)(k + 1) * ldx + j], s1);
+          s2 = fma(Li[k + 2], Xs[(size_t)(k + 2) * ldx + j], s2);
+          s3 = fma(Li[k + 3], Xs[(size_t)(k + 3) * ldx + j], s3);
+        }
+        for (; k < i; ++k) s0 = fma(Li[k], Xs[(size_t)k * ldx + j], s0);
+        Xs[(size_t)i * ldx + j] = -((s0 + s1) + (s2 + s3)) * dinv[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < M * M; idx += nth) {
+    const int r = idx / M, c = idx % M;
+    X[(size_t)r * Mp + c] = (c <= r) ? Xs[(size_t)r * ldx + c] : 0.0;
+  }
+  for (int idx = tid; idx < M * M; idx += nth) {
+    const int r = idx / M, c = idx % M;
+    XT[(size_t)r * Mp + c] = (c >= r) ? Xs[(size_t)c * ldx + r] : 0.0;
+  }
+  __syncthreads();
+}
+
+// shared-memory doubles of the fast path (0 = does not fit): L (M x (M+1)), X (M x ldx), three Mp vectors
+__host__ __device__ inline size_t chol_fast_smem_doubles(int M, int Mp) {
+  const int ldx = (M + 1) & ~1;
+  return (size_t)M * (M + 1) + (size_t)M * ldx + (size_t)3 * Mp;
+}
+
 // ---------------------------------------------------------------------------------------------
-// grid (D, nprob); block 512.  Dynamic smem: 2*Mp doubles (+ M*(M+1) when use_smem).
+// grid (D, nprob); block 512.  Dynamic smem: 2*Mp doubles (+ M*(M+1) when use_smem; chol_fast_smem_doubles when use_smem == 2).
 template <int KIND>
 __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restrict__ probs, double jitter, int use_smem) {
   extern __shared__ __align__(16) double sh[];
@@ -123,7 +171,12 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
   const int st = chol_inplace(A, lda, M, colbuf, &flag);
   if (tid == 0) P.status[d] = st;
   if (st != 0) return;
-  tri_inverse(A, lda, M, P.Linv + (size_t)d * Mp * Mp, Lt, Mp, rowbuf);
+  if (use_smem == 2) {
+    double* Xs = Asm + (size_t)M * (M + 1);
+    tri_inverse_smem(A, lda, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), P.Linv + (size_t)d * Mp * Mp, Lt, Mp);
+  } else {
+    tri_inverse(A, lda, M, P.Linv + (size_t)d * Mp * Mp, Lt, Mp, rowbuf);
+  }
 }
 
 // Blocked path (M too large for shared memory): fill K(Z,Z) + jitter I (lower triangle, identity on the
@@ -361,21 +414,23 @@ __global__ void __launch_bounds__(256) kzz_bwd_kernel(const DevProblem* __restri
 // grid (S*D, nprob); block 512; dynamic smem 2*Mp doubles.
 // Buffers: Sacc[b] holds the full symmetric S (already symmetrized); Wk[b] <- H then L_H;
 //          Hx[b] <- L_H^{-1}; HxT[b] <- L_H^{-T}.
-__global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* __restrict__ probs) {
+__global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* __restrict__ probs, int fast) {
   extern __shared__ __align__(16) double sh[];
   __shared__ int flag;
   const DevProblem& P = probs[blockIdx.y];
   const int b = blockIdx.x, d = b % P.D, s = b / P.D;
   const int M = P.M, Mp = P.Mp, tid = threadIdx.x, nth = blockDim.x;
   const double iq = exp(-P.logQ[d]);
-  double* H = P.Wk + (size_t)b * Mp * Mp;
   const double* S = P.Sacc + (size_t)b * Mp * Mp;
+  // fast: H, its factor and the inverse live in shared memory (sh: 2 Mp vectors, then H, then X, then dinv)
+  double* H = fast ? sh + 2 * Mp : P.Wk + (size_t)b * Mp * Mp;
+  const int ldh = fast ? M + 1 : Mp;
   for (int idx = tid; idx < M * M; idx += nth) {
     const int m = idx / M, n = idx % M;
-    H[(size_t)m * Mp + n] = S[(size_t)m * Mp + n] * iq + (m == n ? 1.0 : 0.0);
+    H[(size_t)m * ldh + n] = S[(size_t)m * Mp + n] * iq + (m == n ? 1.0 : 0.0);
   }
   __syncthreads();
-  const int st = chol_inplace(H, Mp, M, sh, &flag);
+  const int st = chol_inplace(H, ldh, M, sh, &flag);
   if (st != 0) {
     if (tid == 0) P.status[d] = st;
     return;
@@ -383,13 +438,18 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
   // -1/2 logdet H = -sum log L_ii
   if (tid < 32) {
     double t = 0.0;
-    for (int i = tid; i < M; i += 32) t += log(H[(size_t)i * Mp + i]);
+    for (int i = tid; i < M; i += 32) t += log(H[(size_t)i * ldh + i]);
     t = warp_sum(t);
     if (tid == 0) red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -t);
   }
   double* X = P.Hx + (size_t)b * Mp * Mp;
   double* XT = P.HxT + (size_t)b * Mp * Mp;
-  tri_inverse(H, Mp, M, X, XT, Mp, sh + Mp);
+  if (fast) {
+    double* Xs = H + (size_t)M * (M + 1);
+    tri_inverse_smem(H, ldh, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), X, XT, Mp);
+  } else {
+    tri_inverse(H, Mp, M, X, XT, Mp, sh + Mp);
+  }
 }
 
 // SE: per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded) and, in row Din, -1/2 |z~_m|^2 -- the
