@@ -327,9 +327,16 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
                                            int warp, int lane) {
   const int nt = Mp >> 5;
   const int nfull = nt * (nt - 1) / 2, nunits = nfull + nt;
-  for (int i = 0;; ++i) {
+  // units of this warp: i = 0 .. nu-1 with u(i) = i NW + (i odd ? NW-1-warp : warp) < nunits
+  int nu = 0;
+  while (nu * NW + ((nu & 1) ? (NW - 1 - warp) : warp) < nunits) ++nu;
+  // The two warps that share an SM sub-partition (w and w+4) walk their lists in opposite directions: one starts with
+  // full tiles, the other with its (shorter) diagonal tiles, so their flushes -- during which a warp issues no DMMA --
+  // do not coincide and the partner keeps the tensor pipe busy.
+  const bool rev = (warp & 4) != 0;
+  for (int ii = 0; ii < nu; ++ii) {
+    const int i = rev ? nu - 1 - ii : ii;
     const int u = i * NW + ((i & 1) ? (NW - 1 - warp) : warp);
-    if (u >= nunits) break;
     if (u < nfull) {
       // decode (ti > tj) from the linear strictly-lower index u = ti(ti-1)/2 + tj
       int ti = (int)((sqrtf(8.0f * (float)u + 1.0f) + 1.0f) * 0.5f);
