@@ -80,6 +80,7 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_kernel_Kdiag.argtypes = [vp, ci, vp, vp, vp, vp]
     lib.ffvd_kernel_pre_cal.argtypes = [vp, ci, vp, vp, vp, cd, vp]
     lib.ffvd_conditional.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, vp, vp]
+    lib.ffvd_conditional_ex.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, ci, vp, vp]
     lib.ffvd_collapse_u_mean.argtypes = [vp, ci, ctypes.POINTER(_Problem), cd, vp, vp]
     lib.ffvd_logdensity_norm_diag.argtypes = [vp, vp, vp, vp, ci, vp]
     lib.ffvd_nll_grads_uncollapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
@@ -90,7 +91,7 @@ def load_library() -> ctypes.CDLL:
     for name in ("ffvd_ctx_create", "ffvd_ctx_destroy", "ffvd_ctx_synchronize", "ffvd_kernel_K", "ffvd_kernel_Kdiag",
                  "ffvd_kernel_pre_cal", "ffvd_conditional", "ffvd_logdensity_norm_diag", "ffvd_nll_grads_uncollapsed",
                  "ffvd_nll_grads_collapsed", "ffvd_nll_grads_batched", "ffvd_sghmc_update", "ffvd_adam_update",
-                 "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks"):
+                 "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks", "ffvd_conditional_ex"):
         getattr(lib, name).restype = ci
     _lib = lib
     return lib
@@ -230,12 +231,12 @@ class Context:
             b.release()
         return out
 
-    def conditional(self, kind, shared_kernel, Xnew, Z, logv, logl, f, q_sqrt, white, full_cov, jitter, mean_out, var_out):
+    def conditional(self, kind, shared_kernel, Xnew, Z, logv, logl, f, q_sqrt, white, full_cov, jitter, mean_out, var_out, flags=0):
         b = _Borrow()
         try:
-            _check(self._lib.ffvd_conditional(self._h, kind, int(bool(shared_kernel)), b.ptr(Xnew), b.ptr(Z), b.ptr(logv),
-                                              b.ptr(logl), b.ptr(f), b.ptr(q_sqrt), int(bool(white)), int(bool(full_cov)),
-                                              float(jitter), b.ptr(mean_out), b.ptr(var_out)))
+            _check(self._lib.ffvd_conditional_ex(self._h, kind, int(bool(shared_kernel)), b.ptr(Xnew), b.ptr(Z), b.ptr(logv),
+                                                 b.ptr(logl), b.ptr(f), b.ptr(q_sqrt), int(bool(white)), int(bool(full_cov)),
+                                                 float(jitter), int(flags), b.ptr(mean_out), b.ptr(var_out)))
         finally:
             b.release()
         return mean_out, var_out

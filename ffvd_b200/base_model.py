@@ -1,8 +1,7 @@
 """Mirror of the hot-path part of `vfegpssm/base_model.py`: the adaptive SG-HMC update
 (`generate_update_step`, :143-179), its schedule (`sghmc_step`, :915-933), `get_minibatch`
 (:188-194), the Adam step (`train_hypers`, :944-950) and the posterior roll-out / results file of
-`collect_samples_formal` (:197-522).  The particle-Gibbs methods of the reference class are out of scope
-(SURVEY 2.1)."""
+`collect_samples_formal` (:197-522) and the particle-Gibbs sweep for X (`PG_for_X`, :29-75)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
@@ -218,3 +217,76 @@ class BaseModel(object):
                                 running_time_seq=running_time_seq, PG_num=PG_num,
                                 mc_posterior_samples=np.asarray(mc_posterior_samples, dtype=object) if sghmc_var_len else [])
         return self.predict_y, self.predict_y_var
+
+    # ---- base_model.py:29-75 / 78-138
+    def PG_for_X(self, control_inputs, PG_particles, normals=None, eps=None, uniforms=None, assign=True):
+        """Conditional SMC (particle Gibbs) sweep over the latent trajectory, `base_model.py:29-75`: PG_particles - 1 free
+        particles plus the current trajectory as the reference particle; per time step one N = P-1 prediction-time
+        conditional (factors of K(Z,Z) computed once, `kernel_pre_cal`), Gaussian emission weights, multinomial resampling;
+        the returned / assigned trajectory is drawn from the final weights.  Trajectories are kept as per-step states and
+        ancestor indices and traced back at the end (the reference gathers whole trajectories at every step: same result).
+        `normals` (P-1,D), `eps` (T,P-1,D), `uniforms` (T,P-1) inject the randomness (the reference draws unseeded).
+        NB the reference's graph-mode `PG_for_X_speedup` (:78-138), the variant its driver wires up, never executes its
+        assign (the op returned to `session.run` is `tf.ones(1)`) and drops its TensorArray writes: what is mirrored here
+        is the algorithm those two methods describe."""
+        import torch
+        from . import conditionals_multi_output as cmo
+        dev = self.device
+        t64 = lambda a: a.to(dtype=torch.float64, device=dev) if torch.is_tensor(a) else torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
+        X = self.params["X"]
+        if X.dim() != 2:
+            raise NotImplementedError("PG_for_X works on one trajectory")
+        T, D = X.shape[0] - 1, X.shape[1]
+        P1 = int(PG_particles) - 1
+        ctrl = t64(control_inputs) if control_inputs is not None else torch.zeros((T, 0), dtype=torch.float64, device=dev)
+        n_ctrl = ctrl.shape[1] if ctrl.dim() == 2 else 0
+        normals = torch.randn((P1, D), dtype=torch.float64, device=dev) if normals is None else t64(normals)
+        eps = torch.randn((T, P1, D), dtype=torch.float64, device=dev) if eps is None else t64(eps)
+        uniforms = torch.rand((T, P1), dtype=torch.float64, device=dev) if uniforms is None else t64(uniforms)
+        kern = self.kernels[-1]
+        Z, U, C, dvec = self.params["Z"], self.params["U"], self.params["C"], self.params["d"]
+        R = self.params["logR"].exp().reshape(-1)            # Dy == 1 in all bundled data: diagonal factor
+        logR = self.params["logR"].reshape(-1).sum()
+        Qv = self.log_Q.exp()
+        Y = self.data["Y"]
+        factors = cmo.kernel_pre_cal(Z, kern)                  # once per sweep (:36)
+        states = torch.empty((T + 1, P1 + 1, D), dtype=torch.float64, device=dev)
+        states[0, :P1] = normals
+        states[:, P1] = X                                      # reference particle
+        anc = torch.empty((max(T - 1, 0), P1), dtype=torch.long, device=dev)
+        x_t = normals
+
+        def sample(logits, u):
+            cdf = torch.cumsum(torch.softmax(logits, dim=0), dim=0)
+            return torch.clamp(torch.searchsorted(cdf, u.reshape(-1).contiguous()), max=logits.shape[0] - 1)
+
+        last = None
+        for tt in range(T):
+            xc = torch.cat((x_t, ctrl[tt][None, :].expand(P1, n_ctrl)), dim=1).contiguous() if n_ctrl > 0 else x_t.contiguous()
+            mu, var = cmo.conditional_after_kernel_precalculation(factors, xc, Z, kern, U, white=True, full_cov=False)
+            x_next = mu + x_t + eps[tt] * torch.sqrt(var + Qv)
+            states[tt + 1, :P1] = x_next
+            res = (Y[tt][None, :] - (states[tt + 1] @ C + dvec)) / R           # (P, Dy); likelihoods.py:114-127
+            logits = -0.5 * (res * res).sum(dim=1) - logR
+            if tt < T - 1:
+                idx = sample(logits, uniforms[tt])
+                anc[tt] = idx
+                x_t = states[tt + 1][idx]
+            else:
+                last = sample(logits, uniforms[tt][:1])[0]
+        # trace the chosen particle back through its ancestors
+        path = torch.empty((T + 1, D), dtype=torch.float64, device=dev)
+        k = last
+        path[T] = states[T, k]
+        for tt in range(T - 1, -1, -1):
+            # slot k at time tt+1 (free slots only) descends from anc[tt-1][k] at time tt; the reference slot from itself
+            if tt >= 1:
+                k = torch.where(k < P1, anc[tt - 1][torch.clamp(k, max=P1 - 1)], k)
+            path[tt] = states[tt, k]
+        if assign:
+            X.copy_(path)
+        return path
+
+    def gp_x_sampling(self):
+        """`base_model.py:936-942`."""
+        return self.PG_for_X(self.data.get("ctrl"), getattr(self, "PG_particles", 100))

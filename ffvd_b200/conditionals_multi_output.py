@@ -74,7 +74,20 @@ def conditional_after_kernel_precalculation(Lm_inverse_seq, Xnew, Z, kern, f, *,
         raise NotImplementedError("conditional_after_kernel_precalculation: white=False is marked broken in the reference (cmo:359-362)")
     if return_Lm:
         raise ValueError("too many values to unpack (expected 2)")      # cmo:317, same unpack as Q8
-    return conditional(Xnew, Z, kern, f, full_cov=full_cov, q_sqrt=q_sqrt, white=True)
+    st = getattr(Lm_inverse_seq, "stacked", None)
+    if st is None or full_cov or not is_torch(Xnew) or not is_torch(st[1]):
+        return conditional(Xnew, Z, kern, f, full_cov=full_cov, q_sqrt=q_sqrt, white=True)
+    # factors precalculated by kernel_pre_cal on this device: same Z / hyper tensors, Cholesky preparation skipped
+    kind, Zs, logv, logl = st
+    Xnew, f = as_f64(Xnew), to_lib(Xnew, as_f64(f))
+    Xs = Xnew[..., : kern[0].input_dim]
+    Xs = Xs.contiguous()
+    q = None if q_sqrt is None else _q_sqrt_first_output(q_sqrt, Xnew, len(kern))
+    mean = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
+    var = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
+    context_for(Xnew).conditional(kind, False, Xs, Zs, logv, logl, f, q, True, False, JITTER, mean, var,
+                                  flags=_capi.FLAG_REUSE_KZZ | _capi.FLAG_ASYNC)
+    return mean, var
 
 
 def collapse_u_mean_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q):
@@ -101,6 +114,14 @@ def collapse_u_mean_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z,
     return U_mean[None, :, :], Linv
 
 
+class PrecalculatedFactors(list):
+    """What `kernel_pre_cal` returns: the list of D matrices L_d^{-T} (the reference's `Lm_inverse_seq`), plus the
+    stacked tensors the factors were computed from.  Passing it to `conditional_after_kernel_precalculation` tells the
+    library that Z and the kernel hyper-parameters are those very tensors, so the Cholesky factors still held by the
+    context are reused (FFVD_FLAG_REUSE_KZZ) instead of recomputed at every time step of a roll-out / particle sweep."""
+    stacked = None        # (kind, Z, logv, logl)
+
+
 def kernel_pre_cal(X, kern):
     """`conditionals_multi_output.py:124-169`: list of D matrices L_d^{-T}, L_d = chol(K_d(X)+1e-5 I)."""
     X = as_f64(X)
@@ -108,7 +129,9 @@ def kernel_pre_cal(X, kern):
     M = X.shape[0]
     out = empty_like_lib(X, (len(kern), M, M))
     context_for(X).kernel_pre_cal(kind, X, logv, logl, JITTER, out)
-    return [out[d] for d in range(len(kern))]
+    res = PrecalculatedFactors(out[d] for d in range(len(kern)))
+    res.stacked = (kind, X, logv, logl)
+    return res
 
 
 def collapse_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q, batch_size, Y_N):

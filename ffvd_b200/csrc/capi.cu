@@ -825,7 +825,7 @@ extern "C" int ffvd_kernel_Kdiag(ffvd_ctx* c, int kind, DLManagedTensor* X, DLMa
 
 // shared prep for kernel_pre_cal / conditional: one DevProblem with only the Z-side fields.
 static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, const Tens& tl, int nk, int R, double jitter,
-                       Layout& L, DevProblem& P, bool need_scratch = false) {
+                       Layout& L, DevProblem& P, bool need_scratch = false, bool reuse = false) {
   const int M = (int)tZ.shape[0], Din = (int)tZ.shape[1];
   if (Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
   const int Mp = pad_M(M);
@@ -839,10 +839,12 @@ static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, co
   bind_problem(c, L, 0, 0, P);
   CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
-  if (kind == FFVD_KERNEL_SE) TRY(launch_prep<0>(c, L, jitter));
-  else if (kind == FFVD_KERNEL_LINEAR) TRY(launch_prep<1>(c, L, jitter));
+  long long ident = 1469598103934665603LL;
+  for (const double* q : {tZ.d, tv.d, tl.d}) ident = (ident ^ (long long)(uintptr_t)q) * 1099511628211LL;
+  if (tZ.staged || tv.staged || tl.staged) reuse = false;      // staged host tensors get fresh device copies every call
+  if (kind == FFVD_KERNEL_SE) TRY(launch_prep<0>(c, L, jitter, reuse, ident));
+  else if (kind == FFVD_KERNEL_LINEAR) TRY(launch_prep<1>(c, L, jitter, reuse, ident));
   else return fail(FFVD_E_BADARG, "unknown kernel kind");
-  c->kzz_valid = false;           // operator-level calls do not take part in FFVD_FLAG_REUSE_KZZ
   return FFVD_OK;
 }
 
@@ -887,9 +889,21 @@ __global__ void unwhiten_kernel(const DevProblem* __restrict__ probs, const doub
   }
 }
 
+extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                                   DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
+                                   int white, int full_cov, double jitter, int flags, DLManagedTensor* mean_out,
+                                   DLManagedTensor* var_out);
+
 extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
                                 DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
                                 int white, int full_cov, double jitter, DLManagedTensor* mean_out, DLManagedTensor* var_out) {
+  return ffvd_conditional_ex(c, kind, shared_kernel, Xnew, Z, logv, logl, f, q_sqrt, white, full_cov, jitter, 0, mean_out, var_out);
+}
+
+extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                                   DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
+                                   int white, int full_cov, double jitter, int flags, DLManagedTensor* mean_out,
+                                   DLManagedTensor* var_out) {
   if (!c) return fail(FFVD_E_BADARG, "ctx is null");
   if (full_cov) return fail(FFVD_E_UNSUPPORTED, "conditional: full_cov=True (N x N covariances) is not built; the reference driver "
                                                 "runs with full_cov=False (FFVD_Main.py:267)");
@@ -914,7 +928,7 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
   if (tm.numel != (size_t)N * R || tvar.numel != (size_t)N * R) return fail(FFVD_E_SHAPE, "mean/var must be (N,R)");
   if (N == 0) return call.finish();
   Layout L; DevProblem P;
-  TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P, tq.present && tq.ndim == 3));
+  TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P, tq.present && tq.ndim == 3, (flags & FFVD_FLAG_REUSE_KZZ) != 0));
   const int RB = rb_of(P.Mp), BT = 8 * RB;
   P.hs = shared_kernel ? 0 : 1;
   P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;
@@ -950,7 +964,8 @@ extern "C" int ffvd_conditional(ffvd_ctx* c, int kind, int shared_kernel, DLMana
   hyper_kernel<<<dim3(nk > R ? nk : R, 1), 128, 0, c->stream>>>(c->d_probs, kind, nk); c->launches++;
   if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   else TRY((launch_fused<1, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
-  int st = check_status(c, L);
+  int st = FFVD_OK;
+  if (!(flags & FFVD_FLAG_ASYNC)) st = check_status(c, L);
   TRY(call.finish());
   return st;
 }

@@ -84,6 +84,7 @@ class DGPSSM(BaseModel):
         import torch
         self.x_dims, self.n_inducing, self.kernels, self.likelihood = x_dims, n_inducing, kernels, likelihood
         self.window_size = window_size
+        self.PG_particles = PG_particles
         self.output_dim = output_dim or x_dims[-1]
         self.U_collapse = bool(U_collapse)
         self.prior_type = prior_type

@@ -1,7 +1,7 @@
 """Mirror of `vfegpssm/models.py`: `Model` / `RegressionModel` -- argument holder, model construction (:47-74) and the
 outer training loop (:142-168: per iteration one `sghmc_step` (21 nll+gradient evaluations) and one Adam
-`train_hypers` step).  TensorBoard summaries, timing hooks and the particle-Gibbs branch of the reference loop are
-out of scope."""
+`train_hypers` step, plus a particle-Gibbs sweep over X in case 6).  TensorBoard summaries and timing hooks of the
+reference loop are out of scope."""
 from __future__ import annotations
 
 import numpy as np
@@ -64,8 +64,6 @@ class Model(object):
                                 hyperparameter_sampling=A.hyperparameter_sampling, kernel_optimization=A.kernel_optimization,
                                 U_optimization=A.U_optimization, U_collapse=A.U_collapse, Z_optimization=A.Z_optimization,
                                 case_val=A.case_val, **kwargs)
-        if A.X_PG:
-            raise NotImplementedError("the particle-Gibbs X sampler (case 6, base_model.py:78-138) is out of scope (SURVEY 8f rank 4)")
         self.nll_seq, self.rmse_seq, self.ll_seq, self.running_time_seq = [], [], [], []
         it = 0
         while it < 2 * A.iterations:                  # models.py:142-168
@@ -73,6 +71,8 @@ class Model(object):
             self.global_step += 1
             self.model.global_step = self.global_step
             self.model.sghmc_step()
+            if A.X_PG:                                # case 6: models.py:155-158
+                self.model.gp_x_sampling()
             if self.model.trainable:                  # hasattr(self.model, 'hyper_train_op')
                 self.model.train_hypers()
             if progress is not None and it % 100 == 0:

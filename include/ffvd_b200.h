@@ -131,6 +131,16 @@ int ffvd_conditional(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor* Xn
                      DLManagedTensor* q_sqrt, int white, int full_cov, double jitter,
                      DLManagedTensor* mean_out, DLManagedTensor* var_out);
 
+/* The same with flags: FFVD_FLAG_REUSE_KZZ -- the caller asserts that Z, logv, logl (same tensors), kind, jitter and
+ * shapes are those of the previous ffvd_conditional* / ffvd_kernel_pre_cal call on this context, whose factors are then
+ * reused: this is what passing `Lm_inverse_seq` to conditional_after_kernel_precalculation means in the reference
+ * (kernel_pre_cal once, then one conditional per time step: base_model.py:36,49,210,289); FFVD_FLAG_ASYNC skips the
+ * read-back of the Cholesky status. */
+int ffvd_conditional_ex(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                        DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f,
+                        DLManagedTensor* q_sqrt, int white, int full_cov, double jitter, int flags,
+                        DLManagedTensor* mean_out, DLManagedTensor* var_out);
+
 /* conditionals_multi_output.py:206-227 collapse_u_mean_after_kernel_precalculation: the optimal
  * collapsed q(u).  Per sample s and output d: F = K(Xc,Z) L^{-T}, H = F^T F / Q_d + I,
  * U_mean_out[s,:,d] = H^{-1} F^T (x_{1:T,d} - x_{0:T-1,d}) / Q_d   (S,M,D) [(M,D) for 2-d X],

@@ -282,6 +282,44 @@ def rollout(Lm_inverse_seq, x_last, ctrl_future, Z, kern, U_val, q_sqrt, Q, nois
     return torch.stack(xs), torch.stack(vs)
 
 
+def categorical_from_uniform(logits, u):
+    """Categorical(logits).sample with the randomness injected: inverse CDF of softmax(logits) at u in [0,1)."""
+    p = torch.softmax(logits, dim=0)
+    cdf = torch.cumsum(p, dim=0)
+    return torch.clamp(torch.searchsorted(cdf, u.reshape(-1)), max=logits.shape[0] - 1)
+
+
+def pg_for_x(X, Y, ctrl, Z, kern, U, Q, C, d, Rchols, PG_particles, normals, eps, uniforms):
+    """The conditional-SMC (particle Gibbs) sweep of `base_model.py:29-75` (PG_for_X), literally: particles are WHOLE
+    trajectories, gathered on resampling; the last particle is the current trajectory X.  Randomness injected:
+    normals (P-1,D) initial states, eps (T,P-1,D) transition noise, uniforms (T,P-1) resampling draws (row T-1, entry 0
+    picks the returned trajectory).  Returns the new trajectory (T+1,D)."""
+    P1 = PG_particles - 1
+    T = X.shape[0] - 1
+    Linv = kernel_pre_cal(Z, kern)
+    particles = [normals[i][None, :] for i in range(P1)]
+    particles.append(X[0][None, :])
+    for tt in range(T):
+        x_t = torch.stack([p[-1] for p in particles[:-1]])
+        xc = torch.cat((x_t, ctrl[tt] * torch.ones((P1, 1), dtype=DT)), dim=1) if ctrl.shape[1] > 0 else x_t
+        mu, var = conditional_after_kernel_precalculation(Linv, xc, Z, kern, U, white=True, full_cov=False)
+        mu = mu + x_t
+        x_next = mu + eps[tt] * torch.sqrt(var + Q)
+        for i in range(P1):
+            particles[i] = torch.cat((particles[i], x_next[i][None, :]), dim=0)
+        w = list(torch.unbind(logdensity_norm(Y[tt], x_next @ C + d, Rchols)))
+        w.append(logdensity_norm(Y[tt], X[tt + 1][None, :] @ C + d, Rchols)[0])
+        particles[-1] = X[:tt + 2]
+        logits = torch.stack(w)
+        if tt < T - 1:
+            idx = categorical_from_uniform(logits, uniforms[tt])
+            particles = [particles[int(i)] for i in idx]
+            particles.append(X[:tt + 2])
+        else:
+            idx = categorical_from_uniform(logits, uniforms[tt][:1])
+            return particles[int(idx[0])]
+
+
 def collapse_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q, batch_size, Y_N):
     """`conditionals_multi_output.py:230-257`: the three collapsed-bound terms."""
     term1 = 0.0

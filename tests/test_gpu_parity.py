@@ -635,3 +635,33 @@ def test_kzz_reuse_flag(env):
     assert sorted(res[0]) == ["U", "X"]
     for n in res[0]:
         assert_close(res[1][n], res[0][n], 1e-9, n)
+
+
+def test_particle_gibbs_sweep(env):
+    """PG_for_X (base_model.py:29-75): the conditional-SMC sweep with injected randomness against the
+    oracle's literal restatement (whole trajectories gathered at every resampling)."""
+    import torch as th
+    from oracle import ffvd_oracle as O
+    prob = env["byname"]["gas_furnace/0"]
+    T, D = prob.Y.shape[0], prob.X.shape[1]
+    m, ctrl = _model_from_problem(env, prob, 6, iterations=0)
+    model = m.fit(prob.Y)
+    P = 12
+    rng = np.random.default_rng(21)
+    normals, eps, uni = rng.standard_normal((P - 1, D)), rng.standard_normal((T, P - 1, D)), rng.random((T, P - 1))
+    path = model.PG_for_X(prob.ctrl, P, normals=normals, eps=eps, uniforms=uni, assign=False).cpu().numpy()
+    tt = th.as_tensor
+    ok = O._make_kernels(tt(prob.logv), tt(prob.logl), 0, prob.Z.shape[1])
+    ref = O.pg_for_x(tt(prob.X), tt(prob.Y), tt(prob.ctrl), tt(prob.Z), ok, tt(prob.U), tt(np.exp(prob.logQ)), tt(prob.C), tt(prob.d),
+                     tt(np.exp(prob.logR)), P, tt(normals), tt(eps), tt(uni)).numpy()
+    assert path.shape == ref.shape == (T + 1, D)
+    assert_close(ref, path, 1e-8)
+    # the sweep must be able to return the reference trajectory itself and free particles alike: with all the resampling
+    # mass forced onto the last candidate (u -> 1) the reference particle survives everywhere
+    same = model.PG_for_X(prob.ctrl, P, normals=normals, eps=eps, uniforms=np.full((T, P - 1), 1.0 - 1e-12), assign=False)
+    assert_close(prob.X, same.cpu().numpy(), 1e-15)
+    # case 6 outer loop runs: sghmc_step (nothing sampled) + PG sweep + Adam
+    m6, _ = _model_from_problem(env, prob, 6, iterations=1)
+    m6.ARGS.PG_particles = 8
+    mod6 = m6.fit(prob.Y)
+    assert np.isfinite(float(mod6.nll))
