@@ -158,13 +158,16 @@ class BaseModel(object):
         def roll(x_t, U_val, q_sqrt, eps):
             """x_t (n,D), eps (n,L,D) -> states (n,L,D), variances (n,L,D)"""
             xs, vs = [], []
+            # pre-calculate the Cholesky decomposition of the kernel matrix (:209, :235): one factorisation per roll-out,
+            # reused by the L per-step conditionals
+            factors = cmo.kernel_pre_cal(self.params["Z"], kern)
             for t in range(L):
                 if n_ctrl > 0:
                     c = ctrl_all[t + T_train][None, :].expand(x_t.shape[0], n_ctrl)
                     xc = torch.cat((x_t, c), dim=1).contiguous()
                 else:
                     xc = x_t.contiguous()
-                mu, var = cmo.conditional_after_kernel_precalculation(None, xc, self.params["Z"], kern, U_val, white=True,
+                mu, var = cmo.conditional_after_kernel_precalculation(factors, xc, self.params["Z"], kern, U_val, white=True,
                                                                       full_cov=False, q_sqrt=q_sqrt)
                 x_next = mu + x_t + eps[:, t] * torch.sqrt(var + Qv)
                 xs.append(x_next)
