@@ -10,6 +10,17 @@ from oracle import fixtures
 collapsed = len(sys.argv) > 1 and sys.argv[1] == "collapsed"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device("cuda:0")
+
+
+def warm_clocks(seconds=1.0):
+    """sub-millisecond timings are meaningless on a GPU that has not left its idle clocks"""
+    import time as _t
+    a = torch.randn(4096, 4096, device=dev)
+    t0 = _t.perf_counter()
+    while _t.perf_counter() - t0 < seconds:
+        (a @ a).sum().item()
+
+
 ctx = ffvd_b200.Context(0, torch.cuda.current_stream(0).cuda_stream)
 packed = fixtures.load_packed()
 KEYS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR", "Y", "ctrl")
@@ -24,7 +35,8 @@ FL = ffvd_b200.FLAG_PRIOR_Z_NORMAL | ffvd_b200.FLAG_ASYNC
 if len(sys.argv) > 3 and sys.argv[3] == "reuse":
     FL |= ffvd_b200.FLAG_REUSE_KZZ
 call = ctx.prepare_nll_grads(0, collapsed, Ps, Os, flags=FL)
-for _ in range(2):
+warm_clocks()
+for _ in range(5):
     call.run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
