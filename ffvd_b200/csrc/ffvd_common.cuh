@@ -126,6 +126,19 @@ __device__ __forceinline__ double2 ldg_stream2(const double* p) {
   return v;
 }
 
+// 32-byte (256-bit) global accesses, sm_100a LDG/STG.E.256: one lane moves four consecutive doubles, so the four lanes
+// that own a 16-column group of a tile row write / read one full 128-byte line (two 16-byte accesses per lane leave every
+// 32-byte sector half written per instruction).  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(__cvta_generic_to_global(p)), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const double* p, double2& lo, double2& hi) {
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(lo.x), "=d"(lo.y), "=d"(hi.x), "=d"(hi.y) : "l"(__cvta_generic_to_global(p)));
+}
+__device__ __forceinline__ void ldg256_cg(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(__cvta_generic_to_global(p)));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -66,13 +66,11 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
     for (int u = 0; u < RING; ++u) {
       ring[u][0] = ring[u][1] = make_double2(0.0, 0.0);
       if (u < Din) {
-        ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)u * Mp + jb));
-        ring[u][1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)u * Mp + jb + 2));
+        ldg256_nc(ZTd + (size_t)u * Mp + jb, ring[u][0], ring[u][1]);
       }
     }
     if (KIND == 0) {
-      hz[0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)Din * Mp + jb));
-      hz[1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)Din * Mp + jb + 2));
+      ldg256_nc(ZTd + (size_t)Din * Mp + jb, hz[0], hz[1]);
     }
   };
   prologue(16 * group_index(wc, 0) + 4 * q);
@@ -90,15 +88,14 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
         for (int c = 0; c < 4; ++c) s[rb][c] = (KIND == 0) ? hx + h[c] : 0.0;
       }
     }
-    for (int j0 = 0; j0 < Din; j0 += RING) {
+    for (int j0 = 0; j0 < (FFVD_ABLATE == 6 ? 0 : Din); j0 += RING) {
 #pragma unroll
       for (int u = 0; u < RING; ++u) {
         const int jd = j0 + u;
         if (jd < Din) {
           const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
           if (jd + RING < Din) {
-            ring[u][0] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + RING) * Mp + jb));
-            ring[u][1] = __ldg(reinterpret_cast<const double2*>(ZTd + (size_t)(jd + RING) * Mp + jb + 2));
+            ldg256_nc(ZTd + (size_t)(jd + RING) * Mp + jb, ring[u][0], ring[u][1]);
           }
 #pragma unroll
           for (int rb = 0; rb < RB; ++rb) {
@@ -122,7 +119,9 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
       for (int i = 0; i < RBB; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) kv[4 * i + c] = s[rb0 + i][c];
+#if FFVD_ABLATE != 5
       if (KIND == 0) exp_nonpos_n<RBB * 4>(kv);
+#endif
 #pragma unroll
       for (int i = 0; i < RBB; ++i) {
         const int row = row0 + 8 * (rb0 + i) + g;
@@ -131,11 +130,7 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
         double* p = sm.tile + row * lda + jb;
         *reinterpret_cast<double2*>(p) = make_double2(kv[4 * i], kv[4 * i + 1]);
         *reinterpret_cast<double2*>(p + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
-        if (SCR) {
-          double* sp = kscr + (size_t)row * Mp + jb;
-          *reinterpret_cast<double2*>(sp) = make_double2(kv[4 * i], kv[4 * i + 1]);
-          *reinterpret_cast<double2*>(sp + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
-        }
+        if (SCR && FFVD_ABLATE != 4) stg256(kscr + (size_t)row * Mp + jb, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
       }
     }
   }
@@ -1010,10 +1005,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             } else {
 #pragma unroll
               for (int rb = 0; rb < RBW; ++rb) {
-                const double* s = kscr + (size_t)(row0 + 8 * rb + g) * Mp + jb;
-                const double2 k01 = __ldcg(reinterpret_cast<const double2*>(s));
-                const double2 k23 = __ldcg(reinterpret_cast<const double2*>(s + 2));
-                kv[rb][0] = k01.x; kv[rb][1] = k01.y; kv[rb][2] = k23.x; kv[rb][3] = k23.y;
+                ldg256_cg(kscr + (size_t)(row0 + 8 * rb + g) * Mp + jb, kv[rb][0], kv[rb][1], kv[rb][2], kv[rb][3]);
               }
             }
           }

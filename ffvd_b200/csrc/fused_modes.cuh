@@ -5,7 +5,8 @@
 namespace ffvd {
 
 #ifndef FFVD_ABLATE
-#define FFVD_ABLATE 0      // timing experiments only: 1 = no S REDs, 2 = no SYRK, 3 = no L^{-1} operand loads
+#define FFVD_ABLATE 0      // timing experiments only: 1 = no S REDs, 2 = no SYRK, 3 = no L^{-1} operand loads,
+                           // 4 = no K scratch stores, 5 = no exp, 6 = no r^2 loop
 #endif
 
 enum { MODE_UNCOLLAPSED = 0, MODE_COLLAPSED_P1 = 1, MODE_COLLAPSED_P2 = 2, MODE_FORWARD = 3, MODE_COND = 4 };
