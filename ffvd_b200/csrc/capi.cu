@@ -265,7 +265,7 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   const size_t mm = (size_t)Mp * Mp * sizeof(double);
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
   L.off_ZT = take((size_t)nprob * 64 * Mp * 8);          // Z~^T and its fragment-ordered copy
-  L.off_ZTs = take((size_t)nprob * nk * 32 * Mp * 8);
+  L.off_ZTs = take((size_t)nprob * nk * FFVD_ZTS_ROWS * Mp * 8);
   L.off_hyp = take((size_t)nprob * nk * 72 * 8);
   L.off_hq = take((size_t)nprob * D * 4 * 8);
   L.off_UT = take((size_t)nprob * D * Mp * 8);
@@ -330,7 +330,7 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   const size_t mm = (size_t)L.Mp * L.Mp;
   P.ZT = (double*)(a + L.off_ZT) + (size_t)p * 64 * L.Mp;
   P.Zf = P.ZT + (size_t)32 * L.Mp;
-  P.ZTs = (double*)(a + L.off_ZTs) + (size_t)p * L.nk * 32 * L.Mp;
+  P.ZTs = (double*)(a + L.off_ZTs) + (size_t)p * L.nk * FFVD_ZTS_ROWS * L.Mp;
   P.hyp = (double*)(a + L.off_hyp) + (size_t)p * L.nk * 72;
   P.hq = (double*)(a + L.off_hq) + (size_t)p * L.D * 4;
   P.UT = (double*)(a + L.off_UT) + (size_t)p * L.D * L.Mp;

@@ -9,6 +9,7 @@
                                // DMMA fragment reads (row q, column g) and the per-row reads conflict free per half-warp
 #define FFVD_XCOLS 32          // padded column count of X~ = [x, ctrl, 1, 0...]
 #define FFVD_MAX_DIN 31
+#define FFVD_ZTS_ROWS 41         // rows of the scaled Z~^T copy: 0..Din-1 z/l, zeros up to 39 (branch-free padded steps), row 40 = -|z~|^2/2
 #define FFVD_NTERMS_RAW 8      // raw per-sample sums, see below
 
 // raw per-sample term slots (sums of J pieces, before the -1/T scaling)
@@ -25,7 +26,7 @@ struct DevProblem {
   // derived inputs (written by kzz_prep)
   double *ZT;          // [32][Mp]    Z~^T: transposed, zero padded inducing inputs, then a row of ones (m < M), zeros
   double *Zf;          // [Mp/4][4][32] the same matrix in DMMA B-fragment order: entry ((m>>2)*4 + (jd>>3))*32 + (jd&7)*4 + (m&3)
-  double *ZTs;         // [nk][32][Mp] SE: per-kernel scaled copy z~ = z/l (rows 0..Din-1) and row Din = -1/2 |z~_m|^2
+  double *ZTs;         // [nk][FFVD_ZTS_ROWS][Mp] SE: per-kernel scaled copy z~ = z/l (rows 0..Din-1), zero rows, row 40 = -1/2 |z~_m|^2
   double *hyp;         // [nk][72]   per kernel: 1/l^2 [0..31], 1/l [32..63], v [64]           (hyper_kernel)
   double *hq;          // [D][4]     per output dim: Q, 1/Q, log Q                              (hyper_kernel)
   double *UT;          // [D][Mp]    U transposed, zero padded (coalesced staging of u_d)       (hyper_kernel)

@@ -61,17 +61,17 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
   // ring depth in input dims: one step is 4 RB FMAs per lane, so fewer rows per warp need a deeper ring to cover L2 latency
   constexpr int RING = RB >= 8 ? 4 : 8;
   double2 ring[RING][2], hz[2];
+  // SE: the scaled copy has zero rows after the Din real ones (and x~ has zero columns there), so the step loop runs in
+  // whole trips of RING steps with no per-step branch -- the trip is one basic block and the scheduler can request the x
+  // values of later steps while the FMAs of earlier ones issue.  Linear reads Z~^T itself (row Din is the ones row) and
+  // keeps the guarded loop.
   auto prologue = [&](int jb) {
 #pragma unroll
     for (int u = 0; u < RING; ++u) {
       ring[u][0] = ring[u][1] = make_double2(0.0, 0.0);
-      if (u < Din) {
-        ldg256_nc(ZTd + (size_t)u * Mp + jb, ring[u][0], ring[u][1]);
-      }
+      if (KIND == 0 || u < Din) ldg256_nc(ZTd + (size_t)u * Mp + jb, ring[u][0], ring[u][1]);
     }
-    if (KIND == 0) {
-      ldg256_nc(ZTd + (size_t)Din * Mp + jb, hz[0], hz[1]);
-    }
+    if (KIND == 0) ldg256_nc(ZTd + (size_t)(FFVD_ZTS_ROWS - 1) * Mp + jb, hz[0], hz[1]);
   };
   prologue(16 * group_index(wc, 0) + 4 * q);
   const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + g) * FFVD_XLD;
@@ -92,9 +92,11 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
 #pragma unroll
       for (int u = 0; u < RING; ++u) {
         const int jd = j0 + u;
-        if (jd < Din) {
+        if (KIND == 0 || jd < Din) {
           const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
-          if (jd + RING < Din) {
+          if (KIND == 0) {
+            if (j0 + RING < Din) ldg256_nc(ZTd + (size_t)(jd + RING) * Mp + jb, ring[u][0], ring[u][1]);   // uniform per trip
+          } else if (jd + RING < Din) {
             ldg256_nc(ZTd + (size_t)(jd + RING) * Mp + jb, ring[u][0], ring[u][1]);
           }
 #pragma unroll
@@ -703,7 +705,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 
     // ---- P1: K tile -> shared (SE uncollapsed: also to this CTA's L2-resident scratch, needed again for W = Kbar o K)
     compute_k_tile<KIND, RBW, NGW, (KIND == 0 && MODE == MODE_UNCOLLAPSED)>(
-        sm, (KIND == 0) ? P.ZTs + (size_t)dh * 32 * Mp : P.ZT, Mp, Din, v, wc, g, q, M, row0, lda, kscr);
+        sm, (KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT, Mp, Din, v, wc, g, q, M, row0, lda, kscr);
     if (nvalid < BT) {
       // partial last tile of a sample: rows >= nvalid must be inert (exact zeros)
       __syncthreads();

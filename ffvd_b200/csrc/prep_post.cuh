@@ -452,22 +452,22 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
   }
 }
 
-// SE: per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded) and, in row Din, -1/2 |z~_m|^2 -- the
+// SE: per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded) and, in the last row, -1/2 |z~_m|^2 -- the
 // column half of the reference's expansion of the scaled squared distance (kernels_multi_output.py:163-182).
 // grid (nk, nprob); block 256.
 __global__ void __launch_bounds__(256) zscale_kernel(const DevProblem* __restrict__ probs) {
   const DevProblem& P = probs[blockIdx.y];
   const int d = blockIdx.x, M = P.M, Mp = P.Mp, Din = P.Din;
-  double* out = P.ZTs + (size_t)d * 32 * Mp;
+  double* out = P.ZTs + (size_t)d * FFVD_ZTS_ROWS * Mp;
   for (int m = threadIdx.x; m < Mp; m += blockDim.x) {
     double a = 0.0;
-    for (int jd = 0; jd < Din; ++jd) {
+    for (int jd = 0; jd < FFVD_ZTS_ROWS - 1; ++jd) {
       double z = 0.0;
-      if (m < M) z = P.Z[(size_t)m * Din + jd] * exp(-P.logl[(size_t)d * Din + jd]);
-      out[(size_t)jd * Mp + m] = z;
+      if (m < M && jd < Din) z = P.Z[(size_t)m * Din + jd] * exp(-P.logl[(size_t)d * Din + jd]);
+      out[(size_t)jd * Mp + m] = z;                      // rows Din..39 stay zero: the tile kernel's padded steps read them
       a = fma(z, z, a);
     }
-    out[(size_t)Din * Mp + m] = -0.5 * a;
+    out[(size_t)(FFVD_ZTS_ROWS - 1) * Mp + m] = -0.5 * a;
   }
 }
 
