@@ -113,7 +113,7 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
 #pragma unroll
     for (int c = 0; c < 4; ++c) vc[c] = (jb + c < M) ? v : 0.0;
     // exp in lock-step batches of RBB rows x 4 columns
-    constexpr int RBB = RB >= 2 ? 2 : 1;
+    constexpr int RBB = RB >= 4 ? 4 : (RB >= 2 ? 2 : 1);
 #pragma unroll
     for (int rb0 = 0; rb0 < RB; rb0 += RBB) {
       double kv[RBB * 4];
