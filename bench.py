@@ -33,6 +33,10 @@ WORKLOADS = {
     # needs >= 2 GPUs for its 197 GB of X / x-bar / SG-HMC state -- SURVEY 7.2)
     "c3": dict(T=100_000, M=256, D=8, S=64, name="synthetic GPSSM T=100k M=256 D=8 S=64 SE float64 (BASELINE configs[2])"),
     "c3small": dict(T=10_000, M=256, D=8, S=8, name="synthetic GPSSM T=10k M=256 D=8 S=8 SE float64 (smoke-sized)"),
+    # BASELINE.json configs[4] (T=1M, M=512, D=16, S=256 over 8 GPUs = 32 trajectories per GPU): the per-GPU shard, and the
+    # same shard with T cut to 100k so that a step takes seconds instead of ~19 s (not the headline line: --workload only)
+    "c5": dict(T=1_000_000, M=512, D=16, S=32, name="synthetic GPSSM T=1M M=512 D=16 S=256/8 per GPU SE float64 (BASELINE configs[4] shard)"),
+    "c5short": dict(T=100_000, M=512, D=16, S=32, name="synthetic GPSSM T=100k M=512 D=16 S=32 per GPU SE float64 (configs[4] shape, T cut 10x)"),
 }
 CPU_SAMPLE_T = 20_000          # bounded CPU sample: T=20k, S=1 of the same M, D
 
