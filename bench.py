@@ -124,6 +124,13 @@ def time_cpu_oracle(cfg, steps, warmup):
     import torch
     from oracle import ffvd_oracle as O
     from oracle.ffvd_oracle import Problem
+    # all the host threads available (torchrun exports OMP_NUM_THREADS=1 to its workers: undo that for the CPU arm)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     T = min(CPU_SAMPLE_T, cfg["T"])
     h = make_host_data(T, cfg["M"], cfg["D"], 1, seed=1)
     prob = Problem(X=h["X"][0], Z=h["Z"], U=h["U"], logv=h["logv"], logl=h["logl"], logQ=h["logQ"], C=h["C"], d=h["d"],
