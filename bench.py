@@ -315,6 +315,19 @@ def main():
     h2d = X_host.numel() * 8 + noise_host.numel() * 8
     d2h = S * 8
 
+    # ---- the second kernel of the step against its own roofline: the SG-HMC burn-in update of X is an HBM
+    #      stream of 96 B / element (7 reads + 5 writes)
+    reset()
+    st = state["X"]
+    for _ in range(2):
+        ctx.sghmc_update(P["X"], out["g_X"], noise_X, st["xi"], st["g"], st["g2"], st["p"], 0.01, 0.05, float(T + 1), True)
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for _ in range(5):
+        ctx.sghmc_update(P["X"], out["g_X"], noise_X, st["xi"], st["g"], st["g2"], st["p"], 0.01, 0.05, float(T + 1), True)
+    u1.record(); torch.cuda.synchronize()
+    upd_gbs = P["X"].numel() * 96.0 / (u0.elapsed_time(u1) / 5 * 1e-3) * 1e-9
+
     if rank == 0:
         fl_launch = algorithmic_flops_per_unit(M, Din) * S * T * D           # one fused launch covers all units of the rank
         achieved = fl_launch / (fused_ms / max(fused_n, 1) * 1e-3) * 1e-12
@@ -356,6 +369,10 @@ def main():
                          "fused_share_of_step": (fused_ms / max(fused_n, 1)) / ms_per_step,
                          "fused_ms_per_rank": per_rank_fused,
                          "hbm_gbs_measured": peaks.get("hbm_gbs")},
+            "roofline_update": {"bound": "hbm", "achieved": upd_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                "frac": (upd_gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+                                "kernel": "ffvd::sghmc_kernel<burn_in> on X", "bytes_per_element": 96,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"},
             "clocks": clocks,
             "nll_mean": nll_check,
         }
