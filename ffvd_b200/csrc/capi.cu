@@ -453,7 +453,7 @@ static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse =
   }
   size_t smem = (size_t)2 * L.Mp * 8 + (size_t)L.M * (L.M + 1) * 8;
   int mode = 1;
-  if (chol_fast_smem_doubles(L.M, L.Mp) * 8 <= (size_t)c->max_smem && !getenv("FFVD_NO_FAST_CHOL")) {
+  if (chol_fast_fits(L.M, L.Mp, (size_t)c->max_smem) && !getenv("FFVD_NO_FAST_CHOL")) {
     smem = chol_fast_smem_doubles(L.M, L.Mp) * 8;      // L and L^{-1} both in shared memory (M <= ~116)
     mode = 2;
   }
@@ -663,7 +663,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       TRY(blocked_factor_invert(c, Wk, (double*)(c->arena + L.off_Dinv), Hx, HxT, (int*)(c->arena + L.off_status2), nz, M, Mp));
       collapsed_logdet_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
     } else {
-      const bool fast = chol_fast_smem_doubles(M, Mp) * 8 <= (size_t)c->max_smem && !getenv("FFVD_NO_FAST_CHOL");
+      const bool fast = chol_fast_fits(M, Mp, (size_t)c->max_smem) && !getenv("FFVD_NO_FAST_CHOL");
       const size_t sm_chol = fast ? chol_fast_smem_doubles(M, Mp) * 8 : (size_t)2 * Mp * 8;
       CUDA_TRY(cudaFuncSetAttribute(collapsed_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_chol));
       collapsed_chol_kernel<<<dim3(nb, nprob), 512, sm_chol, c->stream>>>(c->d_probs, fast ? 1 : 0); c->launches++;

@@ -8,6 +8,13 @@
 
 namespace ffvd {
 
+#ifdef FFVD_PREP_DEBUG
+__device__ long long g_prep_dbg[256];
+#define FFVD_DBG(i) do { if (threadIdx.x == 0) g_prep_dbg[i] = clock64(); } while (0)
+#else
+#define FFVD_DBG(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // device helpers operating on a generic-address matrix (shared or global)
 // In-place lower Cholesky of the leading M x M block of A (ld = lda); colbuf: M doubles of smem.
@@ -74,45 +81,193 @@ __device__ void tri_inverse(const double* L, int ldl, int M, double* X, double* 
   __syncthreads();
 }
 
-// Fast path for matrices small enough that L AND its inverse fit in shared memory (M <= ~116): X = L^{-1} by forward
-// substitution with ONE THREAD PER COLUMN (columns j and M-1-j paired for balance) -- no barrier and no global-memory
-// round trip inside the substitution (the generic routine above reads the rows of X it has just written back from
-// global memory, ~1 us per row step).  L: M x ldl shared; Xs: M x ldx shared (ldx even keeps the diagonal-stride reads of
-// neighbouring columns conflict free); dinv: M doubles.  Then X / X^T are written to the zero-padded global buffers.
-__device__ void tri_inverse_smem(const double* L, int ldl, int M, double* Xs, int ldx, double* dinv, double* X, double* XT, int Mp) {
-  const int tid = threadIdx.x, nth = blockDim.x;
-  for (int i = tid; i < M; i += nth) dinv[i] = 1.0 / L[(size_t)i * ldl + i];
+// ---------------------------------------------------------------------------------------------
+// Fast path for matrices small enough that L AND its inverse fit in shared memory (M <= FFVD_FAST_MAXM).
+//
+// Why not the generic routines above: at M ~ 100 they are pure latency.  Every trip of their inner loops is a dependent
+// load -> FMA (-> store) of ~70 clocks that the compiler cannot pipeline (it must assume the stores alias the loads), and
+// lanes with different trip counts wait for the longest one, so one column / row step costs 1.2-1.6k clocks whatever its
+// arithmetic (measured on B200: Cholesky 163k, inverse 197k clocks at M = 100).  Both routines below keep the values
+// that are updated in REGISTERS with compile-time indices; shared memory only carries the one column (Cholesky) or the
+// read-only factor (inverse) of the current step, and every load of a step is independent of the step's arithmetic.
+#define FFVD_FAST_MAXM 119        // 4x4 register tiles of the lower triangle <= 512 threads; 8 columns x 16 warps; offsets r < 120
+
+// In-place Cholesky of the lower triangle of A (M x M, row stride lda, SHARED memory), owner computes: thread t keeps
+// one 4x4 tile of the lower triangle (tiles numbered column-major, so finished tile columns are a prefix of the thread
+// order and whole warps retire) in registers for the whole factorisation.
+// Step j: every active thread reads the rows / columns of column j of the trailing matrix that its tile needs (published
+// by their owners at the end of step j-1, double buffered in cb[2][cbs]), forms 1/pivot itself and applies the rank-1
+// update a_ik -= a_ij a_kj / a_jj; the owners of column j+1 publish theirs.  One CTA barrier per column, 8 shared loads
+// per 16 multiply-adds.  The scaling by 1/sqrt(a_jj) is applied once at the end (L_ik = a_ik / sqrt(a_kk), a the value
+// when column k was reached).  Returns 0 or the 1-based failing pivot (like chol_inplace).
+// blockDim.x == 512, M <= FFVD_FAST_MAXM, cbs a multiple of 4 >= M, cb 16-byte aligned.
+__device__ int chol_owner_smem(double* A, int lda, int M, double* cb, int cbs, int* flag) {
+  const int tid = threadIdx.x;
+  const int nt = (M + 3) >> 2, ntile = nt * (nt + 1) / 2;
+  if (tid == 0) *flag = 0;
+  // column-major tile index -> (tk, ti): tile columns 0..tk-1 hold tk*nt - tk(tk-1)/2 tiles
+  const float fm = (float)nt + 0.5f;
+  int tk = (int)(fm - sqrtf(fmaxf(fm * fm - 2.0f * (float)tid, 0.0f)));
+  tk = max(0, min(tk, nt - 1));
+  while (tk > 0 && tk * nt - tk * (tk - 1) / 2 > tid) --tk;
+  while (tk < nt - 1 && (tk + 1) * nt - (tk + 1) * tk / 2 <= tid) ++tk;
+  const bool valid = tid < ntile;
+  const int i0 = valid ? 4 * (tk + (tid - (tk * nt - tk * (tk - 1) / 2))) : 0;
+  const int k0 = valid ? 4 * tk : -8;          // -8: never active
+  double a[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = i0 + r, k = k0 + c;
+      a[r][c] = (valid && i < M && k <= i) ? A[(size_t)i * lda + k] : 0.0;
+    }
+  if (k0 == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (i0 + r < M) cb[i0 + r] = a[r][0];
+  }
   __syncthreads();
-  for (int t = tid; t < (M + 1) / 2; t += nth) {
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int j = half ? (M - 1 - t) : t;
-      if (half && j == t) break;
-      Xs[(size_t)j * ldx + j] = dinv[j];
-      for (int i = j + 1; i < M; ++i) {
-        const double* Li = L + (size_t)i * ldl;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int k = j;
-        for (; k + 3 < i; k += 4) {
-          s0 = fma(Li[k], Xs[(size_t)k * ldx + j], s0);
-          s1 = fma(Li[k + 1], Xs[(size_t)(k + 1) * ldx + j], s1);
-          s2 = fma(Li[k + 2], Xs[(size_t)(k + 2) * ldx + j], s2);
-          s3 = fma(Li[k + 3], Xs[(size_t)(k + 3) * ldx + j], s3);
+  for (int j = 0; j < M; ++j) {
+    FFVD_DBG(128 + j);
+    const double* cur = cb + (j & 1) * cbs;
+    double* nxt = cb + ((j + 1) & 1) * cbs;
+    const double piv = cur[j];
+    if (!(piv > 0.0)) {                       // same value in every thread: the whole CTA leaves together
+      if (tid == 0) *flag = j + 1;
+      break;
+    }
+    if (tid == 511) A[(size_t)j * lda + j] = rsqrt(piv);   // parked on the diagonal until the final scaling (thread 511 owns no tile)
+    if (k0 + 3 > j) {
+      const double inv2 = 1.0 / piv;
+      const double2 ci01 = *reinterpret_cast<const double2*>(cur + i0), ci23 = *reinterpret_cast<const double2*>(cur + i0 + 2);
+      const double2 ck01 = *reinterpret_cast<const double2*>(cur + k0), ck23 = *reinterpret_cast<const double2*>(cur + k0 + 2);
+      const double ci[4] = {-ci01.x * inv2, -ci01.y * inv2, -ci23.x * inv2, -ci23.y * inv2};
+      const double ck[4] = {ck01.x, ck01.y, ck23.x, ck23.y};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (k0 + c > j) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[r][c] = fma(ci[r], ck[c], a[r][c]);
         }
-        for (; k < i; ++k) s0 = fma(Li[k], Xs[(size_t)k * ldx + j], s0);
-        Xs[(size_t)i * ldx + j] = -((s0 + s1) + (s2 + s3)) * dinv[i];
+        if (k0 + c == j + 1) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (i0 + r < M && i0 + r >= k0 + c) nxt[i0 + r] = a[r][c];   // lower part only (a diagonal tile carries unused upper entries)
+        }
       }
     }
+    __syncthreads();
+  }
+  __syncthreads();                            // the early exit above skips the barrier of its iteration
+  const int st = *flag;
+  if (st == 0) {
+    // the diagonal of A holds 1/sqrt(pivot_k); every owned entry (diagonal included) is scaled by it
+    double sc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = min(max(k0 + c, 0), M - 1);
+      sc[c] = A[(size_t)k * lda + k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = i0 + r, k = k0 + c;
+        if (valid && i < M && k <= i) A[(size_t)i * lda + k] = a[r][c] * sc[c];
+      }
   }
   __syncthreads();
-  for (int idx = tid; idx < M * M; idx += nth) {
-    const int r = idx / M, c = idx % M;
-    X[(size_t)r * Mp + c] = (c <= r) ? Xs[(size_t)r * ldx + c] : 0.0;
+  return st;
+}
+
+// X = L^{-1} (lower) by forward substitution, L x_j = e_j; L (M x ldl) and the scratch dinv (M doubles) in SHARED memory.
+// Four lanes per column, eight columns per warp (j0 .. j0+7, j0 a multiple of 8).  Rows advance in blocks of four
+// ABSOLUTE rows i = 4B .. 4B+3, starting at the block that holds row j0 (entries above the diagonal come out as the
+// zeros they are); lane `sub` of a column keeps X[4B' + sub][j] of the finished blocks in registers.  The registers
+// are indexed relative to the current block (y[s] = the entry produced s blocks ago, shifted once per block), which makes
+// every register index a compile-time constant inside a rolled block loop.  All eight columns of a warp work on the same
+// rows and columns of L, so every load of L is a 4-address broadcast.  Per block the four row sums over the finished
+// registers are independent of the block's own results and are formed first (two terms per exit test, eight loads in
+// flight); then two shuffles per row, and the block's own 4x4 triangular solve is done redundantly by the four lanes so
+// that no shuffle sits on the dependent chain.
+// The result is staged in the shared matrix Xs (M x ldx) and written to the zero-padded global buffers X and XT = X^T.
+__device__ void tri_inverse_smem(const double* __restrict__ L, int ldl, int M, double* __restrict__ Xs, int ldx, double* __restrict__ dinv,
+                                 double* __restrict__ X, double* __restrict__ XT, int Mp) {
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
+  for (int i = tid; i < M; i += nth) dinv[i] = 1.0 / L[(size_t)i * ldl + i];
+  __syncthreads();
+  const int sub = lane & 3, cw = lane >> 2;
+  constexpr int NS = (FFVD_FAST_MAXM + 3) / 4;      // register slots per lane
+  const int nB = (M + 3) >> 2;
+  for (int j0 = 8 * warp; j0 < M; j0 += 8 * nw) {
+    const int j = j0 + cw;                       // may be >= M: the lane group solves for a zero right-hand side, stores nothing
+    double y[NS + 1];
+#pragma unroll
+    for (int t = 0; t <= NS; ++t) y[t] = 0.0;
+    const int Bs = j0 >> 2;
+    for (int B = Bs; B < nB; ++B) {
+      FFVD_DBG(64 + B);
+      const int b = B - Bs;                      // finished blocks (warp uniform)
+      // rows of the block (clamped into the matrix) and their operand pointers at column 4B + sub
+      const double* Lr[4];
+      int row[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        row[p] = min(4 * B + p, M - 1);
+        Lr[p] = L + (size_t)row[p] * ldl + 4 * B + sub;
+      }
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int s = 1; s < NS; s += 2) {
+        if (s > b) break;
+        const bool two = s + 1 <= b && s + 1 < NS;
+        double l0[4], l1[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          l0[p] = Lr[p][-4 * s];
+          l1[p] = two ? Lr[p][-4 * (s + 1)] : 0.0;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) v[p] = fma(l1[p], y[(s + 1 < NS) ? s + 1 : s], fma(l0[p], y[s], v[p]));
+      }
+      // (kept below the sums on purpose: loaded earlier these values push the sums out of registers and the compiler
+      // serialises every load of the loop above behind its multiply-add)
+      asm volatile("" ::: "memory");
+      // the 4x4 diagonal block of L that couples the block's own four results, and 1/L_ii
+      double dv[4], lb[4][3];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        dv[p] = dinv[row[p]];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lb[p][c] = (c < p) ? Lr[p][c - sub] : 0.0;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v[p] += __shfl_xor_sync(0xffffffffu, v[p], 1);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v[p] += __shfl_xor_sync(0xffffffffu, v[p], 2);
+      // x_p = (delta(4B+p, j) - v_p - sum_{c<p} l_pc x_c) / L_pp
+      const int jr = j - 4 * B;                  // row of the block that carries the unit right-hand side (if 0..3)
+      const double x0 = ((jr == 0 ? 1.0 : 0.0) - v[0]) * dv[0];
+      const double x1 = ((jr == 1 ? 1.0 : 0.0) - fma(lb[1][0], x0, v[1])) * dv[1];
+      const double x2 = ((jr == 2 ? 1.0 : 0.0) - fma(lb[2][1], x1, fma(lb[2][0], x0, v[2]))) * dv[2];
+      const double x3 = ((jr == 3 ? 1.0 : 0.0) - fma(lb[3][2], x2, fma(lb[3][1], x1, fma(lb[3][0], x0, v[3])))) * dv[3];
+      y[0] = (sub == 0) ? x0 : (sub == 1) ? x1 : (sub == 2) ? x2 : x3;
+      if (j < M && 4 * B + sub < M) Xs[(size_t)(4 * B + sub) * ldx + j] = y[0];
+#pragma unroll
+      for (int t = NS; t > 0; --t) y[t] = y[t - 1];
+    }
   }
-  for (int idx = tid; idx < M * M; idx += nth) {
-    const int r = idx / M, c = idx % M;
-    XT[(size_t)r * Mp + c] = (c >= r) ? Xs[(size_t)c * ldx + r] : 0.0;
-  }
+  FFVD_DBG(100);
+  __syncthreads();
+  FFVD_DBG(101);
+  // rows above each column's first block were never staged: the upper triangle is written as zeros from the index test
+  for (int r = warp; r < M; r += nw)
+    for (int c = lane; c < M; c += 32) {
+      X[(size_t)r * Mp + c] = (c <= r) ? Xs[(size_t)r * ldx + c] : 0.0;
+      XT[(size_t)r * Mp + c] = (c >= r) ? Xs[(size_t)c * ldx + r] : 0.0;
+    }
   __syncthreads();
 }
 
@@ -120,6 +275,9 @@ __device__ void tri_inverse_smem(const double* L, int ldl, int M, double* Xs, in
 __host__ __device__ inline size_t chol_fast_smem_doubles(int M, int Mp) {
   const int ldx = (M + 1) & ~1;
   return (size_t)M * (M + 1) + (size_t)M * ldx + (size_t)3 * Mp;
+}
+__host__ inline bool chol_fast_fits(int M, int Mp, size_t max_smem) {
+  return M <= FFVD_FAST_MAXM && chol_fast_smem_doubles(M, Mp) * 8 <= max_smem;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -149,6 +307,31 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
   const int lda = use_smem ? (M + 1) : Mp;
   const double v = exp(P.logv[d]);
   // K(Z,Z) + jitter I, lower triangle.  kernels_multi_output.py:202-214 / kernels.py:270-276
+  const int ldx2 = (M + 1) & ~1;
+  if (use_smem == 2 && Din <= ldx2) {
+    // fast path: z~ = z / l (SE) or z (linear) staged once in the (still unused) X region, a warp per row of K
+    double* zs = Asm + (size_t)M * (M + 1);
+    const double* hy = P.hyp + (size_t)d * 72 + 32;          // 1 / l, written by hyper_kernel
+    for (int idx = tid; idx < M * Din; idx += nth) zs[idx] = (KIND == 0) ? P.Z[idx] * hy[idx % Din] : P.Z[idx];
+    __syncthreads();
+    const int lane = tid & 31, nw = nth >> 5;
+    for (int m = tid >> 5; m < M; m += nw)
+      for (int n = lane; n <= m; n += 32) {
+        double s = 0.0;
+        for (int jd = 0; jd < Din; ++jd) {
+          const double a = zs[m * Din + jd], b = zs[n * Din + jd];
+          if (KIND == 0) {
+            const double t = a - b;
+            s = fma(t, t, s);
+          } else {
+            s = fma(a, b, s);
+          }
+        }
+        double k = (KIND == 0) ? v * exp(-0.5 * s) : v * s;
+        if (m == n) k += jitter;
+        Asm[(size_t)m * (M + 1) + n] = k;
+      }
+  } else
   for (int idx = tid; idx < M * M; idx += nth) {
     const int m = idx / M, n = idx % M;
     if (n > m) continue;
@@ -168,12 +351,12 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
     A[(size_t)m * lda + n] = k;
   }
   __syncthreads();
-  const int st = chol_inplace(A, lda, M, colbuf, &flag);
+  const int st = (use_smem == 2) ? chol_owner_smem(Asm, M + 1, M, sh, Mp, &flag) : chol_inplace(A, lda, M, colbuf, &flag);
   if (tid == 0) P.status[d] = st;
   if (st != 0) return;
   if (use_smem == 2) {
     double* Xs = Asm + (size_t)M * (M + 1);
-    tri_inverse_smem(A, lda, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), P.Linv + (size_t)d * Mp * Mp, Lt, Mp);
+    tri_inverse_smem(Asm, M + 1, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), P.Linv + (size_t)d * Mp * Mp, Lt, Mp);
   } else {
     tri_inverse(A, lda, M, P.Linv + (size_t)d * Mp * Mp, Lt, Mp, rowbuf);
   }
@@ -430,7 +613,7 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
     H[(size_t)m * ldh + n] = S[(size_t)m * Mp + n] * iq + (m == n ? 1.0 : 0.0);
   }
   __syncthreads();
-  const int st = chol_inplace(H, ldh, M, sh, &flag);
+  const int st = fast ? chol_owner_smem(sh + 2 * Mp, M + 1, M, sh, Mp, &flag) : chol_inplace(H, ldh, M, sh, &flag);
   if (st != 0) {
     if (tid == 0) P.status[d] = st;
     return;
@@ -445,8 +628,9 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
   double* X = P.Hx + (size_t)b * Mp * Mp;
   double* XT = P.HxT + (size_t)b * Mp * Mp;
   if (fast) {
-    double* Xs = H + (size_t)M * (M + 1);
-    tri_inverse_smem(H, ldh, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), X, XT, Mp);
+    double* Hs = sh + 2 * Mp;
+    double* Xs = Hs + (size_t)M * (M + 1);
+    tri_inverse_smem(Hs, M + 1, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), X, XT, Mp);
   } else {
     tri_inverse(H, Mp, M, X, XT, Mp, sh + Mp);
   }
