@@ -442,8 +442,12 @@ __device__ __forceinline__ size_t bmap(const BatchMap& m, int z) { return (size_
 __global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, const double* __restrict__ A,
                                                         const double* __restrict__ B, int n, double alpha,
                                                         BatchMap mC, BatchMap mA, BatchMap mB) {
-  __shared__ __align__(16) double As[64][20];
-  __shared__ __align__(16) double Bs[16][68];
+  // 64 x 64 tile of C per CTA, k in steps of 32.  The next step's A / B slabs are fetched into registers (4 + 4
+  // 16-byte loads per thread, all in flight together) while the current one is multiplied out of shared memory: at
+  // n = 128 the kernel is four L2 round trips long instead of the 64 serialised ones of a load -> store loop.
+  constexpr int BK = 32;
+  __shared__ __align__(16) double As[64][BK + 4];     // stride 36 = 4 mod 16: fragment reads conflict free per half-warp
+  __shared__ __align__(16) double Bs[BK][68];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps: each 32 x 16
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
@@ -453,19 +457,28 @@ __global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, c
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
-  for (int k0 = 0; k0 < n; k0 += 16) {
-    __syncthreads();
-    for (int idx = tid; idx < 64 * 16; idx += 256) {
-      const int r = idx >> 4, cc = idx & 15;
-      As[r][cc] = A[(size_t)(m0 + r) * n + k0 + cc];
+  double2 ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      ra[i] = *reinterpret_cast<const double2*>(A + (size_t)(m0 + (idx >> 4)) * n + k0 + 2 * (idx & 15));
+      rb[i] = *reinterpret_cast<const double2*>(B + (size_t)(k0 + (idx >> 5)) * n + n0 + 2 * (idx & 31));
     }
-    for (int idx = tid; idx < 16 * 64; idx += 256) {
-      const int r = idx >> 6, cc = idx & 63;
-      Bs[r][cc] = B[(size_t)(k0 + r) * n + n0 + cc];
-    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < n; k0 += BK) {
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; kk += 4) {
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      *reinterpret_cast<double2*>(&As[idx >> 4][2 * (idx & 15)]) = ra[i];
+      *reinterpret_cast<double2*>(&Bs[idx >> 5][2 * (idx & 31)]) = rb[i];
+    }
+    __syncthreads();
+    if (k0 + BK < n) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
       double a[4], b[2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[wm * 32 + 8 * i + g][kk + q];
@@ -694,21 +707,45 @@ __global__ void zero_gx_kernel(const DevProblem* __restrict__ probs) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) P.gX[i] = 0.0;
 }
 
+// Four rows of a matrix-vector product per warp: t[r] = sum_{n < M} A[(m0 + r) * ld + n] * x[n] on every lane.  The
+// four loads of a trip are independent and two trips are unrolled, so eight L2 round trips are in flight per lane (a
+// row-at-a-time loop pays them one after the other: ~1 us per row).  Rows >= M repeat row M-1 (discard the result).
+__device__ __forceinline__ void warp_rows4_dot(const double* __restrict__ A, int ld, const double* __restrict__ x, int m0, int M, int lane,
+                                               double (&t)[4]) {
+  const double* a[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    t[r] = 0.0;
+    a[r] = A + (size_t)min(m0 + r, M - 1) * ld;
+  }
+#pragma unroll 2
+  for (int n = lane; n < M; n += 32) {
+    const double xv = x[n];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) t[r] = fma(a[r][n], xv, t[r]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) t[r] += __shfl_xor_sync(0xffffffffu, t[r], o);
+}
+
 // Uncollapsed: w_d = L_d^{-T} u_d, so that the fused kernel can form Kbar = (A L^{-1})/Q + e w^T without touching the
-// A operand of its second contraction.  grid (D, nprob); block 256 (warp per row of the upper-triangular L^{-T}).
+// A operand of its second contraction.  grid (D, nprob); block 256 (four rows of L^{-T} per warp; the zero lower part
+// of the rows is multiplied through).  u_d is read from the transposed copy written by hyper_kernel.
 __global__ void __launch_bounds__(256) ltu_kernel(const DevProblem* __restrict__ probs) {
   const DevProblem& P = probs[blockIdx.y];
-  const int d = blockIdx.x, M = P.M, Mp = P.Mp, D = P.D;
+  const int d = blockIdx.x, M = P.M, Mp = P.Mp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double* LT = P.LinvT + (size_t)d * P.hs * Mp * Mp;
+  const double* u = P.UT + (size_t)d * Mp;
   double* w = P.wvec + (size_t)d * Mp;
-  for (int m = warp; m < Mp; m += 8) {
-    double t = 0.0;
-    if (m < M)
-      for (int n = (m & ~31) + lane; n < M; n += 32) t = fma(LT[(size_t)m * Mp + n], P.U[(size_t)n * D + d], t);
-    t = warp_sum(t);
-    if (lane == 0) w[m] = t;
+  for (int m0 = 4 * warp; m0 < M; m0 += 32) {
+    double t[4];
+    warp_rows4_dot(LT, Mp, u, m0, M, lane, t);
+    if (lane < 4 && m0 + lane < M) w[m0 + lane] = (lane == 0) ? t[0] : (lane == 1) ? t[1] : (lane == 2) ? t[2] : t[3];
   }
+  for (int m = M + threadIdx.x; m < Mp; m += 256) w[m] = 0.0;
 }
 
 // After Hinv = L_H^{-T} L_H^{-1} is in Wk[b]:  c = Hinv b/Q ; w' = L^{-T} c / Q ; quad; dJ/dlogQ;
@@ -723,50 +760,55 @@ __global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __
   double* c = P.cvec + (size_t)b * Mp;
   double* w = P.wvec + (size_t)b * Mp;
   const double* S = P.Sacc + (size_t)b * Mp * Mp;
+  const double* LT = P.LinvT + (size_t)d * Mp * Mp;
   __shared__ double red[4];
+  __shared__ double bs[2048], cs[2048];            // b/Q and c (Mp <= 2048)
   if (tid < 4) red[tid] = 0.0;
-  __syncthreads();
-  // c = Hinv (b/Q)
-  for (int m = warp; m < Mp; m += 8) {
-    double t = 0.0;
-    if (m < M)
-      for (int n = lane; n < M; n += 32) t = fma(Hinv[(size_t)m * Mp + n], bv[n] * iq, t);
-    t = warp_sum(t);
-    if (lane == 0) c[m] = t;
+  for (int n = tid; n < Mp; n += 256) {
+    bs[n] = (n < M) ? bv[n] * iq : 0.0;
+    cs[n] = 0.0;
   }
   __syncthreads();
+  // c = Hinv (b/Q)
+  for (int m0 = 4 * warp; m0 < M; m0 += 32) {
+    double t[4];
+    warp_rows4_dot(Hinv, Mp, bs, m0, M, lane, t);
+    if (lane < 4 && m0 + lane < M) cs[m0 + lane] = (lane == 0) ? t[0] : (lane == 1) ? t[1] : (lane == 2) ? t[2] : t[3];
+  }
+  __syncthreads();
+  for (int n = tid; n < Mp; n += 256) c[n] = cs[n];
   // quad = 1/2 b_s^T c ; c^T b_s ; trace Hinv ; c^T (H - I) c = c^T S c / Q
   double qd = 0.0, tr = 0.0, csc = 0.0;
   for (int m = tid; m < M; m += 256) {
-    qd = fma(bv[m] * iq, c[m], qd);
+    qd = fma(bs[m], cs[m], qd);
     tr += Hinv[(size_t)m * Mp + m];
   }
-  for (int m = warp; m < M; m += 8) {
-    double t = 0.0;
-    for (int n = lane; n < M; n += 32) t = fma(S[(size_t)m * Mp + n], c[n], t);
-    t = warp_sum(t);
-    if (lane == 0) csc = fma(c[m], t, csc);
+  for (int m0 = 4 * warp; m0 < M; m0 += 32) {
+    double t[4], u[4];
+    warp_rows4_dot(S, Mp, cs, m0, M, lane, t);
+    // w' = L^{-T} c / Q   (LinvT is upper; its zero lower part is multiplied through)
+    warp_rows4_dot(LT, Mp, cs, m0, M, lane, u);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (m0 + r < M) csc = fma(cs[m0 + r], t[r], csc);
+    }
+    if (lane < 4 && m0 + lane < M) w[m0 + lane] = ((lane == 0) ? u[0] : (lane == 1) ? u[1] : (lane == 2) ? u[2] : u[3]) * iq;
   }
+  for (int m = M + tid; m < Mp; m += 256) w[m] = 0.0;
   qd = warp_sum(qd); tr = warp_sum(tr); csc = warp_sum(csc);
   if (lane == 0) { atomicAdd(red + 0, qd); atomicAdd(red + 1, tr); atomicAdd(red + 2, csc); }
-  // w' = L^{-T} c / Q   (LinvT is upper: row m, columns n >= m)
-  const double* LT = P.LinvT + (size_t)d * Mp * Mp;
-  for (int m = warp; m < Mp; m += 8) {
-    double t = 0.0;
-    if (m < M)
-      for (int n = m + lane; n < M; n += 32) t = fma(LT[(size_t)m * Mp + n], c[n], t);
-    t = warp_sum(t);
-    if (lane == 0) w[m] = t * iq;
-  }
   __syncthreads();
   if (tid == 0) {
     red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
     red_add(P.gQ + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
   }
   // Mat' in place
-  for (int idx = tid; idx < M * M; idx += 256) {
-    const int m = idx / M, n = idx % M;
-    Hinv[(size_t)m * Mp + n] = ((m == n ? 1.0 : 0.0) - Hinv[(size_t)m * Mp + n] - c[m] * c[n]) * iq;
+  for (int m = warp; m < M; m += 8) {
+    double* row = Hinv + (size_t)m * Mp;
+    const double cm = cs[m];
+#pragma unroll 4
+    for (int n = lane; n < M; n += 32) row[n] = ((m == n ? 1.0 : 0.0) - row[n] - cm * cs[n]) * iq;
   }
 }
 
