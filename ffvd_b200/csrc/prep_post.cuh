@@ -92,14 +92,58 @@ __device__ void tri_inverse(const double* L, int ldl, int M, double* X, double* 
 // read-only factor (inverse) of the current step, and every load of a step is independent of the step's arithmetic.
 #define FFVD_FAST_MAXM 119        // 4x4 register tiles of the lower triangle <= 512 threads; 8 columns x 16 warps; offsets r < 120
 
+// Column j = 4J + JJ of chol_owner_smem (below).  Returns false when the CTA must stop: past the last column, or a
+// non-positive pivot (flag set).  CTA uniform.
+template <int JJ>
+__device__ __forceinline__ bool chol_col_step(double (&a)[4][4], double* A, int lda, int M, double* cb, int cbs, int* flag, int J, int tk, int i0,
+                                              int k0) {
+  const int j = 4 * J + JJ;
+  if (j >= M) return false;
+  FFVD_DBG(128 + j);
+  const double* cur = cb + (JJ & 1) * cbs;
+  double* nxt = cb + ((JJ + 1) & 1) * cbs;
+  const double piv = cur[j];
+  if (!(piv > 0.0)) {                          // same value in every thread: the whole CTA leaves together
+    if (threadIdx.x == 0) *flag = j + 1;
+    return false;
+  }
+  // the tile still has a column > j  <=>  tk > J, or tk == J and JJ < 3
+  if (tk > J || (tk == J && JJ < 3)) {
+    const double inv2 = 1.0 / piv;
+    const double2 ci01 = *reinterpret_cast<const double2*>(cur + i0), ci23 = *reinterpret_cast<const double2*>(cur + i0 + 2);
+    const double2 ck01 = *reinterpret_cast<const double2*>(cur + k0), ck23 = *reinterpret_cast<const double2*>(cur + k0 + 2);
+    const double ci[4] = {-ci01.x * inv2, -ci01.y * inv2, -ci23.x * inv2, -ci23.y * inv2};
+    const double ck[4] = {ck01.x, ck01.y, ck23.x, ck23.y};
+    // columns <= j of the tile are finished (their final values were parked in A when they were published) and are
+    // updated along unconditionally -- garbage from here on, never read again
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r][c] = fma(ci[r], ck[c], a[r][c]);
+    constexpr int cn = (JJ + 1) & 3;           // tile column that holds matrix column j + 1 ...
+    const bool mine = tk == J + (JJ == 3 ? 1 : 0);   // ... in the tiles of this tile column
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (mine && i0 + r < M && i0 + r >= k0 + cn) {   // lower part only (a diagonal tile carries unused upper entries)
+        nxt[i0 + r] = a[r][cn];
+        A[(size_t)(i0 + r) * lda + k0 + cn] = a[r][cn];
+      }
+  }
+  __syncthreads();
+  return true;
+}
+
 // In-place Cholesky of the lower triangle of A (M x M, row stride lda, SHARED memory), owner computes: thread t keeps
 // one 4x4 tile of the lower triangle (tiles numbered column-major, so finished tile columns are a prefix of the thread
 // order and whole warps retire) in registers for the whole factorisation.
 // Step j: every active thread reads the rows / columns of column j of the trailing matrix that its tile needs (published
 // by their owners at the end of step j-1, double buffered in cb[2][cbs]), forms 1/pivot itself and applies the rank-1
-// update a_ik -= a_ij a_kj / a_jj; the owners of column j+1 publish theirs.  One CTA barrier per column, 8 shared loads
-// per 16 multiply-adds.  The scaling by 1/sqrt(a_jj) is applied once at the end (L_ik = a_ik / sqrt(a_kk), a the value
-// when column k was reached).  Returns 0 or the 1-based failing pivot (like chol_inplace).
+// update a_ik -= a_ij a_kj / a_jj; the owners of column j+1 publish theirs and park its final (unscaled) values in A.
+// One CTA barrier per column, 8 shared loads per 16 multiply-adds.  The column loop is unrolled by the tile width so
+// that "which of my columns is the next pivot column" is a compile-time register index (the body is a single-warp
+// latency chain: every select / compare removed from it is time).  The scaling by 1/sqrt(a_jj) is applied once at the
+// end (L_ik = a_ik / sqrt(a_kk), a the value when column k was reached).
+// Returns 0 or the 1-based failing pivot (like chol_inplace).
 // blockDim.x == 512, M <= FFVD_FAST_MAXM, cbs a multiple of 4 >= M, cb 16-byte aligned.
 __device__ int chol_owner_smem(double* A, int lda, int M, double* cb, int cbs, int* flag) {
   const int tid = threadIdx.x;
@@ -113,7 +157,8 @@ __device__ int chol_owner_smem(double* A, int lda, int M, double* cb, int cbs, i
   while (tk < nt - 1 && (tk + 1) * nt - (tk + 1) * tk / 2 <= tid) ++tk;
   const bool valid = tid < ntile;
   const int i0 = valid ? 4 * (tk + (tid - (tk * nt - tk * (tk - 1) / 2))) : 0;
-  const int k0 = valid ? 4 * tk : -8;          // -8: never active
+  if (!valid) tk = -2;                         // never active, never publishes
+  const int k0 = 4 * tk;
   double a[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -122,52 +167,32 @@ __device__ int chol_owner_smem(double* A, int lda, int M, double* cb, int cbs, i
       const int i = i0 + r, k = k0 + c;
       a[r][c] = (valid && i < M && k <= i) ? A[(size_t)i * lda + k] : 0.0;
     }
-  if (k0 == 0) {
+  if (tk == 0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       if (i0 + r < M) cb[i0 + r] = a[r][0];
   }
   __syncthreads();
-  for (int j = 0; j < M; ++j) {
-    FFVD_DBG(128 + j);
-    const double* cur = cb + (j & 1) * cbs;
-    double* nxt = cb + ((j + 1) & 1) * cbs;
-    const double piv = cur[j];
-    if (!(piv > 0.0)) {                       // same value in every thread: the whole CTA leaves together
-      if (tid == 0) *flag = j + 1;
-      break;
-    }
-    if (tid == 511) A[(size_t)j * lda + j] = rsqrt(piv);   // parked on the diagonal until the final scaling (thread 511 owns no tile)
-    if (k0 + 3 > j) {
-      const double inv2 = 1.0 / piv;
-      const double2 ci01 = *reinterpret_cast<const double2*>(cur + i0), ci23 = *reinterpret_cast<const double2*>(cur + i0 + 2);
-      const double2 ck01 = *reinterpret_cast<const double2*>(cur + k0), ck23 = *reinterpret_cast<const double2*>(cur + k0 + 2);
-      const double ci[4] = {-ci01.x * inv2, -ci01.y * inv2, -ci23.x * inv2, -ci23.y * inv2};
-      const double ck[4] = {ck01.x, ck01.y, ck23.x, ck23.y};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (k0 + c > j) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) a[r][c] = fma(ci[r], ck[c], a[r][c]);
-        }
-        if (k0 + c == j + 1) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (i0 + r < M && i0 + r >= k0 + c) nxt[i0 + r] = a[r][c];   // lower part only (a diagonal tile carries unused upper entries)
-        }
-      }
-    }
-    __syncthreads();
+  for (int J = 0; J < nt; ++J) {
+    if (!chol_col_step<0>(a, A, lda, M, cb, cbs, flag, J, tk, i0, k0)) break;
+    if (!chol_col_step<1>(a, A, lda, M, cb, cbs, flag, J, tk, i0, k0)) break;
+    if (!chol_col_step<2>(a, A, lda, M, cb, cbs, flag, J, tk, i0, k0)) break;
+    if (!chol_col_step<3>(a, A, lda, M, cb, cbs, flag, J, tk, i0, k0)) break;
   }
   __syncthreads();                            // the early exit above skips the barrier of its iteration
   const int st = *flag;
   if (st == 0) {
-    // the diagonal of A holds 1/sqrt(pivot_k); every owned entry (diagonal included) is scaled by it
-    double sc[4];
+    // A holds the unscaled columns (column k as it was when it became the pivot column; its diagonal entry is the pivot)
+    double sc[4], v[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int k = min(max(k0 + c, 0), M - 1);
-      sc[c] = A[(size_t)k * lda + k];
+      sc[c] = rsqrt(A[(size_t)k * lda + k]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = min(i0 + r, M - 1);
+        v[r][c] = A[(size_t)i * lda + k];
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -175,7 +200,7 @@ __device__ int chol_owner_smem(double* A, int lda, int M, double* cb, int cbs, i
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int i = i0 + r, k = k0 + c;
-        if (valid && i < M && k <= i) A[(size_t)i * lda + k] = a[r][c] * sc[c];
+        if (valid && i < M && k < M && k <= i) A[(size_t)i * lda + k] = v[r][c] * sc[c];
       }
   }
   __syncthreads();
