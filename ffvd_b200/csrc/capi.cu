@@ -670,7 +670,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     }
     if (!no_grads) {
       TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));          // H^{-1} = L_H^{-T} L_H^{-1}
-      collapsed_vec_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
+      collapsed_vec_kernel<<<dim3(nb, nprob), 1024, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
       TRY(launch_bgemm(c, Hx, Wk, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Mat' L^{-1}
       TRY(launch_bgemm(c, Nmat, LinvT, Hx, Mp, 1.0, nz, idm, lmap, idm));     // N = L^{-T} Mat' L^{-1}
       TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, Din, c->d_probs, nprob, total_items)));
@@ -679,15 +679,19 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     } else {
       // forward only still needs c for the quadratic term
       TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));
-      collapsed_vec_kernel<<<dim3(nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+      collapsed_vec_kernel<<<dim3(nb, nprob), 1024, 0, c->stream>>>(c->d_probs); c->launches++;
     }
   }
   if (!no_grads) {
     TRY(launch_bgemm(c, Wk, Sacc, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Gs L^{-1}
     TRY(launch_bgemm(c, Sacc, LinvT, Wk, Mp, -0.5, nz, idm, lmap, idm));      // Kbar_zz = -1/2 L^{-T} Gs L^{-1}
     const dim3 grow((M + 7) / 8, nb, nprob);
-    wz_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
-    kzz_bwd_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    if (getenv("FFVD_SPLIT_KZZ_BWD")) {                     // the two-kernel form (kept for A/B timing)
+      wz_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+      kzz_bwd_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    } else {
+      kzz_bwd_fused_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    }
   }
   finalize_kernel<KIND><<<nprob, 256, 0, c->stream>>>(c->d_probs, c->d_outs, collapsed, flags); c->launches++;
   if (!no_grads) {

@@ -580,6 +580,88 @@ __global__ void __launch_bounds__(256) wz_kernel(const DevProblem* __restrict__ 
   if (lane == 0) P.rs[(size_t)b * Mp + m] = rs;
 }
 
+// wz_kernel + kzz_bwd_kernel in one pass (the small-M path: two launches and an L2 round trip of Wz less, and the loop
+// over n is spread over the lanes so that a row costs ~3 L2 round trips instead of ~M/2 partially overlapped ones).
+// A warp per row m of Kbar_zz (in Sacc, left untouched): lanes take n = lane, lane + 32, ...; per n the row Z[n][:] is
+// loaded once and used both for the kernel value and for the weighted sums  wzz[jd] = sum_n Wz[m][n] Z[n][jd].
+// grid (ceil(M/8), batch, nprob); block 256.  hyp (1/l, 1/l^2, v) comes from hyper_kernel.
+template <int KIND>
+__global__ void __launch_bounds__(256) kzz_bwd_fused_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.z];
+  const int b = blockIdx.y, d = b % P.D;
+  const int M = P.M, Mp = P.Mp, Din = P.Din;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * 8 + warp;
+  __shared__ double zm[8][32], lsm[8][32];
+  const double* hy = P.hyp + (size_t)d * P.hs * 72;
+  const double il = (KIND == 0 && lane < Din) ? hy[32 + lane] : 0.0;      // 1 / l_jd in lane jd
+  const bool rowok = m < M;
+  const int mc = rowok ? m : M - 1;
+  const double zmine = lane < Din ? P.Z[(size_t)mc * Din + lane] : 0.0;
+  zm[warp][lane] = (KIND == 0) ? zmine * il : zmine;                        // z~_m (SE) for the distance
+  lsm[warp][lane] = il;
+  __syncwarp();
+  const double* Kb = P.Sacc + (size_t)b * Mp * Mp + (size_t)mc * Mp;
+  const double v = hy[64];
+  double rs = 0.0, lpart = 0.0, vpart = 0.0, zb = 0.0;
+  // chunks of eight input dimensions (registers); the kernel values are recomputed per chunk when Din > 8
+  for (int j0 = 0; j0 < Din; j0 += 8) {
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double rsum = 0.0;
+    for (int n = lane; n < M; n += 32) {
+      const double* zn = P.Z + (size_t)n * Din;
+      double wz = Kb[n];
+      if (KIND == 0) {
+        double s = 0.0;
+        for (int jd = 0; jd < Din; ++jd) {
+          const double t = zm[warp][jd] - zn[jd] * lsm[warp][jd];
+          s = fma(t, t, s);
+        }
+        wz *= v * exp(-0.5 * s);
+      }
+      rsum += wz;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (j0 + q < Din) acc[q] = fma(wz, zn[j0 + q], acc[q]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    rs = rsum;
+    double wzz = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wzz = (lane == j0 + q) ? acc[q] : wzz;
+    if (rowok && lane >= j0 && lane < j0 + 8 && lane < Din) {
+      if (KIND == 0) {
+        zb = -2.0 * hy[lane] * (zmine * rs - wzz);
+        lpart = -zmine * zb;
+      } else {
+        zb = 2.0 * v * wzz;
+        vpart = 0.5 * zmine * zb;
+      }
+      red_add(P.gZ + (size_t)m * Din + lane, zb);
+    }
+  }
+  if (KIND == 0) {
+    if (rowok && lane == 0) vpart = rs;
+    // reduce lpart over the 8 rows of the block through shared memory, one atomic per jd
+    __syncthreads();
+    lsm[warp][lane] = lpart;
+    __syncthreads();
+    if (warp == 0 && lane < Din) {
+      double t = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += lsm[r][lane];
+      red_add(P.gl + (size_t)d * Din + lane, t);
+    }
+  }
+  vpart = warp_sum(vpart);
+  if (lane == 0 && vpart != 0.0) red_add(P.gv + d, vpart);
+}
+
 // dJ/dZ, dJ/dlogl, dJ/dlogv contributions of Kbar_zz.  grid (ceil(M/8), batch, nprob); block (32, 8).
 template <int KIND>
 __global__ void __launch_bounds__(256) kzz_bwd_kernel(const DevProblem* __restrict__ probs) {
@@ -646,9 +728,15 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
   // fast: H, its factor and the inverse live in shared memory (sh: 2 Mp vectors, then H, then X, then dinv)
   double* H = fast ? sh + 2 * Mp : P.Wk + (size_t)b * Mp * Mp;
   const int ldh = fast ? M + 1 : Mp;
-  for (int idx = tid; idx < M * M; idx += nth) {
-    const int m = idx / M, n = idx % M;
-    H[(size_t)m * ldh + n] = S[(size_t)m * Mp + n] * iq + (m == n ? 1.0 : 0.0);
+  {
+    // a warp per row, four loads in flight per lane (a flat load -> store loop pays one L2 round trip per element)
+    const int lane = tid & 31, nw = nth >> 5;
+    for (int m = tid >> 5; m < M; m += nw) {
+      const double* __restrict__ Srow = S + (size_t)m * Mp;
+      double* __restrict__ Hrow = H + (size_t)m * ldh;
+#pragma unroll 4
+      for (int n = lane; n < M; n += 32) Hrow[n] = Srow[n] * iq + (m == n ? 1.0 : 0.0);
+    }
   }
   __syncthreads();
   const int st = fast ? chol_owner_smem(sh + 2 * Mp, M + 1, M, sh, Mp, &flag) : chol_inplace(H, ldh, M, sh, &flag);
@@ -775,10 +863,10 @@ __global__ void __launch_bounds__(256) ltu_kernel(const DevProblem* __restrict__
 
 // After Hinv = L_H^{-T} L_H^{-1} is in Wk[b]:  c = Hinv b/Q ; w' = L^{-T} c / Q ; quad; dJ/dlogQ;
 // then Wk[b] <- Mat' = (I - Hinv - c c^T)/Q.     grid (S*D, nprob); block 256.
-__global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __restrict__ probs) {
+__global__ void __launch_bounds__(1024) collapsed_vec_kernel(const DevProblem* __restrict__ probs) {
   const DevProblem& P = probs[blockIdx.y];
   const int b = blockIdx.x, d = b % P.D, s = b / P.D;
-  const int M = P.M, Mp = P.Mp, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = P.M, Mp = P.Mp, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nth = blockDim.x, nw = nth >> 5;
   const double iq = exp(-P.logQ[d]);
   double* Hinv = P.Wk + (size_t)b * Mp * Mp;
   const double* bv = P.ubar + (size_t)b * Mp;      // unscaled F^T delta
@@ -789,26 +877,26 @@ __global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __
   __shared__ double red[4];
   __shared__ double bs[2048], cs[2048];            // b/Q and c (Mp <= 2048)
   if (tid < 4) red[tid] = 0.0;
-  for (int n = tid; n < Mp; n += 256) {
+  for (int n = tid; n < Mp; n += nth) {
     bs[n] = (n < M) ? bv[n] * iq : 0.0;
     cs[n] = 0.0;
   }
   __syncthreads();
   // c = Hinv (b/Q)
-  for (int m0 = 4 * warp; m0 < M; m0 += 32) {
+  for (int m0 = 4 * warp; m0 < M; m0 += 4 * nw) {
     double t[4];
     warp_rows4_dot(Hinv, Mp, bs, m0, M, lane, t);
     if (lane < 4 && m0 + lane < M) cs[m0 + lane] = (lane == 0) ? t[0] : (lane == 1) ? t[1] : (lane == 2) ? t[2] : t[3];
   }
   __syncthreads();
-  for (int n = tid; n < Mp; n += 256) c[n] = cs[n];
+  for (int n = tid; n < Mp; n += nth) c[n] = cs[n];
   // quad = 1/2 b_s^T c ; c^T b_s ; trace Hinv ; c^T (H - I) c = c^T S c / Q
   double qd = 0.0, tr = 0.0, csc = 0.0;
-  for (int m = tid; m < M; m += 256) {
+  for (int m = tid; m < M; m += nth) {
     qd = fma(bs[m], cs[m], qd);
     tr += Hinv[(size_t)m * Mp + m];
   }
-  for (int m0 = 4 * warp; m0 < M; m0 += 32) {
+  for (int m0 = 4 * warp; m0 < M; m0 += 4 * nw) {
     double t[4], u[4];
     warp_rows4_dot(S, Mp, cs, m0, M, lane, t);
     // w' = L^{-T} c / Q   (LinvT is upper; its zero lower part is multiplied through)
@@ -820,7 +908,7 @@ __global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __
     }
     if (lane < 4 && m0 + lane < M) w[m0 + lane] = ((lane == 0) ? u[0] : (lane == 1) ? u[1] : (lane == 2) ? u[2] : u[3]) * iq;
   }
-  for (int m = M + tid; m < Mp; m += 256) w[m] = 0.0;
+  for (int m = M + tid; m < Mp; m += nth) w[m] = 0.0;
   qd = warp_sum(qd); tr = warp_sum(tr); csc = warp_sum(csc);
   if (lane == 0) { atomicAdd(red + 0, qd); atomicAdd(red + 1, tr); atomicAdd(red + 2, csc); }
   __syncthreads();
@@ -828,13 +916,16 @@ __global__ void __launch_bounds__(256) collapsed_vec_kernel(const DevProblem* __
     red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
     red_add(P.gQ + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
   }
-  // Mat' in place
-  for (int m = warp; m < M; m += 8) {
-    double* row = Hinv + (size_t)m * Mp;
-    const double cm = cs[m];
-#pragma unroll 4
-    for (int n = lane; n < M; n += 32) row[n] = ((m == n ? 1.0 : 0.0) - row[n] - cm * cs[n]) * iq;
-  }
+  // Mat' in place: four rows per warp in flight (loads of all four first, then the stores)
+  for (int m0 = 4 * warp; m0 < M; m0 += 4 * nw)
+    for (int n = lane; n < M; n += 32) {
+      double h[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) h[r] = Hinv[(size_t)min(m0 + r, M - 1) * Mp + n];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (m0 + r < M) Hinv[(size_t)(m0 + r) * Mp + n] = ((m0 + r == n ? 1.0 : 0.0) - h[r] - cs[m0 + r] * cs[n]) * iq;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -860,26 +951,56 @@ __device__ __forceinline__ double block_sum_sq(const double* x, int n, double sh
 template <int KIND>
 __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restrict__ probs, const OutPtrs* __restrict__ outs,
                                                        int collapsed, int flags) {
-  __shared__ double red;
   const DevProblem& P = probs[blockIdx.x];
   const OutPtrs& O = outs[blockIdx.x];
-  const int tid = threadIdx.x, nth = blockDim.x;
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
   const int M = P.M, Mp = P.Mp, D = P.D, Din = P.Din, Dy = P.Dy, S = P.S, T = P.T;
   const double sc = -1.0 / (double)T;
   const bool shared_priors = (flags & 16) == 0, x0_prior = (flags & 32) == 0;
   const double npri = !shared_priors ? 0.0 : ((flags & 2) ? 1.0 : (double)S);
   const bool zprior = (flags & 1) != 0;
   const double log005 = log(0.05);
-  double pz = zprior ? -0.5 * block_sum_sq(P.Z, M * Din, 0.0, &red) : 0.0;
-  double ph = -0.5 * block_sum_sq(P.logv, D, log005, &red);
-  if (KIND == 0) ph += -0.5 * block_sum_sq(P.logl, D * Din, 0.0, &red);
-  double pu = collapsed ? 0.0 : -0.5 * block_sum_sq(P.U, M * D, 0.0, &red);
-  double hyp = -0.5 * (block_sum_sq(P.logQ, D, 0.0, &red) + block_sum_sq(P.C, D * Dy, 0.0, &red) +
-                       block_sum_sq(P.dvec, Dy, 0.0, &red) + block_sum_sq(P.logR, Dy * Dy, 0.0, &red));
+  // The eight prior sums of squares in ONE pass: the loads of a trip are independent (one L2 round trip per trip instead
+  // of one block reduction, three barriers and a round trip per array), then a single block reduction of the 8-vector.
+  //   0 Z   1 logv - log 0.05   2 logl   3 U   4 logQ   5 C   6 d   7 logR
+  const double* arr[8] = {zprior ? P.Z : nullptr, P.logv, KIND == 0 ? P.logl : nullptr, collapsed ? nullptr : P.U, P.logQ, P.C, P.dvec, P.logR};
+  const int cnt[8] = {M * Din, D, D * Din, M * D, D, D * Dy, Dy, Dy * Dy};
+  int maxn = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) maxn = max(maxn, arr[k] ? cnt[k] : 0);
+  double part[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int base = 0; base < maxn; base += nth) {
+    const int i = base + tid;
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (arr[k] && i < cnt[k]) ? arr[k][i] - (k == 1 ? log005 : 0.0) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[k] = fma(v[k], v[k], part[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+  __shared__ double wred[32][8];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wred[warp][k] = part[k];
+  }
+  __syncthreads();
+  double tot[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    tot[k] = 0.0;
+    for (int w = 0; w < nw; ++w) tot[k] += wred[w][k];        // fixed order: the same value in every thread, run to run
+  }
+  double pz = -0.5 * tot[0], ph = -0.5 * (tot[1] + tot[2]), pu = -0.5 * tot[3], hyp = -0.5 * (((tot[4] + tot[5]) + tot[6]) + tot[7]);
   if (!shared_priors) pz = ph = pu = hyp = 0.0;
-  for (int s = 0; s < S; ++s) {
-    const double px0 = x0_prior ? -0.5 * block_sum_sq(P.X + (size_t)s * (T + 1) * D, D, 0.0, &red) : 0.0;
-    if (tid == 0) {
+  // per-sample terms: a warp per sample (D <= 31 values of x_0)
+  for (int s = warp; s < S; s += nw) {
+    double x0 = (x0_prior && lane < D) ? P.X[(size_t)s * (T + 1) * D + lane] : 0.0;
+    x0 = warp_sum(x0 * x0);
+    const double px0 = -0.5 * x0;
+    if (lane == 0) {
       const double* r = P.terms_raw + (size_t)s * FFVD_NTERMS_RAW;
       double t[6];
       t[0] = sc * (pu + ph + pz + px0 + hyp);
