@@ -134,6 +134,34 @@ def test_ragged_shapes(env, T, M, D, S, collapsed):
     check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="T%d M%d" % (T, M))
 
 
+@pytest.mark.parametrize("M", (1, 2, 4, 8, 31, 32, 33, 64, 97, 116, 118, 119, 120, 121, 160, 161))
+@pytest.mark.parametrize("collapsed", (False, True))
+def test_small_m_factorisation_paths(env, M, collapsed):
+    """Every branch of the K(Z,Z) / H factorisation: the register-resident single-CTA path (M <= 119: one tile, partial
+    tiles, one warp, the 119 / 120 switch), the shared-memory path above it and the 160 / 161 switch to the blocked one."""
+    from oracle import fixtures, ffvd_oracle as O
+    prob = fixtures.synthetic_problem(T=37, M=M, D=2, S=2, seed=4242 + M)
+    check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="M%d" % M)
+
+
+@pytest.mark.parametrize("M", (6, 100, 140, 300))
+def test_cholesky_failure_is_reported(env, M):
+    """A negative "jitter" larger than the kernel variance makes the first pivot of chol(K(Z,Z)) negative (an exact
+    zero pivot from duplicated inducing points is rounding dependent, here as in LAPACK).  The reference's
+    tf.linalg.cholesky raises; every factorisation path here must return the not-positive-definite status, not NaNs."""
+    from oracle import fixtures
+    prob = fixtures.synthetic_problem(T=20, M=M, D=2, S=1, seed=11)
+    p = dev_problem(env, prob)
+    o = alloc_out(env, p)
+    with pytest.raises(env["ffvd"].NotPositiveDefinite) as ei:
+        env["ctx"].nll_grads(prob.kind, False, p, o, flags=env["ffvd"].FLAG_PRIOR_Z_NORMAL, jitter=-1.0e3)
+    assert "positive definite" in str(ei.value) and ei.value.pivot == 1
+    # the context stays usable
+    good = fixtures.synthetic_problem(T=20, M=M, D=2, S=1, seed=12)
+    from oracle import ffvd_oracle as O
+    check(O.nll_and_grads(good, collapsed=False), run_cuda(env, good, False), what="after failure M%d" % M)
+
+
 @pytest.mark.parametrize("T,M,D,n_ctrl", [(70, 40, 16, 1), (90, 200, 12, 3), (33, 130, 14, 1), (40, 60, 20, 11), (50, 500, 16, 1)])
 @pytest.mark.parametrize("collapsed,kind", ((False, 0), (True, 0), (False, 1)))
 def test_wide_inputs(env, T, M, D, n_ctrl, collapsed, kind):
