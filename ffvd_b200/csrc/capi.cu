@@ -433,16 +433,20 @@ static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
 }
 
 template <int KIND>
-static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse = false, long long ident = 0) {
-  hyper_kernel<<<dim3(L.nk > L.D ? L.nk : L.D, L.nprob), 128, 0, c->stream>>>(c->d_probs, KIND, L.nk); c->launches++;
+static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse = false, long long ident = 0, bool want_ltu = false,
+                       bool* ltu_done = nullptr) {
   long long jbits;
   memcpy(&jbits, &jitter, sizeof jbits);
   std::vector<long long> key = c->arena_key;
   key.push_back(KIND); key.push_back(jbits); key.push_back(ident);
-  if (reuse && c->kzz_valid && key == c->kzz_key) return FFVD_OK;     // factors of the previous call are still in the arena
+  const bool reused = reuse && c->kzz_valid && key == c->kzz_key;     // factors of the previous call are still in the arena
+  if (ltu_done) *ltu_done = false;
+  // hyp / hq / U^T every call (U changes under REUSE_KZZ); the scaled Z~^T (SE) only when the factors are rebuilt
+  hyper_kernel<<<dim3(L.nk > L.D ? L.nk : L.D, L.nprob), 128, 0, c->stream>>>(c->d_probs, KIND, L.nk, (KIND == 0 && !reused) ? 1 : 0);
+  c->launches++;
+  if (reused) return FFVD_OK;
   c->kzz_valid = true;
   c->kzz_key = key;
-  if (KIND == 0) { zscale_kernel<<<dim3(L.nk, L.nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
   if (use_blocked(c, L.M, L.Mp)) {
     double* Lfac = (double*)(c->arena + L.off_Lfac);
     const size_t nel = (size_t)L.Mp * L.Mp > (size_t)32 * L.Mp ? (size_t)L.Mp * L.Mp : (size_t)32 * L.Mp;
@@ -458,7 +462,9 @@ static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse =
     mode = 2;
   }
   CUDA_TRY(cudaFuncSetAttribute(kzz_prep_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kzz_prep_kernel<KIND><<<dim3(L.nk, L.nprob), 512, smem, c->stream>>>(c->d_probs, jitter, mode);
+  const int do_ltu = (mode == 2 && want_ltu) ? 1 : 0;     // w = L^{-T} u from the shared-memory inverse (else ltu_kernel)
+  kzz_prep_kernel<KIND><<<dim3(L.nk, L.nprob), 512, smem, c->stream>>>(c->d_probs, jitter, mode, do_ltu);
+  if (ltu_done) *ltu_done = do_ltu != 0;
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return FFVD_OK;
@@ -640,7 +646,8 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   long long ident = 1469598103934665603LL;      // FNV-1a over the addresses of Z / logv / logl of every problem: the factors in
   for (auto& t : pt)                             // the arena belong to exactly these tensors
     for (const double* q : {t.Z.d, t.logv.d, t.logl.d}) ident = (ident ^ (long long)(uintptr_t)q) * 1099511628211LL;
-  TRY(launch_prep<KIND>(c, L, jitter, (flags & FFVD_FLAG_REUSE_KZZ) != 0, ident));
+  bool ltu_done = false;
+  TRY(launch_prep<KIND>(c, L, jitter, (flags & FFVD_FLAG_REUSE_KZZ) != 0, ident, !collapsed && !no_grads, &ltu_done));
   const int nz = nprob * nb;
   const BatchMap idm = {1, 1, 1};                // z -> z
   const BatchMap lmap = {nb, D, D};              // z -> (z / nb) * D + z % D
@@ -652,7 +659,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   if (no_grads && !collapsed) {
     TRY((launch_fused<KIND, MODE_FORWARD>(c, Mp, Din, c->d_probs, nprob, total_items)));
   } else if (!collapsed) {
-    ltu_kernel<<<dim3(D, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    if (!ltu_done) { ltu_kernel<<<dim3(D, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
     TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, Din, c->d_probs, nprob, total_items)));
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 0); c->launches++;
   } else {
@@ -965,7 +972,7 @@ extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLM
     CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
   }
   // U (possibly un-whitened) was bound after setup_zside ran the prep kernels: refresh U^T
-  hyper_kernel<<<dim3(nk > R ? nk : R, 1), 128, 0, c->stream>>>(c->d_probs, kind, nk); c->launches++;
+  hyper_kernel<<<dim3(nk > R ? nk : R, 1), 128, 0, c->stream>>>(c->d_probs, kind, nk, 0); c->launches++;
   if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   else TRY((launch_fused<1, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   int st = FFVD_OK;

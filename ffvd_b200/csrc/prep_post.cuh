@@ -308,7 +308,7 @@ __host__ inline bool chol_fast_fits(int M, int Mp, size_t max_smem) {
 // ---------------------------------------------------------------------------------------------
 // grid (D, nprob); block 512.  Dynamic smem: 2*Mp doubles (+ M*(M+1) when use_smem; chol_fast_smem_doubles when use_smem == 2).
 template <int KIND>
-__global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restrict__ probs, double jitter, int use_smem) {
+__global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restrict__ probs, double jitter, int use_smem, int do_ltu) {
   extern __shared__ __align__(16) double sh[];
   __shared__ int flag;
   const DevProblem& P = probs[blockIdx.y];
@@ -381,7 +381,33 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
   if (st != 0) return;
   if (use_smem == 2) {
     double* Xs = Asm + (size_t)M * (M + 1);
-    tri_inverse_smem(Asm, M + 1, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), P.Linv + (size_t)d * Mp * Mp, Lt, Mp);
+    const int ldx = (M + 1) & ~1;
+    tri_inverse_smem(Asm, M + 1, M, Xs, ldx, Xs + (size_t)M * ldx, P.Linv + (size_t)d * Mp * Mp, Lt, Mp);
+    if (do_ltu && P.U) {
+      // the work of ltu_kernel, w = L^{-T} u, from the inverse still in shared memory (one launch and an L2 round trip of
+      // L^{-T} less): thread m forms sum_{n >= m} X[n][m] u[n] over consecutive-m (conflict-free) rows of X
+      double* us = Xs + (size_t)M * ldx;                     // the inverse's 1/L_ii scratch is free again
+      for (int dd = P.hs ? d : 0; dd < (P.hs ? d + 1 : P.D); ++dd) {
+        __syncthreads();
+        for (int n = tid; n < M; n += nth) us[n] = P.UT[(size_t)dd * Mp + n];
+        __syncthreads();
+        double* w = P.wvec + (size_t)dd * Mp;
+        for (int m = tid; m < Mp; m += nth) {
+          double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+          if (m < M) {
+            int n = m;
+            for (; n + 3 < M; n += 4) {
+              t0 = fma(Xs[(size_t)n * ldx + m], us[n], t0);
+              t1 = fma(Xs[(size_t)(n + 1) * ldx + m], us[n + 1], t1);
+              t2 = fma(Xs[(size_t)(n + 2) * ldx + m], us[n + 2], t2);
+              t3 = fma(Xs[(size_t)(n + 3) * ldx + m], us[n + 3], t3);
+            }
+            for (; n < M; ++n) t0 = fma(Xs[(size_t)n * ldx + m], us[n], t0);
+          }
+          w[m] = (t0 + t1) + (t2 + t3);
+        }
+      }
+    }
   } else {
     tri_inverse(A, lda, M, P.Linv + (size_t)d * Mp * Mp, Lt, Mp, rowbuf);
   }
@@ -784,9 +810,11 @@ __global__ void __launch_bounds__(256) zscale_kernel(const DevProblem* __restric
 // Per-evaluation scalars the tile kernel would otherwise re-derive (with FP64 exp calls) in every work item:
 // hyp[k] = {1/l_j^2, 1/l_j, v} per kernel, hq[d] = {Q, 1/Q, log Q} per output dim, UT = U^T zero padded.
 // grid (max(nk, D), nprob); block 128.
-__global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int nk) {
+// zs != 0 (SE only): also the work of zscale_kernel for kernel k (one launch less on the small-problem path).
+__global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int nk, int zs) {
   const DevProblem& P = probs[blockIdx.y];
   const int k = blockIdx.x, t = threadIdx.x, Din = P.Din, D = P.D, M = P.M, Mp = P.Mp;
+  __shared__ double sils[32];
   if (k < nk) {
     double* h = P.hyp + (size_t)k * 72;
     if (t < 32) {
@@ -797,8 +825,23 @@ __global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int
         sil = exp(-ll);
       }
       h[t] = il2; h[32 + t] = sil;
+      sils[t] = sil;
     }
     if (t == 32) h[64] = exp(P.logv[k]);
+  }
+  __syncthreads();
+  if (zs && k < nk) {
+    double* out = P.ZTs + (size_t)k * FFVD_ZTS_ROWS * Mp;
+    for (int m = t; m < Mp; m += blockDim.x) {
+      double a = 0.0;
+      for (int jd = 0; jd < FFVD_ZTS_ROWS - 1; ++jd) {
+        double z = 0.0;
+        if (m < M && jd < Din) z = P.Z[(size_t)m * Din + jd] * sils[jd];
+        out[(size_t)jd * Mp + m] = z;                      // rows Din..39 stay zero: the tile kernel's padded steps read them
+        a = fma(z, z, a);
+      }
+      out[(size_t)(FFVD_ZTS_ROWS - 1) * Mp + m] = -0.5 * a;
+    }
   }
   if (k < D) {
     if (t == 33) {

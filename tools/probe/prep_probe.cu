@@ -80,12 +80,12 @@ int main(int argc, char** argv) {
     size_t smem = (size_t)2 * Mp * 8 + (size_t)M * (M + 1) * 8;
     if (mode == 2) { if (!chol_fast_fits(M, Mp, (size_t)max_smem)) { printf("mode 2 does not fit\n"); continue; } smem = chol_fast_smem_doubles(M, Mp) * 8; }
     CK(cudaFuncSetAttribute(kzz_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hyper_kernel<<<dim3(D, 1), 128>>>(dP, 0, D);
-    for (int it = 0; it < 3; ++it) kzz_prep_kernel<0><<<dim3(D, 1), 512, smem>>>(dP, jitter, mode);
+    hyper_kernel<<<dim3(D, 1), 128>>>(dP, 0, D, 0);
+    for (int it = 0; it < 3; ++it) kzz_prep_kernel<0><<<dim3(D, 1), 512, smem>>>(dP, jitter, mode, 0);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
     const int reps = 20;
-    for (int it = 0; it < reps; ++it) kzz_prep_kernel<0><<<dim3(D, 1), 512, smem>>>(dP, jitter, mode);
+    for (int it = 0; it < reps; ++it) kzz_prep_kernel<0><<<dim3(D, 1), 512, smem>>>(dP, jitter, mode, 0);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
