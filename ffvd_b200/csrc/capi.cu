@@ -54,6 +54,7 @@ struct ffvd_ctx {
   std::vector<long long> kzz_key;
   size_t last_off_cvec = 0, last_off_HxT = 0;
   int last_Mp = 0, last_nb = 0;
+  int cur_rb = 0;                  // tile height (row blocks of 8) chosen for the call in flight, 0 = fused_cfg's default
   int probs_cap = 0;
   int* h_status = nullptr;     // pinned
   size_t h_status_cap = 0;
@@ -385,7 +386,8 @@ static FusedCfg fused_cfg(int Mp) {
 template <int KIND, int MODE>
 static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs, int nprob, long long total_items) {
   const int ngw = Mp / 128;
-  const FusedCfg cfg = fused_cfg(Mp);
+  FusedCfg cfg = fused_cfg(Mp);
+  if (c->cur_rb) cfg.rb = c->cur_rb;
 #ifdef FFVD_SPLIT_BUILD
   ffvd_fused_fn kern = ffvd_fused_lookup(KIND, MODE, cfg.rb, ngw, cfg.nw, cfg.minb);    // instantiated in fused_inst.cu objects
 #else
@@ -413,6 +415,16 @@ static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs,
   return FFVD_OK;
 }
 static int rb_of(int Mp) { return fused_cfg(Mp).rb; }
+// Tile height for a call with `rows` x-rows per (sample, output dim) pair and `pairs` such pairs: the default, except that
+// at Mp = 128 half-height tiles are used while they still fit one wave of the persistent grid -- a launch with fewer
+// work items than SMs (the single-chain case: T = 512, D = 4 -> 64 items) is one item's latency long, and half the rows
+// is nearly half the latency (C1: fused kernel 38 -> 24 us).
+static int rb_for_call(const ffvd_ctx* c, int Mp, long long pairs, long long rows) {
+  const int rb = rb_of(Mp);
+  if (Mp != 128 || rb != 8 || getenv("FFVD_RB")) return rb;
+  const long long items4 = pairs * ((rows + 31) / 32);
+  return items4 <= c->num_sms ? 4 : rb;
+}
 // output dims per block of the work-item order: keep the operand matrices of one block (16 Mp^2 bytes per dim) within
 // ~16 MB of L2.  FFVD_DBLK overrides (experiments).
 static int dblk_of(int Mp, int D) {
@@ -603,7 +615,10 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   const int nb = collapsed ? pt[0].S * D : D;
   Layout L = make_layout(nprob, nb, D, D, M, Mp, Din, Dy, sumS, collapsed != 0, true);
   TRY(ensure_arena(c, L));
-  const int RB = rb_of(Mp), BT = 8 * RB;
+  long long pairs = 0, maxT = 0;
+  for (auto& t : pt) { pairs += (long long)D * t.S; maxT = t.T > maxT ? t.T : maxT; }
+  const int RB = rb_for_call(c, Mp, pairs, maxT), BT = 8 * RB;
+  c->cur_rb = RB;
 
   std::vector<DevProblem> hp(nprob);
   std::vector<OutPtrs> ho(nprob);
@@ -940,7 +955,8 @@ extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLM
   if (N == 0) return call.finish();
   Layout L; DevProblem P;
   TRY(setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P, tq.present && tq.ndim == 3, (flags & FFVD_FLAG_REUSE_KZZ) != 0));
-  const int RB = rb_of(P.Mp), BT = 8 * RB;
+  const int RB = rb_for_call(c, P.Mp, R, N), BT = 8 * RB;
+  c->cur_rb = RB;
   P.hs = shared_kernel ? 0 : 1;
   P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;
   P.ntiles = (N + BT - 1) / BT; P.dblk = dblk_of(P.Mp, R); P.item_begin = 0; P.nitems = (long long)R * P.ntiles;
