@@ -207,6 +207,141 @@ __device__ int chol_owner_smem(double* A, int lda, int M, double* cb, int cbs, i
   return st;
 }
 
+// Panel form of chol_owner_smem: four columns per step, two CTA barriers per step.
+//   phase A  the owners of tile column J (their registers ARE the panel, column block J of the trailing matrix) read
+//            the raw 4x4 diagonal block, factorise it (each of them, redundantly: ~M/4 threads), turn their own rows
+//            into rows of L by a 4-step forward substitution (L_i = P_i L_DD^{-T}), store them into A (final, no
+//            deferred scaling) and publish them in lb;
+//   phase B  every tile right of the panel reads its L_i and L_k rows from lb and applies the rank-4 update
+//            a -= L_i L_k^T (16 shared loads per 64 multiply-adds); the next diagonal tile publishes its raw block.
+// ceil(M/4) steps instead of M: the per-column chain (barrier, pivot load, reciprocal, publish) is paid once per four
+// columns, and nothing but the tiny diagonal factorisation is redundant (a first version in which every thread solved
+// for the L rows it needed was FP64-throughput bound and no faster than the column form).
+// Padded rows / columns (M not a multiple of 4) carry an identity diagonal.  lb holds the L rows per 4-row group, 16
+// values plus 2 doubles of padding: neighbouring lanes own neighbouring row groups, and a group stride of 9 x 16 bytes
+// (odd) spreads the 16-byte accesses of eight lanes over all banks.  scratch: FFVD_PTILE * (ceil(M/4) + 1) doubles,
+// 16-byte aligned.  Returns 0 or the 1-based failing pivot.  blockDim.x == 512, M <= FFVD_FAST_MAXM.
+#define FFVD_PTILE 18
+__device__ int chol_panel_smem(double* A, int lda, int M, double* scratch, int* flag) {
+  const int tid = threadIdx.x;
+  const int nt = (M + 3) >> 2, ntile = nt * (nt + 1) / 2;
+  double* db = scratch;                        // raw diagonal block of the current step (row r at db + 4 r)
+  double* lb = scratch + FFVD_PTILE;           // L rows of the current panel, group g at lb + FFVD_PTILE * g
+  if (tid == 0) *flag = 0;
+  const float fm = (float)nt + 0.5f;
+  int tk = (int)(fm - sqrtf(fmaxf(fm * fm - 2.0f * (float)tid, 0.0f)));
+  tk = max(0, min(tk, nt - 1));
+  while (tk > 0 && tk * nt - tk * (tk - 1) / 2 > tid) --tk;
+  while (tk < nt - 1 && (tk + 1) * nt - (tk + 1) * tk / 2 <= tid) ++tk;
+  const bool valid = tid < ntile;
+  const int ti = valid ? tk + (tid - (tk * nt - tk * (tk - 1) / 2)) : 0;
+  const int i0 = 4 * ti;
+  if (!valid) tk = -2;                         // never active
+  const int k0 = 4 * tk;
+  double a[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = i0 + r, k = k0 + c;
+      a[r][c] = (valid && i < M && k <= i) ? A[(size_t)i * lda + k] : ((valid && i == k) ? 1.0 : 0.0);
+    }
+  if (tk == 0 && ti == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      *reinterpret_cast<double2*>(db + 4 * r) = make_double2(a[r][0], a[r][1]);
+      *reinterpret_cast<double2*>(db + 4 * r + 2) = make_double2(a[r][2], a[r][3]);
+    }
+  }
+  __syncthreads();
+  for (int J = 0; J < nt; ++J) {
+    if (tk == J) {
+      // 4x4 diagonal block (lower part) -> its Cholesky factor l and the reciprocal diagonal r
+      const double d00 = db[0];
+      const double2 d1 = *reinterpret_cast<const double2*>(db + 4);
+      const double2 d2a = *reinterpret_cast<const double2*>(db + 8);
+      const double d22 = db[10];
+      const double2 d3a = *reinterpret_cast<const double2*>(db + 12), d3b = *reinterpret_cast<const double2*>(db + 14);
+      int bad = 0;
+      if (!(d00 > 0.0)) bad = 1;
+      const double r0 = rsqrt(d00);
+      const double l10 = d1.x * r0, l20 = d2a.x * r0, l30 = d3a.x * r0;
+      const double e11 = fma(-l10, l10, d1.y);
+      if (!bad && !(e11 > 0.0)) bad = 2;
+      const double r1 = rsqrt(e11);
+      const double l21 = fma(-l20, l10, d2a.y) * r1, l31 = fma(-l30, l10, d3a.y) * r1;
+      const double e22 = fma(-l21, l21, fma(-l20, l20, d22));
+      if (!bad && !(e22 > 0.0)) bad = 3;
+      const double r2 = rsqrt(e22);
+      const double l32 = fma(-l31, l21, fma(-l30, l20, d3b.x)) * r2;
+      const double e33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, d3b.y)));
+      if (!bad && !(e33 > 0.0)) bad = 4;
+      const double r3 = rsqrt(e33);
+      if (bad) {
+        if (4 * J + bad <= M) *flag = 4 * J + bad;   // every panel owner writes the same value (padding cannot fail)
+      } else {
+        double* lg = lb + FFVD_PTILE * ti;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double x0 = a[r][0] * r0;
+          const double x1 = fma(-x0, l10, a[r][1]) * r1;
+          const double x2 = fma(-x1, l21, fma(-x0, l20, a[r][2])) * r2;
+          const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, a[r][3]))) * r3;
+          *reinterpret_cast<double2*>(lg + 4 * r) = make_double2(x0, x1);
+          *reinterpret_cast<double2*>(lg + 4 * r + 2) = make_double2(x2, x3);
+          const int i = i0 + r;
+          if (i < M) {                           // rows of L, final (a diagonal tile carries unused upper entries)
+            double* Ar = A + (size_t)i * lda + k0;
+            Ar[0] = x0;
+            if (k0 + 1 <= i) Ar[1] = x1;
+            if (k0 + 2 <= i) Ar[2] = x2;
+            if (k0 + 3 <= i) Ar[3] = x3;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (*flag) break;                          // CTA uniform
+    if (tk > J) {
+      const double* li = lb + FFVD_PTILE * ti;
+      const double* lk = lb + FFVD_PTILE * tk;
+      double Li[4][4], Lk[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double2 p01 = *reinterpret_cast<const double2*>(li + 4 * r), p23 = *reinterpret_cast<const double2*>(li + 4 * r + 2);
+        const double2 q01 = *reinterpret_cast<const double2*>(lk + 4 * r), q23 = *reinterpret_cast<const double2*>(lk + 4 * r + 2);
+        Li[r][0] = p01.x; Li[r][1] = p01.y; Li[r][2] = p23.x; Li[r][3] = p23.y;
+        Lk[r][0] = q01.x; Lk[r][1] = q01.y; Lk[r][2] = q23.x; Lk[r][3] = q23.y;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a[r][c] = fma(-Li[r][m], Lk[c][m], a[r][c]);
+      if (tk == J + 1 && ti == tk) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          *reinterpret_cast<double2*>(db + 4 * r) = make_double2(a[r][0], a[r][1]);
+          *reinterpret_cast<double2*>(db + 4 * r + 2) = make_double2(a[r][2], a[r][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  return *flag;
+}
+
+// Cholesky of the fast path: the panel form when its panel buffer fits the scratch region (the still unused X staging
+// matrix, M * ldx doubles), else the column form.
+__device__ __forceinline__ int chol_fast_smem(double* A, int lda, int M, double* cb, int cbs, double* scratch, int* flag) {
+#ifndef FFVD_CHOL_COLUMN_FORM
+  if (M >= 8) return chol_panel_smem(A, lda, M, scratch, flag);     // 18 (ceil(M/4) + 1) <= M * ldx
+#endif
+  return chol_owner_smem(A, lda, M, cb, cbs, flag);
+}
+
 // X = L^{-1} (lower) by forward substitution, L x_j = e_j; L (M x ldl) and the scratch dinv (M doubles) in SHARED memory.
 // Four lanes per column, eight columns per warp (j0 .. j0+7, j0 a multiple of 8).  Rows advance in blocks of four
 // ABSOLUTE rows i = 4B .. 4B+3, starting at the block that holds row j0 (entries above the diagonal come out as the
@@ -376,7 +511,7 @@ __global__ void __launch_bounds__(512) kzz_prep_kernel(const DevProblem* __restr
     A[(size_t)m * lda + n] = k;
   }
   __syncthreads();
-  const int st = (use_smem == 2) ? chol_owner_smem(Asm, M + 1, M, sh, Mp, &flag) : chol_inplace(A, lda, M, colbuf, &flag);
+  const int st = (use_smem == 2) ? chol_fast_smem(Asm, M + 1, M, sh, Mp, Asm + (size_t)M * (M + 1), &flag) : chol_inplace(A, lda, M, colbuf, &flag);
   if (tid == 0) P.status[d] = st;
   if (st != 0) return;
   if (use_smem == 2) {
@@ -765,7 +900,7 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
     }
   }
   __syncthreads();
-  const int st = fast ? chol_owner_smem(sh + 2 * Mp, M + 1, M, sh, Mp, &flag) : chol_inplace(H, ldh, M, sh, &flag);
+  const int st = fast ? chol_fast_smem(sh + 2 * Mp, M + 1, M, sh, Mp, sh + 2 * Mp + (size_t)M * (M + 1), &flag) : chol_inplace(H, ldh, M, sh, &flag);
   if (st != 0) {
     if (tid == 0) P.status[d] = st;
     return;

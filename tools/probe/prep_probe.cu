@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(512) phase_kernel(const double* Ain, int M, in
   for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) Asm[(idx / M) * (M + 1) + idx % M] = Ain[idx];
   __syncthreads();
   const long long t0 = clock64();
-  chol_owner_smem(Asm, M + 1, M, sh, Mp, &flag);
+  chol_fast_smem(Asm, M + 1, M, sh, Mp, Asm + (size_t)M * (M + 1), &flag);
   const long long t1 = clock64();
   double* Xs = Asm + (size_t)M * (M + 1);
   tri_inverse_smem(Asm, M + 1, M, Xs, (M + 1) & ~1, Xs + (size_t)M * ((M + 1) & ~1), X, XT, Mp);
