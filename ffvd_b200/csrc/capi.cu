@@ -440,6 +440,11 @@ static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X
 
 static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
   if (const char* e = getenv("FFVD_BLOCKED_CHOL")) return atoi(e) != 0;
+  if (chol_fast_fits(M, Mp, (size_t)c->max_smem)) return false;     // register-resident single-CTA path (M <= 119)
+  // Above it the single-CTA fallback (generic shared-memory Cholesky + substitution, latency bound: 0.41 ms at M = 120,
+  // 0.83 ms at M = 160 for four matrices) only beats the multi-kernel blocked path (0.35 ms at Mp = 128, 0.76 ms at
+  // Mp = 256, flat in M) for 129 <= M <= ~152 (tools/prep_paths.py)
+  if (Mp == 128 || M > 152) return true;
   const size_t full = (size_t)2 * Mp * 8 + (size_t)M * (M + 1) * 8;
   return (int)full > c->max_smem;          // single-CTA shared-memory path only while the matrix fits
 }

@@ -134,11 +134,12 @@ def test_ragged_shapes(env, T, M, D, S, collapsed):
     check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="T%d M%d" % (T, M))
 
 
-@pytest.mark.parametrize("M", (1, 2, 4, 8, 31, 32, 33, 64, 97, 116, 118, 119, 120, 121, 160, 161))
+@pytest.mark.parametrize("M", (1, 2, 4, 7, 8, 9, 31, 32, 33, 64, 97, 116, 118, 119, 120, 128, 129, 140, 152, 153, 168))
 @pytest.mark.parametrize("collapsed", (False, True))
 def test_small_m_factorisation_paths(env, M, collapsed):
-    """Every branch of the K(Z,Z) / H factorisation: the register-resident single-CTA path (M <= 119: one tile, partial
-    tiles, one warp, the 119 / 120 switch), the shared-memory path above it and the 160 / 161 switch to the blocked one."""
+    """Every branch of the K(Z,Z) / H factorisation: the register-resident single-CTA path (M <= 119: column form below
+    M = 8, panel form above, one tile, partial tiles, one warp), the blocked multi-kernel path for 120 <= M <= 128 and
+    M > 152, and the generic shared-memory single-CTA path in between."""
     from oracle import fixtures, ffvd_oracle as O
     prob = fixtures.synthetic_problem(T=37, M=M, D=2, S=2, seed=4242 + M)
     check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="M%d" % M)
