@@ -73,59 +73,31 @@ __device__ __forceinline__ void block_foreach(double (&c)[4][2][2], F f) {
 
 // Factor the diagonal block kb of every matrix, store L_kk (lower) back and inv(L_kk) into Dinv[b][kb].
 // grid (nbatch); block 256.  status[b] = first failing pivot (1-based, global index) if it is < M.
+// The 64 x 64 block goes through the register-resident routines of the small-M path (prep_post.cuh: panel Cholesky,
+// row-block forward substitution): this kernel is launched once per block column, strictly one after the other, and
+// with a textbook column loop (three barriers per column, one thread per column of the inverse) it cost ~100 us a time.
+// dynamic smem: L 64 x 65, X staging 64 x 64 (+ 64 spare: the panel scratch lives there during the factorisation), 64 x 1/L_ii
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, double* __restrict__ Dinv, int* __restrict__ status,
                                                           int kb, int M, int Mp) {
-  extern __shared__ __align__(16) double dsm[];          // 2 x 64 x 65 doubles (dynamic: above the 48 KB static limit)
-  double (*L)[65] = reinterpret_cast<double (*)[65]>(dsm);
-  double (*X)[65] = reinterpret_cast<double (*)[65]>(dsm + 64 * 65);
+  extern __shared__ __align__(16) double dsm[];
+  double* L = dsm;                                       // 64 x 65
+  double* Xs = dsm + 64 * 65;                            // 64 x 64
+  double* dinv = dsm + 2 * 64 * 65;                      // 64
   __shared__ int flag;
   const int b = blockIdx.x, tid = threadIdx.x, nblk = Mp / 64;
   double* Ab = A + (size_t)b * Mp * Mp + (size_t)(kb * 64) * Mp + kb * 64;
-  if (tid == 0) flag = 0;
-  for (int idx = tid; idx < 64 * 64; idx += 256) L[idx >> 6][idx & 63] = Ab[(size_t)(idx >> 6) * Mp + (idx & 63)];
+  for (int idx = tid; idx < 64 * 64; idx += 256) L[(idx >> 6) * 65 + (idx & 63)] = Ab[(size_t)(idx >> 6) * Mp + (idx & 63)];
   __syncthreads();
-  for (int j = 0; j < 64; ++j) {
-    const double piv = L[j][j];
-    if (!(piv > 0.0)) {
-      if (tid == 0) flag = j + 1;
-      break;
-    }
-    const double ljj = sqrt(piv), inv = 1.0 / ljj;
-    __syncthreads();
-    if (tid == 0) L[j][j] = ljj;
-    for (int i = j + 1 + tid; i < 64; i += 256) L[i][j] *= inv;
-    __syncthreads();
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int i = idx >> 6, k = idx & 63;
-      if (i > j && k > j && k <= i) L[i][k] = fma(-L[i][j], L[k][j], L[i][k]);
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  if (flag != 0) {
-    if (tid == 0 && kb * 64 + flag <= M && status[b] == 0) status[b] = kb * 64 + flag;
+  const int st = chol_panel_smem(L, 65, 64, Xs, &flag);
+  if (st != 0) {
+    if (tid == 0 && kb * 64 + st <= M && status[b] == 0) status[b] = kb * 64 + st;
     return;
   }
-  // X = L^{-1}: thread j < 64 owns column j (forward substitution)
-  if (tid < 64) {
-    const int j = tid;
-    for (int i = 0; i < 64; ++i) {
-      double s = (i == j) ? 1.0 : 0.0;
-      if (i >= j) {
-        for (int k = j; k < i; ++k) s = fma(-L[i][k], X[k][j], s);
-        X[i][j] = s / L[i][i];
-      } else {
-        X[i][j] = 0.0;
-      }
-    }
-  }
-  __syncthreads();
-  double* Db = Dinv + ((size_t)b * nblk + kb) * 64 * 64;
   for (int idx = tid; idx < 64 * 64; idx += 256) {
     const int i = idx >> 6, k = idx & 63;
-    Ab[(size_t)i * Mp + k] = (k <= i) ? L[i][k] : 0.0;
-    Db[idx] = X[i][k];
+    Ab[(size_t)i * Mp + k] = (k <= i) ? L[i * 65 + k] : 0.0;
   }
+  tri_inverse_smem(L, 65, 64, Xs, 64, dinv, Dinv + ((size_t)b * nblk + kb) * 64 * 64, nullptr, 64);
 }
 
 // Panel: A[i,kb] <- A[i,kb] * inv(L_kk)^T for block rows i > kb.  grid (nblk-kb-1, nbatch); block 256.

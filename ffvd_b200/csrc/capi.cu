@@ -441,12 +441,10 @@ static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X
 static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
   if (const char* e = getenv("FFVD_BLOCKED_CHOL")) return atoi(e) != 0;
   if (chol_fast_fits(M, Mp, (size_t)c->max_smem)) return false;     // register-resident single-CTA path (M <= 119)
-  // Above it the single-CTA fallback (generic shared-memory Cholesky + substitution, latency bound: 0.41 ms at M = 120,
-  // 0.83 ms at M = 160 for four matrices) only beats the multi-kernel blocked path (0.35 ms at Mp = 128, 0.76 ms at
-  // Mp = 256, flat in M) for 129 <= M <= ~152 (tools/prep_paths.py)
-  if (Mp == 128 || M > 152) return true;
-  const size_t full = (size_t)2 * Mp * 8 + (size_t)M * (M + 1) * 8;
-  return (int)full > c->max_smem;          // single-CTA shared-memory path only while the matrix fits
+  // Above it the multi-kernel blocked path (whose 64 x 64 diagonal blocks go through the same register-resident
+  // routines) wins at every M: 0.21 ms at Mp = 128, 0.48 ms at Mp = 256 for four matrices against 0.41 ... 0.83 ms of the
+  // generic single-CTA shared-memory routines (tools/prep_paths.py), which stay reachable with FFVD_BLOCKED_CHOL=0.
+  return true;
 }
 
 template <int KIND>
@@ -514,7 +512,7 @@ static int check_status(ffvd_ctx* c, const Layout& L) {
 static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X, double* XT, int* status, int nbatch,
                                  int M, int Mp) {
   const int nblk = Mp / 64;
-  const size_t sm_potrf = (size_t)2 * 64 * 65 * 8, sm_trtri = (size_t)64 * 68 * 8;
+  const size_t sm_potrf = (size_t)(2 * 64 * 65 + 64) * 8, sm_trtri = (size_t)64 * 68 * 8;
   CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf));
   CUDA_TRY(cudaFuncSetAttribute(trtri_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trtri));
   for (int kb = 0; kb < nblk; ++kb) {

@@ -426,7 +426,7 @@ __device__ void tri_inverse_smem(const double* __restrict__ L, int ldl, int M, d
   for (int r = warp; r < M; r += nw)
     for (int c = lane; c < M; c += 32) {
       X[(size_t)r * Mp + c] = (c <= r) ? Xs[(size_t)r * ldx + c] : 0.0;
-      XT[(size_t)r * Mp + c] = (c >= r) ? Xs[(size_t)c * ldx + r] : 0.0;
+      if (XT) XT[(size_t)r * Mp + c] = (c >= r) ? Xs[(size_t)c * ldx + r] : 0.0;
     }
   __syncthreads();
 }

@@ -138,8 +138,8 @@ def test_ragged_shapes(env, T, M, D, S, collapsed):
 @pytest.mark.parametrize("collapsed", (False, True))
 def test_small_m_factorisation_paths(env, M, collapsed):
     """Every branch of the K(Z,Z) / H factorisation: the register-resident single-CTA path (M <= 119: column form below
-    M = 8, panel form above, one tile, partial tiles, one warp), the blocked multi-kernel path for 120 <= M <= 128 and
-    M > 152, and the generic shared-memory single-CTA path in between."""
+    M = 8, panel form above, one tile, partial tiles, one warp) and the blocked multi-kernel path above it (one, two
+    and three 64-blocks, ragged last block)."""
     from oracle import fixtures, ffvd_oracle as O
     prob = fixtures.synthetic_problem(T=37, M=M, D=2, S=2, seed=4242 + M)
     check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="M%d" % M)
