@@ -18,24 +18,28 @@ __device__ __forceinline__ void block_gemm_acc(double (&c)[4][2][2], const doubl
                                                double (*Bs)[68]) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
+  // the next 16-deep slab travels (registers) while the current one is multiplied out of shared memory
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      ra[i] = A[(size_t)(idx >> 4) * lda + k0 + (idx & 15)];
+      rb[i] = TRANS_B ? B[(size_t)(idx >> 4) * ldb + k0 + (idx & 15)] : B[(size_t)(k0 + (idx >> 6)) * ldb + (idx & 63)];
+    }
+  };
+  if (K > 0) fetch(0);
   for (int k0 = 0; k0 < K; k0 += 16) {
     __syncthreads();
-    for (int idx = tid; idx < 64 * 16; idx += 256) {
-      const int r = idx >> 4, cc = idx & 15;
-      As[r][cc] = A[(size_t)r * lda + k0 + cc];
-    }
-    if (TRANS_B) {
-      for (int idx = tid; idx < 64 * 16; idx += 256) {
-        const int n = idx >> 4, kk = idx & 15;
-        Bs[kk][n] = B[(size_t)n * ldb + k0 + kk];
-      }
-    } else {
-      for (int idx = tid; idx < 16 * 64; idx += 256) {
-        const int kk = idx >> 6, n = idx & 63;
-        Bs[kk][n] = B[(size_t)(k0 + kk) * ldb + n];
-      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      As[idx >> 4][idx & 15] = ra[i];
+      if (TRANS_B) Bs[idx & 15][idx >> 4] = rb[i];
+      else Bs[idx >> 6][idx & 63] = rb[i];
     }
     __syncthreads();
+    if (k0 + 16 < K) fetch(k0 + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; kk += 4) {
       double a[4], b[2];
