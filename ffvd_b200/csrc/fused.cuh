@@ -51,7 +51,7 @@ struct Smem {
 // when SCR, to the CTA's L2 scratch copy that W = Kbar o K reads back).  Rows >= nvalid are NOT masked here (the
 // caller zeroes them in the rare partial tile); columns >= M get exact zeros through the per-column factor.
 // SE follows the reference's expansion (kernels_multi_output.py:163-182): -r^2/2 = x~.z~ - |x~|^2/2 - |z~|^2/2 with
-// x~ = x/l (sm.xsc, sm.xn2h) and z~ = z/l (ZTd rows 0..Din-1, row Din = -|z~|^2/2, zscale_kernel): one FMA per
+// x~ = x/l (sm.xsc, sm.xn2h) and z~ = z/l (ZTd rows 0..Din-1, row Din = -|z~|^2/2, written by hyper_kernel): one FMA per
 // (element, input dim); exp through the branch-free, lock-step exp_nonpos_n.  Linear: ZTd = Z~^T unscaled.
 // The ZTd rows stream from L2 through a 4- or 8-slot register ring (that many input dims ahead); the first rows of the next column
 // group are requested before the exp / store work of the current one.

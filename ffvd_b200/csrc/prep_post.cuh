@@ -923,29 +923,12 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
   }
 }
 
-// SE: per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded) and, in the last row, -1/2 |z~_m|^2 -- the
-// column half of the reference's expansion of the scaled squared distance (kernels_multi_output.py:163-182).
-// grid (nk, nprob); block 256.
-__global__ void __launch_bounds__(256) zscale_kernel(const DevProblem* __restrict__ probs) {
-  const DevProblem& P = probs[blockIdx.y];
-  const int d = blockIdx.x, M = P.M, Mp = P.Mp, Din = P.Din;
-  double* out = P.ZTs + (size_t)d * FFVD_ZTS_ROWS * Mp;
-  for (int m = threadIdx.x; m < Mp; m += blockDim.x) {
-    double a = 0.0;
-    for (int jd = 0; jd < FFVD_ZTS_ROWS - 1; ++jd) {
-      double z = 0.0;
-      if (m < M && jd < Din) z = P.Z[(size_t)m * Din + jd] * exp(-P.logl[(size_t)d * Din + jd]);
-      out[(size_t)jd * Mp + m] = z;                      // rows Din..39 stay zero: the tile kernel's padded steps read them
-      a = fma(z, z, a);
-    }
-    out[(size_t)(FFVD_ZTS_ROWS - 1) * Mp + m] = -0.5 * a;
-  }
-}
-
 // Per-evaluation scalars the tile kernel would otherwise re-derive (with FP64 exp calls) in every work item:
 // hyp[k] = {1/l_j^2, 1/l_j, v} per kernel, hq[d] = {Q, 1/Q, log Q} per output dim, UT = U^T zero padded.
 // grid (max(nk, D), nprob); block 128.
-// zs != 0 (SE only): also the work of zscale_kernel for kernel k (one launch less on the small-problem path).
+// zs != 0 (SE only): also the per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded, 40 rows) and, in
+// row 40, -1/2 |z~_m|^2 -- the column half of the reference's expansion of the scaled squared distance
+// (kernels_multi_output.py:163-182).  Skipped when the factors of the previous call are reused (Z, l unchanged).
 __global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int nk, int zs) {
   const DevProblem& P = probs[blockIdx.y];
   const int k = blockIdx.x, t = threadIdx.x, Din = P.Din, D = P.D, M = P.M, Mp = P.Mp;
@@ -1110,19 +1093,6 @@ __global__ void __launch_bounds__(1024) collapsed_vec_kernel(const DevProblem* _
 struct OutPtrs {
   double *nll, *terms, *g_Z, *g_U, *g_logv, *g_logl, *g_logQ, *g_C, *g_d, *g_logR;
 };
-
-__device__ __forceinline__ double block_sum_sq(const double* x, int n, double shift, double* red) {
-  double t = 0.0;
-  if (x)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double y = x[i] - shift; t = fma(y, y, t); }
-  t = warp_sum(t);
-  __syncthreads();
-  if (threadIdx.x == 0) *red = 0.0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) atomicAdd(red, t);
-  __syncthreads();
-  return *red;
-}
 
 // priors (dgp_model.py:105-143,252,326-334), -1/T scaling, term assembly (dgp_model.py:286-297).
 // grid (nprob); block 256.
