@@ -718,11 +718,15 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       kzz_bwd_fused_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
     }
   }
-  finalize_kernel<KIND><<<nprob, 256, 0, c->stream>>>(c->d_probs, c->d_outs, collapsed, flags); c->launches++;
-  if (!no_grads) {
-    size_t maxn = 0;
-    for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
-    scale_gx_kernel<<<dim3(grid1d(maxn), nprob), 256, 0, c->stream>>>(c->d_probs, flags); c->launches++;
+  {
+    int gx_blocks = 0;
+    if (!no_grads) {
+      size_t maxn = 0;
+      for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
+      gx_blocks = grid1d(maxn);
+    }
+    finalize_kernel<KIND><<<dim3(1 + gx_blocks, nprob), 256, 0, c->stream>>>(c->d_probs, c->d_outs, collapsed, flags, gx_blocks);
+    c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
   for (auto& t : pt)

@@ -1095,12 +1095,25 @@ struct OutPtrs {
 };
 
 // priors (dgp_model.py:105-143,252,326-334), -1/T scaling, term assembly (dgp_model.py:286-297).
-// grid (nprob); block 256.
+// grid (1 + gx_blocks, nprob); block 256: block 0 of a problem assembles the terms and the small gradients, the others
+// scale x-bar (gx_blocks = 0: no x-bar, e.g. FFVD_FLAG_NO_GRADS).
 template <int KIND>
 __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restrict__ probs, const OutPtrs* __restrict__ outs,
-                                                       int collapsed, int flags) {
-  const DevProblem& P = probs[blockIdx.x];
-  const OutPtrs& O = outs[blockIdx.x];
+                                                       int collapsed, int flags, int gx_blocks) {
+  const DevProblem& P = probs[blockIdx.y];
+  if (blockIdx.x > 0) {
+    // blocks 1 .. gx_blocks: the work of scale_gx_kernel (one launch less), g_X = -(raw - [t==0] X_0)/T in place
+    const size_t per = (size_t)(P.T + 1) * P.D, n = per * P.S;
+    const double scx = -1.0 / (double)P.T;
+    for (size_t i = (size_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < n; i += (size_t)gx_blocks * blockDim.x) {
+      const size_t r = i % per;
+      double v = P.gX[i];
+      if (r < (size_t)P.D && !(flags & 32)) v -= P.X[i];
+      P.gX[i] = scx * v;
+    }
+    return;
+  }
+  const OutPtrs& O = outs[blockIdx.y];
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
   const int M = P.M, Mp = P.Mp, D = P.D, Din = P.Din, Dy = P.Dy, S = P.S, T = P.T;
   const double sc = -1.0 / (double)T;
@@ -1173,19 +1186,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
   if (O.g_C) for (int i = tid; i < D * Dy; i += nth) O.g_C[i] = sc * (P.gC[i] - npri * P.C[i]);
   if (O.g_d) for (int i = tid; i < Dy; i += nth) O.g_d[i] = sc * (P.gd[i] - npri * P.dvec[i]);
   if (O.g_logR) for (int i = tid; i < Dy * Dy; i += nth) O.g_logR[i] = sc * ((i < Dy ? P.gR[i] : 0.0) - npri * P.logR[i]);
-}
-
-// g_X = -(raw - [t==0] X_0)/T, in place.   grid (blocks, nprob)
-__global__ void scale_gx_kernel(const DevProblem* __restrict__ probs, int flags) {
-  const DevProblem& P = probs[blockIdx.y];
-  const size_t per = (size_t)(P.T + 1) * P.D, n = per * P.S;
-  const double sc = -1.0 / (double)P.T;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i % per;
-    double v = P.gX[i];
-    if (r < (size_t)P.D && !(flags & 32)) v -= P.X[i];
-    P.gX[i] = sc * v;
-  }
 }
 
 }  // namespace ffvd
