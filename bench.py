@@ -217,6 +217,7 @@ def main():
     h = make_host_data(T, M, D, S, seed=1000 + rank)
     P = {k: torch.as_tensor(v, dtype=torch.float64, device=dev).contiguous() for k, v in h.items()}
     X_host = torch.as_tensor(h["X"]).pin_memory()
+    torch.manual_seed(4321 + rank)                  # fixed noise: nll_mean is comparable from run to run
     noise_host = torch.randn(X_host.shape, dtype=torch.float64).pin_memory()
     noise_X = noise_host.to(dev)                    # pre-filled device noise: generation is outside the timed region
     noise_U = torch.randn(P["U"].shape, dtype=torch.float64, device=dev)
