@@ -487,7 +487,11 @@ static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse =
 
 static int launch_bgemm(ffvd_ctx* c, double* C, const double* A, const double* B, int n, double alpha, int batch,
                         BatchMap mC, BatchMap mA, BatchMap mB) {
-  bgemm_nn_kernel<<<dim3(n / 64, n / 64, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB);
+  // half-height tiles while the launch would not fill the GPU with 64 x 64 ones
+  if ((long long)(n / 64) * (n / 64) * batch < c->num_sms)
+    bgemm_nn_kernel<32><<<dim3(n / 64, n / 32, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB);
+  else
+    bgemm_nn_kernel<64><<<dim3(n / 64, n / 64, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return FFVD_OK;

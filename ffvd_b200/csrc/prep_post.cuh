@@ -625,30 +625,37 @@ __global__ void __launch_bounds__(256) collapsed_logdet_kernel(const DevProblem*
 struct BatchMap { int div, mul, mod; };   // matrix index = (z / div) * mul + (z % mod)
 __device__ __forceinline__ size_t bmap(const BatchMap& m, int z) { return (size_t)(z / m.div) * m.mul + (z % m.mod); }
 
+// TM = 64 or 32 rows of C per CTA (32: twice the CTAs, for launches that would leave most SMs idle -- a 128^3 product
+// per matrix of a 4-matrix batch is 16 CTAs of 64 x 64, each bound by its own DMMA throughput).
+template <int TM>
 __global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, const double* __restrict__ A,
                                                         const double* __restrict__ B, int n, double alpha,
                                                         BatchMap mC, BatchMap mA, BatchMap mB) {
-  // 64 x 64 tile of C per CTA, k in steps of 32.  The next step's A / B slabs are fetched into registers (4 + 4
-  // 16-byte loads per thread, all in flight together) while the current one is multiplied out of shared memory: at
-  // n = 128 the kernel is four L2 round trips long instead of the 64 serialised ones of a load -> store loop.
-  constexpr int BK = 32;
-  __shared__ __align__(16) double As[64][BK + 4];     // stride 36 = 4 mod 16: fragment reads conflict free per half-warp
+  // TM x 64 tile of C per CTA, k in steps of 32.  The next step's A / B slabs are fetched into registers (16-byte
+  // loads, all in flight together) while the current one is multiplied out of shared memory: at n = 128 the kernel is
+  // four L2 round trips long instead of the 64 serialised ones of a load -> store loop.
+  constexpr int BK = 32, NI = TM / 16, NA = TM / 16;   // NI: 8-row blocks per warp, NA: A loads per thread
+  __shared__ __align__(16) double As[TM][BK + 4];     // stride 36 = 4 mod 16: fragment reads conflict free per half-warp
   __shared__ __align__(16) double Bs[BK][68];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps: each 32 x 16
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps: each (TM/2) x 16
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
   A += bmap(mA, blockIdx.z) * n * n; B += bmap(mB, blockIdx.z) * n * n; C += bmap(mC, blockIdx.z) * n * n;
-  double c[4][2][2];
+  double c[NI][2][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
-  double2 ra[4], rb[4];
+  double2 ra[NA], rb[4];
   auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + 256 * i;
+      ra[i] = *reinterpret_cast<const double2*>(A + (size_t)(m0 + (idx >> 4)) * n + k0 + 2 * (idx & 15));
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + 256 * i;
-      ra[i] = *reinterpret_cast<const double2*>(A + (size_t)(m0 + (idx >> 4)) * n + k0 + 2 * (idx & 15));
       rb[i] = *reinterpret_cast<const double2*>(B + (size_t)(k0 + (idx >> 5)) * n + n0 + 2 * (idx & 31));
     }
   };
@@ -656,31 +663,35 @@ __global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, c
   for (int k0 = 0; k0 < n; k0 += BK) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NA; ++i) {
       const int idx = tid + 256 * i;
       *reinterpret_cast<double2*>(&As[idx >> 4][2 * (idx & 15)]) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
       *reinterpret_cast<double2*>(&Bs[idx >> 5][2 * (idx & 31)]) = rb[i];
     }
     __syncthreads();
     if (k0 + BK < n) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double a[4], b[2];
+      double a[NI], b[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[wm * 32 + 8 * i + g][kk + q];
+      for (int i = 0; i < NI; ++i) a[i] = As[wm * (TM / 2) + 8 * i + g][kk + q];
 #pragma unroll
       for (int j = 0; j < 2; ++j) b[j] = Bs[kk + q][wn * 16 + 8 * j + g];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      double* p = C + (size_t)(m0 + wm * 32 + 8 * i + g) * n + n0 + wn * 16 + 8 * j + 2 * q;
+      double* p = C + (size_t)(m0 + wm * (TM / 2) + 8 * i + g) * n + n0 + wn * 16 + 8 * j + 2 * q;
       *reinterpret_cast<double2*>(p) = make_double2(alpha * c[i][j][0], alpha * c[i][j][1]);
     }
 }
