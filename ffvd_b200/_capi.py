@@ -35,6 +35,10 @@ class FFVDError(RuntimeError):
         self.status = status
 
 
+class StaleFactorsError(FFVDError):
+    """FLAG_REUSE_KZZ was set although Z / logv / logl changed since the factors were built (status -8)."""
+
+
 class NotPositiveDefinite(FloatingPointError):
     """Raised when a Cholesky factorisation fails (the reference raises InvalidArgumentError)."""
 
@@ -132,6 +136,8 @@ def _check(status: int):
         raise NotPositiveDefinite(status, msg)
     if status in (-1, -2, -3, -4):
         raise ValueError("libffvd_b200 status %d: %s" % (status, msg))
+    if status == -8:
+        raise StaleFactorsError(status, msg)
     raise FFVDError(status, msg)
 
 

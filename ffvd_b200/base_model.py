@@ -94,7 +94,10 @@ class BaseModel(object):
         """One TF1-Adam step on the trainable set, with the SG-HMC variables fed from a random
         window entry (the feed is temporary, as in the reference's feed_dict)."""
         import torch
-        _, lr = self.get_minibatch(self.global_step)
+        # base_model.py:945: get_minibatch() is called WITHOUT an argument, so global_step is always 1 and the Adam rate is
+        # the constant 0.003 * 0.95**(1/1000); set `model.decay_lr = True` for the decaying schedule the formula
+        # suggests (an opt-in, not the reference's behaviour)
+        _, lr = self.get_minibatch(self.global_step) if getattr(self, "decay_lr", False) else self.get_minibatch()
         saved = {}
         self._kzz_clean = False                       # the window feed and the Adam step may move Z / hyper-parameters
         if self.window:

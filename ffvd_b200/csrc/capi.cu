@@ -76,6 +76,7 @@ extern "C" const char* ffvd_status_string(int s) {
     case FFVD_E_CUDA: return "CUDA runtime error";
     case FFVD_E_UNSUPPORTED: return "option not supported by this build";
     case FFVD_E_LIMIT: return "size beyond this build's limits";
+    case FFVD_E_STALE: return "FFVD_FLAG_REUSE_KZZ: Z / kernel hyper-parameters changed since the cached factors were built";
     default: return s > 0 ? "matrix not positive definite (status = 1-based failing pivot)" : "unknown status";
   }
 }
@@ -88,7 +89,7 @@ extern "C" int ffvd_ctx_create(int device, void* stream, ffvd_ctx** out) {
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) return fail(FFVD_E_DEVICE, "libffvd_b200 requires an sm_100a (B200) device");
+  if (prop.major != 10) return fail(FFVD_E_DEVICE, "libffvd_b200 requires an sm_100a (B200) device");
   ffvd_ctx* c = new ffvd_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
@@ -250,7 +251,7 @@ struct Layout {
   long long sumS;
   bool collapsed;
   size_t off_ZT, off_ZTs, off_hyp, off_hq, off_UT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
-      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, total;
+      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, off_guard, total;
   int nfac;                        // matrices in the blocked-factorisation pools: nprob * max(nk, nb)
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
   size_t small_per;                // doubles of small accumulators per problem
@@ -258,8 +259,9 @@ struct Layout {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int Din, int Dy, long long sumS, bool collapsed,
-                          bool need_acc) {
+static const int kMaxCtasPerSm = 2;      // co-resident fused CTAs per SM the K-tile scratch is sized for (FFVD_MINB <= 2)
+static Layout make_layout(const ffvd_ctx* c, int nprob, int nb, int nk, int D, int M, int Mp, int Din, int Dy, long long sumS,
+                          bool collapsed, bool need_acc) {
   Layout L;
   L.nprob = nprob; L.nb = nb; L.nk = nk; L.D = D; L.M = M; L.Mp = Mp; L.Din = Din; L.Dy = Dy; L.sumS = sumS; L.collapsed = collapsed;
   size_t o = 0;
@@ -270,7 +272,8 @@ static Layout make_layout(int nprob, int nb, int nk, int D, int M, int Mp, int D
   L.off_hyp = take((size_t)nprob * nk * 72 * 8);
   L.off_hq = take((size_t)nprob * D * 4 * 8);
   L.off_UT = take((size_t)nprob * D * Mp * 8);
-  L.off_kscr = take((size_t)320 * 64 * Mp * 8);          // per-CTA K-tile scratch of the fused kernel (<= 2 CTAs / SM)
+  L.off_kscr = take((size_t)c->num_sms * kMaxCtasPerSm * 64 * Mp * 8);   // per-CTA K-tile scratch of the fused kernel
+  L.off_guard = take((size_t)nprob * 4 * 8);             // REUSE_KZZ content guard (outside the per-call zero region)
   L.off_Linv = take((size_t)nprob * nk * mm);
   L.off_LinvT = take((size_t)nprob * nk * mm);
   L.off_utmp = take((size_t)nprob * M * D * 8);
@@ -317,7 +320,7 @@ static int ensure_arena(ffvd_ctx* c, const Layout& L) {
     CUDA_TRY(cudaMalloc((void**)&c->d_outs, sizeof(OutPtrs) * L.nprob));
     c->probs_cap = L.nprob;
   }
-  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk) + (size_t)L.nfac;
+  const size_t ns = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk) + (size_t)L.nfac + 2 + (size_t)L.nprob * 8;   // + guard words
   if (c->h_status_cap < ns) {
     if (c->h_status) CUDA_TRY(cudaFreeHost(c->h_status));
     CUDA_TRY(cudaMallocHost((void**)&c->h_status, ns * sizeof(int)));
@@ -356,6 +359,7 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   P.gR = sm;
   P.terms_raw = (double*)(a + L.off_terms) + (size_t)s_begin * FFVD_NTERMS_RAW;
   P.status = (int*)(a + L.off_status) + (size_t)p * (L.nb > L.nk ? L.nb : L.nk);
+  P.guard = (unsigned long long*)(a + L.off_guard) + (size_t)p * 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -402,6 +406,7 @@ static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs,
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * cfg.nw, smem));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > cfg.minb) per_sm = cfg.minb;
+  if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;           // the K-tile scratch holds num_sms * kMaxCtasPerSm tiles
   const long long cap = (long long)c->num_sms * per_sm;      // persistent grid: every CTA resident
   long long grid = total_items < cap ? total_items : cap;
   if (grid < 1) return FFVD_OK;
@@ -457,11 +462,13 @@ static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse =
   const bool reused = reuse && c->kzz_valid && key == c->kzz_key;     // factors of the previous call are still in the arena
   if (ltu_done) *ltu_done = false;
   // hyp / hq / U^T every call (U changes under REUSE_KZZ); the scaled Z~^T (SE) only when the factors are rebuilt
-  hyper_kernel<<<dim3(L.nk > L.D ? L.nk : L.D, L.nprob), 128, 0, c->stream>>>(c->d_probs, KIND, L.nk, (KIND == 0 && !reused) ? 1 : 0);
+  // content guard: record the hash of Z / logv / logl when the factors are (re)built, verify it when they are reused
+  hyper_kernel<<<dim3(L.nk > L.D ? L.nk : L.D, L.nprob), 128, 0, c->stream>>>(c->d_probs, KIND, L.nk, (KIND == 0 && !reused) ? 1 : 0,
+                                                                              reused ? 2 : 1);
   c->launches++;
   if (reused) return FFVD_OK;
-  c->kzz_valid = true;
-  c->kzz_key = key;
+  c->kzz_valid = true;          // check_status clears it again if the factorisation fails; ASYNC callers are covered by the
+  c->kzz_key = key;             // device-side guard (finalize_kernel drops the record of a failed factorisation)
   if (use_blocked(c, L.M, L.Mp)) {
     double* Lfac = (double*)(c->arena + L.off_Lfac);
     const size_t nel = (size_t)L.Mp * L.Mp > (size_t)32 * L.Mp ? (size_t)L.Mp * L.Mp : (size_t)32 * L.Mp;
@@ -501,9 +508,18 @@ static int check_status(ffvd_ctx* c, const Layout& L) {
   const size_t n1 = (size_t)L.nprob * (L.nb > L.nk ? L.nb : L.nk), n2 = (size_t)L.nfac;
   CUDA_TRY(cudaMemcpyAsync(c->h_status, c->arena + L.off_status, n1 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->h_status + n1, c->arena + L.off_status2, n2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long* hg = (unsigned long long*)(c->h_status + n1 + n2 + ((n1 + n2) & 1));
+  CUDA_TRY(cudaMemcpyAsync(hg, c->arena + L.off_guard, (size_t)L.nprob * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int p = 0; p < L.nprob; ++p)
+    if (hg[(size_t)p * 4 + 3] != 0) {
+      c->kzz_valid = false;
+      return fail(FFVD_E_STALE, "FFVD_FLAG_REUSE_KZZ: the contents of Z / logv / logl differ from those the cached Cholesky factors "
+                                "were built from (results of this call are NaN); call again without the flag");
+    }
   for (size_t i = 0; i < n1 + n2; ++i)
     if (c->h_status[i] != 0) {
+      c->kzz_valid = false;      // never reuse the factors of a failed factorisation
       char buf[160];
       snprintf(buf, sizeof buf, "Cholesky failed: matrix %zu not positive definite at pivot %d", i < n1 ? i : i - n1, c->h_status[i]);
       g_last_error = buf;
@@ -620,7 +636,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   if (Mp < 0) return fail(FFVD_E_LIMIT, "M > 2048 is not supported by this build");
   const bool no_grads = (flags & FFVD_FLAG_NO_GRADS) != 0;
   const int nb = collapsed ? pt[0].S * D : D;
-  Layout L = make_layout(nprob, nb, D, D, M, Mp, Din, Dy, sumS, collapsed != 0, true);
+  Layout L = make_layout(c, nprob, nb, D, D, M, Mp, Din, Dy, sumS, collapsed != 0, true);
   TRY(ensure_arena(c, L));
   long long pairs = 0, maxT = 0;
   for (auto& t : pt) { pairs += (long long)D * t.S; maxT = t.T > maxT ? t.T : maxT; }
@@ -729,7 +745,8 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
       gx_blocks = grid1d(maxn);
     }
-    finalize_kernel<KIND><<<dim3(1 + gx_blocks, nprob), 256, 0, c->stream>>>(c->d_probs, c->d_outs, collapsed, flags, gx_blocks);
+    finalize_kernel<KIND><<<dim3(1 + gx_blocks, nprob), 256, 0, c->stream>>>(c->d_probs, c->d_outs, collapsed, flags, gx_blocks,
+                                                                             nb > D ? nb : D, (const int*)(c->arena + L.off_status2), L.nfac);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -867,7 +884,7 @@ static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, co
   if (Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
   const int Mp = pad_M(M);
   if (Mp < 0) return fail(FFVD_E_LIMIT, "M > 2048 is not supported by this build");
-  L = make_layout(1, need_scratch ? R : nk, nk, R, M, Mp, Din, 1, 1, false, need_scratch);
+  L = make_layout(c, 1, need_scratch ? R : nk, nk, R, M, Mp, Din, 1, 1, false, need_scratch);
   TRY(ensure_arena(c, L));
   memset(&P, 0, sizeof P);
   P.Z = tZ.d; P.logv = tv.d; P.logl = tl.d;
@@ -999,7 +1016,7 @@ extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLM
     CUDA_TRY(cudaMemcpyAsync(c->d_probs, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
   }
   // U (possibly un-whitened) was bound after setup_zside ran the prep kernels: refresh U^T
-  hyper_kernel<<<dim3(nk > R ? nk : R, 1), 128, 0, c->stream>>>(c->d_probs, kind, nk, 0); c->launches++;
+  hyper_kernel<<<dim3(nk > R ? nk : R, 1), 128, 0, c->stream>>>(c->d_probs, kind, nk, 0, 0); c->launches++;
   if (kind == FFVD_KERNEL_SE) TRY((launch_fused<0, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   else TRY((launch_fused<1, MODE_COND>(c, P.Mp, P.Din, c->d_probs, 1, P.nitems)));
   int st = FFVD_OK;

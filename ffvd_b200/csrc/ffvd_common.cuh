@@ -52,6 +52,8 @@ struct DevProblem {
   double *Hx, *HxT;    // [S*D][Mp][Mp] collapsed scratch: L_H^{-1}, L_H^{-T} / Mat' S
   double *rs;          // [nb][Mp] row sums of Wz
   int *status;         // [D] 0 ok, else 1-based failing pivot
+  unsigned long long *guard;   // [4] content guard of the cached K(Z,Z) factors (FFVD_FLAG_REUSE_KZZ): running hash of
+                               //     Z / logv / logl, hash at factorisation time, block counter, stale flag (hyper_kernel)
   double *cond_mean, *cond_var;   // conditional(): (N,R) outputs
   const double *qmat;  // conditional() with q_sqrt: qmode 3 -> [nq][Mp][Mp] zero padded factors (var += |Q^T a|^2);
                        //                            qmode 2 -> [M][R] per-point scales      (var += sum (q_m a_m)^2)
@@ -76,15 +78,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // so that the FP64 pipe always has N independent FMAs to issue (the pipe is narrow: two warps per scheduler cannot
 // hide its latency with one dependent Horner chain each).
 // x = n ln2 + r, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^n applied to the exponent bits.
-// <= 1 ulp from the correctly rounded result on [-700, 1e-9] (checked on the host against libm).  Valid for
-// x >= -1e6 (the low word of t must hold n); below -708 the result saturates near 1e-308, i.e. 0 at the scale of
-// every quantity the kernels form.
+// <= 1 ulp from the correctly rounded result on [-700, 1e-9] (checked on the host against libm).  The argument is
+// clamped at -745 first (one DMNMX): the low word of t must hold n, and without the clamp an argument below ~-1.5e9
+// (|x/l - z/l| > 5e4, e.g. a diverging chain on logl) would wrap n and return a huge / Inf / NaN kernel value instead of
+// 0.  Below -708 the result saturates near 1e-308, i.e. 0 at the scale of every quantity the kernels form.
 template <int N>
 __device__ __forceinline__ void exp_nonpos_n(double (&x)[N]) {
   double r[N], p[N];
   int n[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
+    x[i] = fmax(x[i], -745.0);
     const double t = fma(x[i], 1.4426950408889634, 6755399441055744.0);
     n[i] = max(__double2loint(t), -1022);      // x < -708: the scale saturates at 2^-1022 (result ~ 1e-308 ~ 0)
     const double nd = t - 6755399441055744.0;

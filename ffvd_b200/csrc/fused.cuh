@@ -792,7 +792,9 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
               double sq = 0.0;
 #pragma unroll
               for (int w = 0; w < 8; ++w) sq += sm.rowpart[(2 * 8 + w) * BT + r];
-              P.cond_mean[(size_t)(t0 + r) * D + d] = su;
+              // REUSE_KZZ content guard (hyper_kernel): factors that do not belong to this Z poison the result
+              const bool stale = P.guard && P.guard[3] != 0;
+              P.cond_mean[(size_t)(t0 + r) * D + d] = stale ? __longlong_as_double(0x7ff8000000000000ll) : su;
               P.cond_var[(size_t)(t0 + r) * D + d] = sig2 + sq;
             } else if (MODE == MODE_COLLAPSED_P1) {
               const double delta = xn - xd;

@@ -940,7 +940,18 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
 // zs != 0 (SE only): also the per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded, 40 rows) and, in
 // row 40, -1/2 |z~_m|^2 -- the column half of the reference's expansion of the scaled squared distance
 // (kernels_multi_output.py:163-182).  Skipped when the factors of the previous call are reused (Z, l unchanged).
-__global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int nk, int zs) {
+// guard != 0: content guard of FFVD_FLAG_REUSE_KZZ.  Every block adds the (order-independent) hash of its slice of Z, logv,
+// logl to P.guard[0]; the last block to finish either records it as the hash the factors were built from (guard == 1) or
+// compares it with that record (guard == 2, the factors are being reused) and raises the sticky stale flag P.guard[3] on a
+// mismatch -- the evaluation then returns NaN (finalize_kernel / the COND statistics) and the next synchronising call
+// FFVD_E_STALE, instead of silently using the factors of another Z.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+__global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int nk, int zs, int guard) {
   const DevProblem& P = probs[blockIdx.y];
   const int k = blockIdx.x, t = threadIdx.x, Din = P.Din, D = P.D, M = P.M, Mp = P.Mp;
   __shared__ double sils[32];
@@ -981,6 +992,29 @@ __global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int
     }
     if (P.U)
       for (int j = t; j < Mp; j += blockDim.x) P.UT[(size_t)k * Mp + j] = (j < M) ? P.U[(size_t)j * D + k] : 0.0;
+  }
+  if (guard && P.guard) {
+    const int nz = M * Din, nl = (kind == 0) ? nk * Din : 0, ntot = nz + nk + nl;
+    unsigned long long h = 0;
+    for (int i = k * blockDim.x + t; i < ntot; i += gridDim.x * blockDim.x) {
+      const double v = (i < nz) ? P.Z[i] : (i < nz + nk ? P.logv[i - nz] : P.logl[i - nz - nk]);
+      h += mix64((unsigned long long)__double_as_longlong(v) ^ mix64((unsigned long long)i + 1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((t & 31) == 0 && h) atomicAdd(P.guard + 0, h);
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      const unsigned long long done = atomicAdd(P.guard + 2, 1ull);
+      if (done == (unsigned long long)gridDim.x - 1) {
+        __threadfence();
+        const unsigned long long cur = atomicAdd(P.guard + 0, 0ull) | 1ull;      // never 0: 0 marks "no valid factors"
+        if (guard == 1) { P.guard[1] = cur; P.guard[3] = 0; }
+        else if (P.guard[1] != cur) P.guard[3] = 1;
+        P.guard[0] = 0; P.guard[2] = 0;
+      }
+    }
   }
 }
 
@@ -1110,7 +1144,8 @@ struct OutPtrs {
 // scale x-bar (gx_blocks = 0: no x-bar, e.g. FFVD_FLAG_NO_GRADS).
 template <int KIND>
 __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restrict__ probs, const OutPtrs* __restrict__ outs,
-                                                       int collapsed, int flags, int gx_blocks) {
+                                                       int collapsed, int flags, int gx_blocks, int nstatus,
+                                                       const int* __restrict__ status2, int nstatus2) {
   const DevProblem& P = probs[blockIdx.y];
   if (blockIdx.x > 0) {
     // blocks 1 .. gx_blocks: the work of scale_gx_kernel (one launch less), g_X = -(raw - [t==0] X_0)/T in place
@@ -1167,6 +1202,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
   }
   double pz = -0.5 * tot[0], ph = -0.5 * (tot[1] + tot[2]), pu = -0.5 * tot[3], hyp = -0.5 * (((tot[4] + tot[5]) + tot[6]) + tot[7]);
   if (!shared_priors) pz = ph = pu = hyp = 0.0;
+  const bool stale = P.guard && P.guard[3] != 0;
+  if (tid == 0 && P.guard) {
+    // a failed factorisation must not be reusable (FFVD_FLAG_ASYNC callers never read the status): drop the record
+    bool bad = false;
+    for (int i = 0; i < nstatus; ++i) bad = bad || P.status[i] != 0;
+    for (int i = 0; i < nstatus2; ++i) bad = bad || status2[i] != 0;        // blocked path: any matrix of the batch
+    if (bad) P.guard[1] = 0;
+  }
   // per-sample terms: a warp per sample (D <= 31 values of x_0)
   for (int s = warp; s < S; s += nw) {
     double x0 = (x0_prior && lane < D) ? P.X[(size_t)s * (T + 1) * D + lane] : 0.0;
@@ -1181,6 +1224,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
       t[3] = sc * r[FFVD_RAW_TRACE];
       t[4] = collapsed ? sc * r[FFVD_RAW_LOGDET] : 0.0;
       t[5] = collapsed ? sc * r[FFVD_RAW_QUAD] : 0.0;
+      if (stale) {                  // FFVD_FLAG_REUSE_KZZ with a Z / hyper-parameter content that the cached factors were not built from
+#pragma unroll
+        for (int k = 0; k < 6; ++k) t[k] = __longlong_as_double(0x7ff8000000000000ll);
+      }
       if (O.terms) for (int k = 0; k < 6; ++k) O.terms[(size_t)s * 6 + k] = t[k];
       if (O.nll) O.nll[s] = ((t[0] + t[1]) + (t[2] + t[3])) + (t[4] + t[5]);
     }

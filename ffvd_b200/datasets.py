@@ -69,3 +69,19 @@ def arguments_from_factnonlin(factnonlin):
 CASE_TABLE = {1: (True, True, True, False, False), 2: (False, False, True, False, False), 3: (False, False, False, False, False),
               4: (True, False, True, True, False), 5: (False, False, True, True, False), 6: (True, True, True, False, True),
               7: (False, False, False, False, False)}
+
+
+def load_packed_problems(path):
+    """The packed copy of the 95 bundled warm starts x 6 datasets (`tests/golden/fixtures.npz`, written by
+    `tests/golden/make_fixtures.py` with the `FFVD_Main.py:212-254` mapping) as a list of problem dicts
+    {X, Z, U, logv, logl, logQ, C, d, logR, Y, ctrl} of NumPy arrays -- BASELINE configs[3]'s many-small-chains batch."""
+    z = np.load(path, allow_pickle=False)
+    out = []
+    for nm in [str(n) for n in z["names"]]:
+        ds = nm.split("/")[0]
+        p = {k: np.array(z["%s__%s" % (nm, k)], dtype=np.float64) for k in ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR")}
+        p["Y"] = np.array(z["data__%s__Y" % ds], dtype=np.float64)
+        p["ctrl"] = np.array(z["data__%s__ctrl" % ds], dtype=np.float64)
+        p["name"] = nm
+        out.append(p)
+    return out

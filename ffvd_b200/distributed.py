@@ -3,6 +3,11 @@ no data-path collective; a single all-reduce of the packed shared-parameter grad
 scalar objective per evaluation.  `torch.distributed` (NCCL on GPUs, gloo in the
 CPU tests) is the transport; x-bar never leaves its owner.
 
+Replicated parameters (Z, U, kernel hyper-parameters, logQ, C, d, logR) are updated redundantly on every rank from the
+all-reduced gradient.  When such a parameter is SG-HMC sampled its injected noise must therefore be IDENTICAL on every
+rank (draw it from a rank-independent seed, or broadcast it from rank 0 -- `shared_noise`); only the noise of the sharded
+X is per rank.  Otherwise the replicas drift apart after the first update and the ranks evaluate different models.
+
 When there are fewer trajectories than GPUs (one long chain), `time_block` / `evaluate_time_sharded` shard T instead
 (SURVEY 8e): contiguous blocks of transitions with a one-row halo, uncollapsed form."""
 from __future__ import annotations
@@ -22,6 +27,13 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 def round_robin(n: int, rank: int, world: int) -> List[int]:
     """Whole independent chains dealt round-robin (BASELINE config 4); no collective needed."""
     return list(range(rank, n, world))
+
+
+def shared_noise(shape, step: int, seed: int = 0, device=None):
+    """N(0,1) noise for a REPLICATED parameter: a function of (seed, step) only, so every rank draws the same tensor."""
+    import torch
+    g = torch.Generator(device=device if device is not None else "cpu").manual_seed((int(seed) * 1000003 + int(step)) & 0x7FFFFFFFFFFFFFFF)
+    return torch.randn(tuple(shape), dtype=torch.float64, device=device, generator=g)
 
 
 def pack(outputs: Dict[str, object], names: Sequence[str] = SHARED):

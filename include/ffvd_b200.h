@@ -50,6 +50,7 @@ typedef struct DLManagedTensor {
 #define FFVD_E_CUDA          -5   /* CUDA runtime error (message in ffvd_last_error)        */
 #define FFVD_E_UNSUPPORTED   -6   /* valid reference option that this build does not cover  */
 #define FFVD_E_LIMIT         -7   /* size beyond this build's limits (M > 2048, Din > 31)   */
+#define FFVD_E_STALE         -8   /* FFVD_FLAG_REUSE_KZZ although Z / logv / logl changed (results of the call are NaN) */
 
 #define FFVD_KERNEL_SE      0     /* kernels_multi_output.py:240-247 SquaredExponential (ARD) */
 #define FFVD_KERNEL_LINEAR  1     /* kernels.py:250-281 LinearK (scalar variance)              */
@@ -62,7 +63,10 @@ typedef struct DLManagedTensor {
 /* The caller asserts that Z, logv, logl, the kernel kind, the jitter and every shape are unchanged since the previous
  * ffvd_nll_grads_* call on this context: K(Z,Z)'s Cholesky factor, L^{-1}, L^{-T} and the scaled inducing inputs are
  * reused instead of recomputed (SG-HMC chains that sample only X / U evaluate 21 times per outer iteration with fixed Z
- * and hyper-parameters, base_model.py:915-933).  Ignored when the context holds no factors for these shapes. */
+ * and hyper-parameters, base_model.py:915-933).  Ignored when the context holds no factors for these shapes.
+ * The assertion is CHECKED on the device: a 64-bit content hash of Z / logv / logl is recorded when the factors are built
+ * and compared on every reusing call; on a mismatch the call's nll / terms (conditional: mean / var) are NaN and the next
+ * call that synchronises returns FFVD_E_STALE.  The factors of a failed factorisation are never reused. */
 #define FFVD_FLAG_REUSE_KZZ       64
 /* time-sharded evaluation of ONE trajectory (ffvd_b200/distributed.py: a block of consecutive transitions per GPU):
  * every block is an ordinary problem whose nll / gradients are then rescaled by T_block / T_total by the caller */
