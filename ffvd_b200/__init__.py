@@ -6,8 +6,8 @@ conditionals_multi_output, likelihoods, dgp_model, base_model.  All arithmetic r
 hand-written CUDA through the C ABI in include/ffvd_b200.h (ffvd_b200/_capi.py); there is no
 CPU fallback.
 """
-from ._capi import (Context, FFVDError, NotPositiveDefinite, KERNEL_SE, KERNEL_LINEAR, FLAG_PRIOR_Z_NORMAL,
+from ._capi import (Context, FFVDError, NotPositiveDefinite, StaleFactorsError, KERNEL_SE, KERNEL_LINEAR, FLAG_PRIOR_Z_NORMAL,
                     FLAG_PRIOR_ONCE, FLAG_NO_GRADS, FLAG_ASYNC, FLAG_NO_SHARED_PRIORS, FLAG_NO_X0_PRIOR, FLAG_REUSE_KZZ, LIB_PATH, load_library)
 
-__all__ = ["Context", "FFVDError", "NotPositiveDefinite", "KERNEL_SE", "KERNEL_LINEAR", "FLAG_PRIOR_Z_NORMAL",
+__all__ = ["Context", "FFVDError", "NotPositiveDefinite", "StaleFactorsError", "KERNEL_SE", "KERNEL_LINEAR", "FLAG_PRIOR_Z_NORMAL",
            "FLAG_PRIOR_ONCE", "FLAG_NO_GRADS", "FLAG_ASYNC", "FLAG_NO_SHARED_PRIORS", "FLAG_NO_X0_PRIOR", "FLAG_REUSE_KZZ", "LIB_PATH", "load_library"]

@@ -39,7 +39,10 @@ class Model(object):
             raise Exception("Invalid prior type")
 
     def _fit(self, Y_train, tensorboard_savepath, dataname, fileid, lik, X_train, Ystd, kernel_type, kernel_train_flag,
-             Y_test=None, data_uu=None, progress=None, **kwargs):
+             Y_test=None, data_uu=None, progress=None, sghmc_noise=None, window_index=None, **kwargs):
+        """`sghmc_noise(it, k)` -> {name: N(0,1) array} for SG-HMC evaluation k (0..20) of outer iteration `it`, and
+        `window_index(it)` -> the window entry `train_hypers` feeds, inject the randomness the reference draws unseeded
+        (tf.random.normal, np.random.randint) so that a run can be compared with the reference's (tests)."""
         Y_train = np.asarray(Y_train, dtype=np.float64)
         if len(Y_train.shape) == 1:
             Y_train = Y_train[:, None]
@@ -70,11 +73,11 @@ class Model(object):
             it += 1
             self.global_step += 1
             self.model.global_step = self.global_step
-            self.model.sghmc_step()
+            self.model.sghmc_step(noise_fn=(lambda k, _it=it - 1: sghmc_noise(_it, k)) if sghmc_noise is not None else None)
             if A.X_PG:                                # case 6: models.py:155-158
                 self.model.gp_x_sampling()
             if self.model.trainable:                  # hasattr(self.model, 'hyper_train_op')
-                self.model.train_hypers()
+                self.model.train_hypers(window_index(it - 1) if window_index is not None else None)
             if progress is not None and it % 100 == 0:
                 progress(it)
         return self.model
@@ -85,12 +88,13 @@ class RegressionModel(Model):
         super().__init__(prior_type, output_dim)
 
     def fit(self, Y_train, Y_test=None, tensorboard_savepath='', dataname='', fileid='', kernel_type='SquaredExponential',
-            kernel_train_flag=True, likelihood_traning=True, X_train=None, X_test=None, Ystd=None, data_uu=None, **kwargs):
+            kernel_train_flag=True, likelihood_traning=True, X_train=None, X_test=None, Ystd=None, data_uu=None, sghmc_noise=None,
+            window_index=None, **kwargs):
         Y_train = np.asarray(Y_train, dtype=np.float64)
         lik = Gaussian(Y_train.shape[1], self.ARGS.x_dims[-1], CC=self.ARGS.CC, DD=self.ARGS.DD, RR_chol=self.ARGS.RR_chol,
                        hyperparameter_sampling=self.ARGS.hyperparameter_sampling, likelihood_traning=likelihood_traning)
         return self._fit(Y_train, tensorboard_savepath, dataname, fileid, lik, X_train, Ystd, kernel_type, kernel_train_flag,
-                         Y_test=Y_test, data_uu=data_uu, **kwargs)
+                         Y_test=Y_test, data_uu=data_uu, sghmc_noise=sghmc_noise, window_index=window_index, **kwargs)
 
 
 def configure(model: Model, arguments: dict, control_inputs, case_val, Y_train_std=1.0, **overrides):

@@ -45,8 +45,14 @@ CASES = {  # FFVD_Main.py:273-324 : (kernel_optimization, U_optimization, Z_opti
 }
 
 
+def build_model_keep(ds, ini_file, case_val):
+    """build_model without resetting the shim (make_reference_golden_next.py re-runs the constructor on a kept variable store)."""
+    return build_model(ds, ini_file, case_val, seed=None)
+
+
 def build_model(ds, ini_file, case_val, seed):
-    tf.reset_shim(seed)
+    if seed is not None:
+        tf.reset_shim(seed)
     Y_train, Y_test, control_inputs, Y_std, Y_mean, u_mean, u_std = FFVD_Main.create_dataset(ds + "/")
     f = np.load(ini_file, allow_pickle=True)
     T = Y_train.shape[0]

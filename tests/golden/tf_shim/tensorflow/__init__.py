@@ -21,7 +21,13 @@ int64 = torch.int64
 _TRAINABLE = []
 _RNG = torch.Generator().manual_seed(0)
 NOISE_LOG = []          # every tf.random.normal draw, in call order
+UNIFORM_LOG = []        # every uniform draw behind tfp Categorical.sample, in call order
 PLACEHOLDER_VALUES = {}  # dtype -> value returned by tf.compat.v1.placeholder
+# TF1 graph re-execution: a `session.run(op)` of the reference evaluates the graph on the CURRENT variable values.  The
+# eager shim emulates that by re-running the model constructor; VARIABLE_OVERRIDES maps the creation index of a Variable
+# (deterministic: the constructor creates them in a fixed order) to the value it holds now.
+VARIABLE_OVERRIDES = {}
+_VAR_COUNT = [0]
 
 
 def _t(x, dtype=None):
@@ -33,7 +39,12 @@ def _t(x, dtype=None):
 
 
 def Variable(initial_value, dtype=None, trainable=True, name=None):
+    idx = _VAR_COUNT[0]
+    _VAR_COUNT[0] += 1
+    if idx in VARIABLE_OVERRIDES:
+        initial_value = VARIABLE_OVERRIDES[idx]
     v = _t(initial_value, dtype).detach().clone()
+    v._tf_index = idx
     if v.dtype.is_floating_point:
         v.requires_grad_(True)
     v._tf_name = name
@@ -138,7 +149,7 @@ def expand_dims(x, axis):
 
 
 def stack(values, axis=0):
-    if all(not isinstance(v, torch.Tensor) for v in values):
+    if all(not isinstance(v, (torch.Tensor, list, tuple)) for v in values):
         return [int(v) for v in values]
     return torch.stack([_t(v) for v in values], dim=axis)
 
@@ -147,8 +158,18 @@ def concat(values, axis):
     return torch.cat([_t(v) for v in values], dim=axis)
 
 
-def gather(x, idx, axis=-1):
-    return torch.index_select(_t(x), axis, torch.as_tensor(idx, dtype=torch.long))
+def gather(x, idx, axis=None):
+    """tf.gather: axis defaults to 0 (the reference's particle resampling); kernels_multi_output.py passes axis=-1."""
+    x = _t(x)
+    idx = torch.as_tensor(idx, dtype=torch.long)
+    ax = 0 if axis is None else axis
+    if idx.dim() == 0:
+        return x.select(ax, int(idx))
+    return torch.index_select(x, ax, idx)
+
+
+def unstack(x, axis=0):
+    return list(torch.unbind(_t(x), dim=axis))
 
 
 def assert_equal(a, b):
@@ -213,7 +234,14 @@ class _Session:
         pass
 
     def run(self, fetches, feed_dict=None):
-        return fetches
+        # TF returns NumPy values; variables keep their current (construction-time) value in this eager shim
+        def conv(f):
+            if isinstance(f, torch.Tensor):
+                return f.detach().numpy().copy()
+            if isinstance(f, (list, tuple)):
+                return type(f)(conv(v) for v in f)
+            return f
+        return conv(fetches)
 
 
 class _Adam:
@@ -229,8 +257,14 @@ class _Adam:
         return self.grads_and_vars
 
 
+class _HList(list):
+    """A placeholder value that can also be a feed_dict key (the reference builds {placeholder: value} dicts)."""
+    __hash__ = object.__hash__
+
+
 def _placeholder(dtype, shape=None):
-    return PLACEHOLDER_VALUES[dtype]
+    v = PLACEHOLDER_VALUES[dtype]
+    return _HList(v) if isinstance(v, list) else v
 
 
 def _config_proto():
@@ -252,7 +286,30 @@ compat = types.SimpleNamespace(v1=v1)
 keras = types.SimpleNamespace(backend=types.SimpleNamespace(clear_session=lambda: None))
 
 
-def reset_shim(seed=0):
+def reset_shim(seed=0, keep_overrides=False):
     _TRAINABLE.clear()
     NOISE_LOG.clear()
+    UNIFORM_LOG.clear()
+    _VAR_COUNT[0] = 0
+    if not keep_overrides:
+        VARIABLE_OVERRIDES.clear()
     _RNG.manual_seed(seed)
+
+
+# tf.Tensor.get_shape().ndims (conditionals_multi_output.py:368): the shim's tensors are torch tensors
+class _ShapeView:
+    def __init__(self, t):
+        self.ndims = t.dim()
+        self._s = tuple(t.shape)
+
+    def __getitem__(self, i):
+        return self._s[i]
+
+    def __len__(self):
+        return len(self._s)
+
+    def as_list(self):
+        return list(self._s)
+
+
+torch.Tensor.get_shape = lambda self: _ShapeView(self)

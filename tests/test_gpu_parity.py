@@ -694,3 +694,138 @@ def test_particle_gibbs_sweep(env):
     m6.ARGS.PG_particles = 8
     mod6 = m6.fit(prob.Y)
     assert np.isfinite(float(mod6.nll))
+
+
+# ---- SURVEY 8(f) rows against golden vectors from the REFERENCE'S OWN SOURCE (reference_shim_golden_next.npz) -----------
+@pytest.fixture(scope="module")
+def gold_next():
+    import os
+    from util import GOLDEN
+    return np.load(os.path.join(GOLDEN, "reference_shim_golden_next.npz"), allow_pickle=False)
+
+
+def test_f2_collapsed_qu_and_conditional_vs_reference_source(env, gold_next):
+    """cmo:206-227 and cmo:306-387 (q_sqrt 3-d with the reference's first-output broadcasting, and None) -- CUDA vs the
+    reference source's outputs."""
+    import torch as th
+    from ffvd_b200 import conditionals_multi_output as cmo
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    g = gold_next
+    prob = env["byname"]["actuator/0"]
+    T, D, Din = prob.Y.shape[0], prob.X.shape[1], prob.Z.shape[1]
+    kerns = [SquaredExponential(Din, variance=np.exp(prob.logv[k]), lengthscales=np.exp(prob.logl[k]), ARD=True) for k in range(D)]
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    Xc = np.concatenate([prob.X[:T], prob.ctrl], axis=1)
+    U_mean, Lseq = cmo.collapse_u_mean_after_kernel_precalculation(None, t(Xc), t(prob.X), t(prob.Z), kerns, t(np.exp(prob.logQ)))
+    assert_close(g["f2/U_mean"], U_mean.cpu().numpy(), TOL, "U_mean")
+    assert_close(g["f2/LHinvT"], Lseq.cpu().numpy(), TOL, "LHinvT")
+    scale = float(np.max(np.exp(prob.logv)))
+    for tag, q in (("q3", t(g["f2/LHinvT"])), ("qnone", None)):
+        mu, var = cmo.conditional_after_kernel_precalculation(None, t(g["f2/Xnew"]), t(prob.Z), kerns, t(g["f2/U_mean"][0]), white=True, q_sqrt=q)
+        assert_close(g["f2/cond_%s/mean" % tag], mu.cpu().numpy(), TOL, tag)
+        assert np.max(np.abs(g["f2/cond_%s/var" % tag] - var.cpu().numpy())) <= TOL * scale
+
+
+@pytest.mark.parametrize("case_val,tag", ((4, "collapsed"), (2, "uncollapsed")))
+def test_f2_rollout_vs_reference_source(env, gold_next, case_val, tag, tmp_path):
+    """`collect_samples_formal` (base_model.py:197-522) on the CUDA path vs the same method executed from the reference
+    source with its logged noise: predict_y, predict_y_var, fit_y, RMSE and the results-file keys."""
+    g = gold_next
+    prob = env["byname"]["actuator/0"]
+    m, ctrl = _model_from_problem(env, prob, case_val, iterations=0, extra_ctrl=g["f2/ctrl_future"])
+    model = m.fit(prob.Y, kernel_type="SquaredExponential")
+    base = str(tmp_path / "run")
+    py, pv = model.collect_samples_formal(3, 1, ctrl, 30, sghmc_var_len=0, U_collapse=(case_val == 4), Y_test=g["f2/Y_test"], Y_train_std=1.7,
+                                          save_path_file=base, Y_train=prob.Y, case="C%d" % case_val, noise=g["f2/rollout_%s/noise" % tag])
+    assert_close(g["f2/rollout_%s/predict_y" % tag], py, TOL, "predict_y")
+    assert_close(g["f2/rollout_%s/predict_y_var" % tag].reshape(-1), np.asarray(pv).reshape(-1), TOL, "predict_y_var")
+    assert_close(g["f2/rollout_%s/fit_y" % tag], model.fit_y, 1e-12, "fit_y")
+    assert abs(model.RMSE_val - float(g["f2/rollout_%s/RMSE" % tag])) <= TOL * model.RMSE_val
+    res = np.load(base + "_results.npz", allow_pickle=True)
+    assert sorted(res.files) == sorted(str(k) for k in g["f2/rollout_%s/file_keys" % tag])
+    for k in ("y_train_vfe", "y_test_vfe", "X_val", "Z_val", "log_QQ"):
+        assert_close(g["f2/rollout_%s/file/%s" % (tag, k)], np.asarray(res[k], dtype=np.float64), TOL, k)
+
+
+def test_f4_particle_gibbs_vs_reference_source(env, gold_next):
+    """`BaseModel.PG_for_X` (base_model.py:29-75) on the CUDA path vs the reference source's sweep with its logged draws."""
+    g = gold_next
+    prob = env["byname"]["gas_furnace/0"]
+    m, _ = _model_from_problem(env, prob, 6, iterations=0)
+    model = m.fit(prob.Y)
+    path = model.PG_for_X(prob.ctrl, int(g["f4/P"]), normals=g["f4/normals"], eps=g["f4/eps"], uniforms=g["f4/uniforms"], assign=False)
+    assert_close(g["f4/X_after"], path.cpu().numpy(), 1e-8, "PG trajectory")
+
+
+@pytest.mark.parametrize("case_val", (2, 4))
+def test_f3_outer_loop_vs_reference_source(env, gold_next, case_val):
+    """`Model._fit` (models.py:142-168: sghmc_step + train_hypers per outer iteration) on the CUDA path vs the reference's
+    update expressions re-executed per session.run: final value of EVERY parameter after 2 (case 2: kernel hypers and U
+    SG-HMC sampled, 42 SG-HMC evaluations) / 4 (case 4, the CLI default: Adam on everything, collapsed bound) iterations."""
+    from oracle import loop
+    g = gold_next
+    key = "f3/case%d" % case_val
+    prob = env["byname"]["actuator/0"]
+    iters = int(g[key + "/iters"])
+    D = prob.X.shape[1]
+    nf = loop.reference_noise_fn(g, key, D)
+    m, _ = _model_from_problem(env, prob, case_val, iterations=iters // 2)
+    widx = [int(i) for i in g[key + "/window_index"]]
+    noise = (lambda it, k: {n: nf(21 * it + k, n) for n in ("logv", "logl", "U")}) if case_val == 2 else None
+    model = m.fit(prob.Y, kernel_type="SquaredExponential", sghmc_noise=noise, window_index=lambda it: widx[it])
+    assert m.global_step == iters
+    for k in GKEYS:
+        assert_close(g["%s/%s" % (key, k)], model.params[k].cpu().numpy(), 5e-9, "%s %s" % (key, k))
+    assert abs(float(model.nll) - float(g[key + "/nll_final"])) <= 1e-9 * abs(float(g[key + "/nll_final"]))
+
+
+@pytest.mark.parametrize("M", (90, 200))
+def test_reuse_kzz_content_guard(env, M):
+    """FFVD_FLAG_REUSE_KZZ is keyed on tensor addresses; the device-side content hash of Z / logv / logl must catch an
+    IN-PLACE change: the reusing call returns FFVD_E_STALE (nll = NaN under FFVD_FLAG_ASYNC) instead of silently using the
+    factors of another Z, and the factors of a FAILED factorisation are never reused (single-CTA and blocked paths)."""
+    from oracle import fixtures, ffvd_oracle as O
+    torch, ctx, F = env["torch"], env["ctx"], env["ffvd"]
+    prob = fixtures.synthetic_problem(T=100, M=M, D=3, S=1, seed=5)
+    p = dev_problem(env, prob)
+    o = alloc_out(env, p)
+    base = F.FLAG_PRIOR_Z_NORMAL
+    ctx.nll_grads(0, False, p, o, flags=base)
+    ctx.nll_grads(0, False, p, o, flags=base | F.FLAG_REUSE_KZZ)            # legitimate reuse
+    assert np.isfinite(o["nll"].cpu().numpy()).all()
+    p["Z"].mul_(1.01)                                                        # same address, new contents
+    with pytest.raises(F.StaleFactorsError):
+        ctx.nll_grads(0, False, p, o, flags=base | F.FLAG_REUSE_KZZ)
+    assert np.isnan(o["nll"].cpu().numpy()).all()
+    ctx.nll_grads(0, False, p, o, flags=base | F.FLAG_REUSE_KZZ)            # the host dropped the record: a full preparation
+    prob2 = copy.deepcopy(prob); prob2.Z = p["Z"].cpu().numpy()
+    check(O.nll_and_grads(prob2, collapsed=False), {k: (v.cpu().numpy()[0] if k in ("nll", "terms") else v.cpu().numpy()) for k, v in o.items()},
+          what="after stale")
+    # asynchronous caller: no status is read, the NaN is the signal
+    p["logl"].add_(0.01)
+    ctx.nll_grads(0, False, p, o, flags=base | F.FLAG_REUSE_KZZ | F.FLAG_ASYNC)
+    torch.cuda.synchronize()
+    assert np.isnan(o["nll"].cpu().numpy()).all()
+    ctx.nll_grads(0, False, p, o, flags=base)
+    # a failed factorisation (asynchronous call, status never read) must not be reusable
+    ctx.nll_grads(0, False, p, o, flags=base | F.FLAG_ASYNC, jitter=-1.0e3)
+    ctx.nll_grads(0, False, p, o, flags=base | F.FLAG_REUSE_KZZ | F.FLAG_ASYNC, jitter=-1.0e3)
+    torch.cuda.synchronize()
+    assert np.isnan(o["nll"].cpu().numpy()).all()
+    ctx.nll_grads(0, False, p, o, flags=base)
+    assert np.isfinite(o["nll"].cpu().numpy()).all()
+
+
+def test_device_data_generator(env):
+    """bench.py's device-side AR(1) generator (shapes too large to ship from the host) against scipy's filter
+    on the same innovations, across block boundaries."""
+    import bench
+    from scipy.signal import lfilter
+    torch = env["torch"]
+    eps = torch.randn((3, 1037, 4), dtype=torch.float64, device=env["dev"])
+    x = bench.ar1_filter_device(eps.clone()).cpu().numpy()
+    ref = lfilter([1.0], [1.0, -0.95], eps.cpu().numpy(), axis=1)
+    assert np.max(np.abs(x - ref)) <= 1e-12
+    d = bench.make_device_data(500, 64, 3, 2, seed=1, dev=env["dev"])
+    assert tuple(d["X"].shape) == (2, 501, 3) and tuple(d["Y"].shape) == (500, 1) and tuple(d["ctrl"].shape) == (500, 1)
+    assert abs(float(d["X"].std()) - 1.0) < 0.3
