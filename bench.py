@@ -274,7 +274,7 @@ def multi_gpu_parity(ctx, dev, rank, world):
     mine = dict(full); mine["X"] = full["X"][rank * Sp:(rank + 1) * Sp].contiguous()
     out = alloc_outputs(mine, Sp, dev)
     ctx.nll_grads(ffvd_b200.KERNEL_SE, False, mine, out, flags=ffvd_b200.FLAG_PRIOR_Z_NORMAL)
-    fd.allreduce_shared(out)
+    ctx.allreduce_shared(out)
     nll_all = [torch.empty(Sp, dtype=torch.float64, device=dev) for _ in range(world)]
     dist.all_gather(nll_all, out["nll"])
     res = None
@@ -344,7 +344,9 @@ class StepRunner:
         nzX = self.noise_X if nzX is None else nzX
         self.ctx.nll_grads(self.kind, False, Pd, self.out, flags=self.flags)
         if self.world > 1:
-            fd.allreduce_shared(self.out)           # one packed NCCL all-reduce of Z/U/hyper gradients
+            # one packed NCCL all-reduce of the Z/U/hyper-parameter gradients, through the library's own communicator
+            # (ffvd_allreduce_shared: pack, ncclAllReduce, unpack on the context's stream)
+            self.ctx.allreduce_shared(self.out)
         for n, nz in (("X", nzX), ("U", self.noise_U)):
             st = self.state[n]
             self.ctx.sghmc_update(Pd[n], self.out["g_" + n], nz, st["xi"], st["g"], st["g2"], st["p"], 0.01, 0.05, float(self.T + 1), True)
@@ -484,6 +486,9 @@ def main():
     T, M, D, S = cfg["T"], cfg["M"], cfg["D"], cfg["S"]
     Din = D + 1
     ctx = ffvd_b200.Context(local, torch.cuda.current_stream(local).cuda_stream)
+    if world > 1:
+        from ffvd_b200 import distributed as fd
+        fd.init_native_comm(ctx)                    # NCCL communicator owned by the library (C ABI); torch only ships the id
 
     def barrier():
         if world > 1:

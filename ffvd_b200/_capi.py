@@ -87,6 +87,14 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_conditional_ex.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, ci, vp, vp]
     lib.ffvd_collapse_u_mean.argtypes = [vp, ci, ctypes.POINTER(_Problem), cd, vp, vp]
     lib.ffvd_logdensity_norm_diag.argtypes = [vp, vp, vp, vp, ci, vp]
+    lib.ffvd_logdensity_norm.argtypes = [vp, vp, vp, vp, vp]
+    lib.ffvd_debug_exp.argtypes = [vp, vp, vp]
+    lib.ffvd_comm_unique_id.argtypes = [vp]
+    lib.ffvd_comm_init.argtypes = [vp, vp, ci, ci]
+    lib.ffvd_comm_destroy.argtypes = [vp]
+    lib.ffvd_comm_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.ffvd_allreduce_shared.argtypes = [vp, ctypes.POINTER(_Outputs), ci]
+    lib.ffvd_allreduce.argtypes = [vp, vp]
     lib.ffvd_nll_grads_uncollapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
     lib.ffvd_nll_grads_collapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
     lib.ffvd_nll_grads_batched.argtypes = [vp, ci, ci, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
@@ -95,7 +103,8 @@ def load_library() -> ctypes.CDLL:
     for name in ("ffvd_ctx_create", "ffvd_ctx_destroy", "ffvd_ctx_synchronize", "ffvd_kernel_K", "ffvd_kernel_Kdiag",
                  "ffvd_kernel_pre_cal", "ffvd_conditional", "ffvd_logdensity_norm_diag", "ffvd_nll_grads_uncollapsed",
                  "ffvd_nll_grads_collapsed", "ffvd_nll_grads_batched", "ffvd_sghmc_update", "ffvd_adam_update",
-                 "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks", "ffvd_conditional_ex"):
+                 "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks", "ffvd_conditional_ex", "ffvd_logdensity_norm", "ffvd_debug_exp", "ffvd_comm_unique_id", "ffvd_comm_init",
+                 "ffvd_comm_destroy", "ffvd_comm_info", "ffvd_allreduce_shared", "ffvd_allreduce"):
         getattr(lib, name).restype = ci
     _lib = lib
     return lib
@@ -261,6 +270,62 @@ class Context:
         b = _Borrow()
         try:
             _check(self._lib.ffvd_logdensity_norm_diag(self._h, b.ptr(y), b.ptr(ymean), b.ptr(Rchols), int(bool(vec)), b.ptr(out)))
+        finally:
+            b.release()
+        return out
+
+    # ---- multi-GPU: NCCL communicator behind the C ABI
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id (create on rank 0, ship to the other ranks, pass to `comm_init` everywhere)."""
+        buf = ctypes.create_string_buffer(128)
+        _check(load_library().ffvd_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        if len(unique_id) != 128:
+            raise ValueError("NCCL unique id must be 128 bytes")
+        _check(self._lib.ffvd_comm_init(self._h, ctypes.c_char_p(unique_id), int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        _check(self._lib.ffvd_comm_destroy(self._h))
+
+    def comm_info(self):
+        r, n, v = ctypes.c_int(0), ctypes.c_int(1), ctypes.c_int(0)
+        _check(self._lib.ffvd_comm_info(self._h, ctypes.byref(r), ctypes.byref(n), ctypes.byref(v)))
+        return r.value, n.value, v.value
+
+    def allreduce_shared(self, outputs: dict, with_scalars: bool = False):
+        """ONE NCCL all-reduce of the packed shared-parameter gradients (in place); g_X stays on its owner."""
+        b = _Borrow()
+        try:
+            O = _Outputs()
+            self._fill(b, O, _OUTPUT_FIELDS, {k: v for k, v in outputs.items() if k != "g_X"})
+            _check(self._lib.ffvd_allreduce_shared(self._h, ctypes.byref(O), int(bool(with_scalars))))
+        finally:
+            b.release()
+        return outputs
+
+    def allreduce(self, tensor):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_allreduce(self._h, b.ptr(tensor)))
+        finally:
+            b.release()
+        return tensor
+
+    def debug_exp(self, x, out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_debug_exp(self._h, b.ptr(x), b.ptr(out)))
+        finally:
+            b.release()
+        return out
+
+    def logdensity_norm(self, y, ymean, Rchols, out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_logdensity_norm(self._h, b.ptr(y), b.ptr(ymean), b.ptr(Rchols), b.ptr(out)))
         finally:
             b.release()
         return out

@@ -250,9 +250,9 @@ class BaseModel(object):
         eps = torch.randn((T, P1, D), dtype=torch.float64, device=dev) if eps is None else t64(eps)
         uniforms = torch.rand((T, P1), dtype=torch.float64, device=dev) if uniforms is None else t64(uniforms)
         kern = self.kernels[-1]
-        Z, U, C, dvec = self.params["Z"], self.params["U"], self.params["C"], self.params["d"]
-        R = self.params["logR"].exp().reshape(-1)            # Dy == 1 in all bundled data: diagonal factor
-        logR = self.params["logR"].reshape(-1).sum()
+        from .likelihoods import logdensity_norm
+        Z, U = self.params["Z"], self.params["U"]
+        Rchols = self.likelihood.Rchols                       # (Dy,Dy) lower factor; likelihoods.py:114-127 on the device
         Qv = self.log_Q.exp()
         Y = self.data["Y"]
         factors = cmo.kernel_pre_cal(Z, kern)                  # once per sweep (:36)
@@ -272,8 +272,8 @@ class BaseModel(object):
             mu, var = cmo.conditional_after_kernel_precalculation(factors, xc, Z, kern, U, white=True, full_cov=False)
             x_next = mu + x_t + eps[tt] * torch.sqrt(var + Qv)
             states[tt + 1, :P1] = x_next
-            res = (Y[tt][None, :] - (states[tt + 1] @ C + dvec)) / R           # (P, Dy); likelihoods.py:114-127
-            logits = -0.5 * (res * res).sum(dim=1) - logR
+            y_mu = self.likelihood.predict_mean(states[tt + 1].contiguous())   # (P, Dy): free particles and the reference one (:61-65)
+            logits = logdensity_norm(Y[tt].contiguous(), y_mu, Rchols)
             if tt < T - 1:
                 idx = sample(logits, uniforms[tt])
                 anc[tt] = idx

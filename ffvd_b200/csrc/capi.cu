@@ -19,6 +19,7 @@
 #include "fused_table.cuh"
 #include "prep_post.cuh"
 #include "blocked_chol.cuh"
+#include "comm.cuh"
 
 using namespace ffvd;
 
@@ -62,6 +63,11 @@ struct ffvd_ctx {
   static const int kRing = 256;
   cudaEvent_t ev0[kRing], ev1[kRing];
   long long ev_count = 0;
+  // NCCL communicator (ffvd_comm_init) and the packed all-reduce buffer
+  NcclComm comm = nullptr;
+  int comm_rank = 0, comm_nranks = 1;
+  double* pack_buf = nullptr;
+  size_t pack_cap = 0;
 };
 
 extern "C" int ffvd_version(void) { return 100; }
@@ -114,6 +120,8 @@ extern "C" int ffvd_ctx_destroy(ffvd_ctx* c) {
   if (c->d_probs) cudaFree(c->d_probs);
   if (c->d_outs) cudaFree(c->d_outs);
   if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->comm) { if (const NcclApi* a = nccl_api(nullptr)) a->CommDestroy(c->comm); c->comm = nullptr; }
+  if (c->pack_buf) cudaFree(c->pack_buf);
   for (int i = 0; i < ffvd_ctx::kRing; ++i) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -156,6 +164,63 @@ extern "C" int ffvd_debug_phase_clocks(ffvd_ctx* c, int reset, uint64_t* out16) 
   (void)c; (void)reset; (void)out16;
   return fail(FFVD_E_UNSUPPORTED, "library was not built with -DFFVD_PHASE_TIMING");
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: NCCL communicator per context
+#define NCCL_TRY(api, expr)                                                                                        \
+  do {                                                                                                             \
+    int _r = (expr);                                                                                               \
+    if (_r != 0) return fail(FFVD_E_CUDA, std::string(#expr) + ": NCCL error " + ((api)->GetErrorString ? (api)->GetErrorString(_r) : "?")); \
+  } while (0)
+
+extern "C" int ffvd_comm_unique_id(void* id128) {
+  if (!id128) return fail(FFVD_E_BADARG, "id128 is null");
+  std::string err;
+  const NcclApi* a = nccl_api(&err);
+  if (!a) return fail(FFVD_E_UNSUPPORTED, err);
+  NcclUniqueId id;
+  NCCL_TRY(a, a->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_comm_init(ffvd_ctx* c, const void* id128, int rank, int nranks) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(FFVD_E_BADARG, "ffvd_comm_init: bad argument");
+  std::string err;
+  const NcclApi* a = nccl_api(&err);
+  if (!a) return fail(FFVD_E_UNSUPPORTED, err);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->comm) { NCCL_TRY(a, a->CommDestroy(c->comm)); c->comm = nullptr; }
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NCCL_TRY(a, a->CommInitRank(&c->comm, nranks, id, rank));
+  c->comm_rank = rank; c->comm_nranks = nranks;
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_comm_destroy(ffvd_ctx* c) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (c->comm) {
+    const NcclApi* a = nccl_api(nullptr);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (a) NCCL_TRY(a, a->CommDestroy(c->comm));
+    c->comm = nullptr;
+  }
+  c->comm_rank = 0; c->comm_nranks = 1;
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_comm_info(ffvd_ctx* c, int* rank, int* nranks, int* nccl_version) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (rank) *rank = c->comm_rank;
+  if (nranks) *nranks = c->comm ? c->comm_nranks : 1;
+  if (nccl_version) {
+    *nccl_version = 0;
+    const NcclApi* a = nccl_api(nullptr);
+    if (a && a->GetVersion) a->GetVersion(nccl_version);
+  }
+  return FFVD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -440,6 +505,17 @@ static int dblk_of(int Mp, int D) {
   return b;
 }
 
+// Work-item form (see fused_kernel): one item per (sample, tile, block of dblk dims) -- the CTA stages the x tile once and
+// loops over the dims -- when that still leaves >= 32 items per CTA of the persistent grid (tail <= 3%); one item per
+// (sample, tile, d) otherwise.  FFVD_DL=0/1 overrides (A/B timing).
+static void set_items(const ffvd_ctx* c, DevProblem& P, long long pairs_st /* S * ntiles */) {
+  const int nblk = (P.D + P.dblk - 1) / P.dblk;
+  bool loop = P.dblk > 1 && pairs_st * nblk >= (long long)32 * c->num_sms;
+  if (const char* e = getenv("FFVD_DL")) loop = atoi(e) != 0 && P.dblk > 1;
+  P.dl = loop ? P.dblk : 1;
+  P.nitems = loop ? pairs_st * nblk : pairs_st * P.D;
+}
+
 static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X, double* XT, int* status, int nbatch,
                                  int M, int Mp);
 
@@ -656,7 +732,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     P.ntiles = (t.T + BT - 1) / BT;
     P.dblk = dblk_of(Mp, D);
     P.item_begin = item;
-    P.nitems = (long long)D * t.S * P.ntiles;
+    set_items(c, P, (long long)t.S * P.ntiles);
     item += P.nitems;
     bind_problem(c, L, p, s_begin, P);
     s_begin += t.S;
@@ -756,6 +832,58 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   if (!(flags & 8)) st = check_status(c, L);
   TRY(call.finish());
   return st;
+}
+
+// One all-reduce (sum, float64) of a list of device tensors packed into one buffer.
+static int allreduce_list(ffvd_ctx* c, Call& call, DLManagedTensor* const* list, const char* const* names, int n) {
+  if (!c->comm || c->comm_nranks == 1) return FFVD_OK;          // single rank: the sum is the value
+  const NcclApi* a = nccl_api(nullptr);
+  if (!a) return fail(FFVD_E_UNSUPPORTED, "NCCL is not loaded");
+  PackList pl;
+  pl.n = 0; pl.off[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!list[i]) continue;
+    Tens t;
+    TRY(call.import(list[i], false, t, names[i]));
+    if (t.staged) return fail(FFVD_E_DEVICE, std::string(names[i]) + ": the collective works on device tensors only");
+    if (t.numel == 0) continue;
+    if (pl.n == 12) return fail(FFVD_E_LIMIT, "at most 12 tensors per packed all-reduce");
+    pl.ptr[pl.n] = t.d;
+    pl.off[pl.n + 1] = pl.off[pl.n] + (long long)t.numel;
+    pl.n++;
+  }
+  const size_t total = (size_t)pl.off[pl.n];
+  if (!total) return FFVD_OK;
+  if (c->pack_cap < total) {
+    if (c->pack_buf) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->pack_buf)); }
+    CUDA_TRY(cudaMalloc((void**)&c->pack_buf, total * sizeof(double)));
+    c->pack_cap = total;
+  }
+  pack_kernel<<<grid1d(total), 256, 0, c->stream>>>(pl, c->pack_buf, 0); c->launches++;
+  NCCL_TRY(a, a->AllReduce(c->pack_buf, c->pack_buf, total, kNcclFloat64, kNcclSum, c->comm, c->stream));
+  pack_kernel<<<grid1d(total), 256, 0, c->stream>>>(pl, c->pack_buf, 1); c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_allreduce_shared(ffvd_ctx* c, const ffvd_outputs* o, int with_scalars) {
+  if (!c || !o) return fail(FFVD_E_BADARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  DLManagedTensor* list[10] = {o->g_Z, o->g_U, o->g_logv, o->g_logl, o->g_logQ, o->g_C, o->g_d, o->g_logR,
+                               with_scalars ? o->nll : nullptr, with_scalars ? o->terms : nullptr};
+  const char* names[10] = {"g_Z", "g_U", "g_logv", "g_logl", "g_logQ", "g_C", "g_d", "g_logR", "nll", "terms"};
+  TRY(allreduce_list(c, call, list, names, 10));
+  return call.finish();
+}
+
+extern "C" int ffvd_allreduce(ffvd_ctx* c, DLManagedTensor* t) {
+  if (!c || !t) return fail(FFVD_E_BADARG, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  const char* nm = "tensor";
+  TRY(allreduce_list(c, call, &t, &nm, 1));
+  return call.finish();
 }
 
 extern "C" int ffvd_nll_grads_uncollapsed(ffvd_ctx* c, int kind, const ffvd_problem* p, int flags, double jitter,
@@ -987,7 +1115,8 @@ extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLM
   c->cur_rb = RB;
   P.hs = shared_kernel ? 0 : 1;
   P.X = tX.d; P.S = 1; P.T = N; P.xrows = N; P.Dx = Din; P.nc = 0; P.Dy = 1;
-  P.ntiles = (N + BT - 1) / BT; P.dblk = dblk_of(P.Mp, R); P.item_begin = 0; P.nitems = (long long)R * P.ntiles;
+  P.ntiles = (N + BT - 1) / BT; P.dblk = dblk_of(P.Mp, R); P.item_begin = 0;
+  set_items(c, P, (long long)P.ntiles);
   P.cond_mean = tm.d; P.cond_var = tvar.d;
   if (tq.present) {
     if (tq.ndim == 2) {                       // (M,R) per-point scales, conditionals_multi_output.py:51-52
@@ -1040,6 +1169,52 @@ extern "C" int ffvd_logdensity_norm_diag(ffvd_ctx* c, DLManagedTensor* y, DLMana
   if (tr.numel != (size_t)Dy) return fail(FFVD_E_SHAPE, "Rchols must be (Dy)");
   if (to.numel != (vec ? (size_t)N : (size_t)N * Dy)) return fail(FFVD_E_SHAPE, "out has the wrong size");
   if (N) { logdensity_diag_kernel<<<grid1d(N), 256, 0, c->stream>>>(ty.d, tm.d, tr.d, N, Dy, vec, to.d); c->launches++; }
+  return call.finish();
+}
+
+// Diagnostic: the fused kernels' branch-free exp routine applied elementwise (accuracy tests against libm).
+__global__ void debug_exp_kernel(const double* __restrict__ x, double* __restrict__ out, size_t n) {
+  __shared__ double tab[64];
+  if (threadIdx.x < 64) tab[threadIdx.x] = g_exp2_tab[threadIdx.x];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double a[1] = {x[i]};
+    exp_nonpos_n<1>(a, tab);
+    out[i] = a[0];
+  }
+}
+extern "C" int ffvd_debug_exp(ffvd_ctx* c, DLManagedTensor* x, DLManagedTensor* out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tx, to;
+  TRY(call.import(x, false, tx, "x"));
+  TRY(call.import(out, true, to, "out"));
+  if (tx.numel != to.numel) return fail(FFVD_E_SHAPE, "x and out must have the same size");
+  if (tx.numel) { debug_exp_kernel<<<grid1d(tx.numel), 256, 0, c->stream>>>(tx.d, to.d, tx.numel); c->launches++; }
+  return call.finish();
+}
+
+extern "C" int ffvd_logdensity_norm(ffvd_ctx* c, DLManagedTensor* y, DLManagedTensor* ymean, DLManagedTensor* Rchols,
+                                    DLManagedTensor* out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens ty, tm, tr, to;
+  TRY(call.import(y, false, ty, "y"));
+  TRY(call.import(ymean, false, tm, "ymean"));
+  TRY(call.import(Rchols, false, tr, "Rchols"));
+  TRY(call.import(out, true, to, "out"));
+  if (tm.ndim != 2) return fail(FFVD_E_SHAPE, "ymean must be (N,Dy)");
+  const int N = (int)tm.shape[0], Dy = (int)tm.shape[1];
+  if (Dy < 1 || Dy > FFVD_MAX_DY) return fail(FFVD_E_LIMIT, "logdensity_norm: Dy must be in 1..64");
+  if (ty.numel != (size_t)N * Dy && ty.numel != (size_t)Dy) return fail(FFVD_E_SHAPE, "y must be (N,Dy), or one row (Dy) broadcast over ymean");
+  if (tr.numel != (size_t)Dy * Dy) return fail(FFVD_E_SHAPE, "Rchols must be (Dy,Dy)");
+  if (to.numel != (size_t)N) return fail(FFVD_E_SHAPE, "out must be (N)");
+  if (N) {
+    logdensity_full_kernel<<<grid1d(N, 128), 128, 0, c->stream>>>(ty.d, ty.numel == (size_t)Dy && N != 1 ? 1 : N, tm.d, tr.d, N, Dy, to.d);
+    c->launches++;
+  }
   return call.finish();
 }
 

@@ -59,6 +59,38 @@ __global__ void logdensity_diag_kernel(const double* __restrict__ y, const doubl
   }
 }
 
+// likelihoods.py:114-127 logdensity_norm with a FULL lower-triangular noise factor L = Rchols (the particle-Gibbs weights,
+// base_model.py:62-66): alpha = L^{-1} (y - ymean)^T by forward substitution (tf.linalg.triangular_solve(lower=True) reads
+// only the lower triangle), out[n] = -1/2 |alpha_n|^2 - sum_i log L_ii.  y has N rows or ONE row broadcast against the N
+// rows of ymean (the reference subtracts self.Y[tt] from a (P,Dy) matrix).  One thread per row; Dy <= 64.
+#define FFVD_MAX_DY 64
+__global__ void __launch_bounds__(128) logdensity_full_kernel(const double* __restrict__ y, int y_rows, const double* __restrict__ ymean,
+                                                              const double* __restrict__ L, int N, int Dy, double* __restrict__ out) {
+  __shared__ double Ls[FFVD_MAX_DY * FFVD_MAX_DY];
+  __shared__ double logdet;
+  for (int i = threadIdx.x; i < Dy * Dy; i += blockDim.x) Ls[i] = L[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < Dy; ++i) a += log(Ls[i * Dy + i]);
+    logdet = a;
+  }
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    double alpha[FFVD_MAX_DY];
+    const double* yr = y + (size_t)(y_rows == 1 ? 0 : n) * Dy;
+    double ss = 0.0;
+    for (int i = 0; i < Dy; ++i) {
+      double t = yr[i] - ymean[(size_t)n * Dy + i];
+      for (int j = 0; j < i; ++j) t = fma(-Ls[i * Dy + j], alpha[j], t);
+      t /= Ls[i * Dy + i];
+      alpha[i] = t;
+      ss = fma(t, t, ss);
+    }
+    out[n] = -0.5 * ss - logdet;
+  }
+}
+
 // base_model.py:150-179: adaptive SG-HMC, Jacobi semantics (all right-hand sides read pre-step state).
 // 12 streams/element in burn-in (7 reads + 5 writes = 96 B), 7 in sampling (5 R + 2 W = 56 B).
 __device__ __forceinline__ void sghmc_one(double& th, double gr, double nz, double& xio, double& go, double& g2o, double& po,

@@ -64,8 +64,9 @@ struct DevProblem {
   int hs;              // hyper-parameter / Linv stride per output dim: 1 = list of D kernels, 0 = one shared kernel
   int ntiles;          // tiles per sample
   int dblk;            // output dims per block of the work-item order (see fused_kernel)
+  int dl;              // 1: one work item per (sample, tile, d); > 1 (= dblk): one per (sample, tile, block of dims)
   long long item_begin;   // first work item of this problem (prefix sum)
-  long long nitems;       // D * S * ntiles
+  long long nitems;       // work items: D * S * ntiles (dl == 1) or ceil(D / dblk) * S * ntiles (dl > 1)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -77,39 +78,59 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // exp(x) for x <= ~0 (the SE kernel argument -r^2/2), branch free, N independent evaluations advanced in lock step
 // so that the FP64 pipe always has N independent FMAs to issue (the pipe is narrow: two warps per scheduler cannot
 // hide its latency with one dependent Horner chain each).
-// x = n ln2 + r, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation 4e-18), 2^n applied to the exponent bits.
-// <= 1 ulp from the correctly rounded result on [-700, 1e-9] (checked on the host against libm).  The argument is
-// clamped at -745 first (one DMNMX): the low word of t must hold n, and without the clamp an argument below ~-1.5e9
-// (|x/l - z/l| > 5e4, e.g. a diverging chain on logl) would wrap n and return a huge / Inf / NaN kernel value instead of
-// 0.  Below -708 the result saturates near 1e-308, i.e. 0 at the scale of every quantity the kernels form.
+// Table method: x = (64 n + j) ln2/64 + r with |r| <= ln2/128, exp(x) = 2^n * T[j] * exp(r), T[j] = 2^(j/64) correctly
+// rounded (64 doubles, staged in shared memory by the caller), exp(r) - 1 = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)
+// (truncation r^6/720 <= 3.5e-17 relative).  11 FP64 operations per value against 19 for the degree-13 polynomial this
+// replaces (the K tile is FP64-pipe work that competes with the DMMAs); <= 1.5 ulp on [-745, 0] (tests: ffvd_debug_exp).
+// The argument is clamped at -745 first: the low word of t must hold the integer, and without the clamp an argument
+// below ~-2e7 (|x/l - z/l| > 6e3, e.g. a diverging chain on logl) would wrap it and return a huge / Inf / NaN kernel
+// value instead of 0.  Below -708 the scale saturates at 2^-1022 (result ~ 1e-308, i.e. 0 at the scale of every quantity
+// the kernels form).
+static __device__ const double g_exp2_tab[64] = {
+  0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+  0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+  0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+  0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+  0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+  0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+  0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+  0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+  0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+  0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+  0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+  0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+  0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+  0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+  0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+  0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
 template <int N>
-__device__ __forceinline__ void exp_nonpos_n(double (&x)[N]) {
-  double r[N], p[N];
+__device__ __forceinline__ void exp_nonpos_n(double (&x)[N], const double* __restrict__ tab /* shared-memory copy of g_exp2_tab */) {
+  double r[N], q[N], tj[N];
   int n[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     x[i] = fmax(x[i], -745.0);
-    const double t = fma(x[i], 1.4426950408889634, 6755399441055744.0);
-    n[i] = max(__double2loint(t), -1022);      // x < -708: the scale saturates at 2^-1022 (result ~ 1e-308 ~ 0)
-    const double nd = t - 6755399441055744.0;
-    r[i] = fma(nd, -6.93147180369123816490e-01, x[i]);
-    r[i] = fma(nd, -1.90821492927058770002e-10, r[i]);
-    p[i] = fma(1.0 / 6227020800.0, r[i], 1.0 / 479001600.0);
+    const double t = fma(x[i], 92.33248261689366, 6755399441055744.0);     // 64 / ln 2, 1.5 * 2^52
+    const int k = __double2loint(t);                                        // round(x * 64 / ln 2), two's complement
+    const double kd = t - 6755399441055744.0;
+    r[i] = fma(kd, -0x1.62e42fec00000p-7, x[i]);                            // ln2/64 head (30 bits: kd * head is exact)
+    r[i] = fma(kd, -0x1.d1cf79abc9e3bp-38, r[i]);                           // ln2/64 tail
+    tj[i] = tab[k & 63];
+    n[i] = max(k >> 6, -1022);
+    q[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
   }
-  const double cf[12] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
-                         1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,           1.0,          1.0};
 #pragma unroll
-  for (int k = 0; k < 12; ++k)
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], r[i], 1.0 / 6.0);
 #pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], cf[k]);
+  for (int i = 0; i < N; ++i) q[i] = fma(q[i], r[i], 0.5);
 #pragma unroll
-  for (int i = 0; i < N; ++i) x[i] = __hiloint2double(__double2hiint(p[i]) + (n[i] << 20), __double2loint(p[i]));
-}
-
-__device__ __forceinline__ double exp_nonpos(double x) {
-  double a[1] = {x};
-  exp_nonpos_n<1>(a);
-  return a[0];
+  for (int i = 0; i < N; ++i) {
+    const double r2 = r[i] * r[i];
+    const double em1 = fma(r2, q[i], r[i]);
+    const double p = fma(tj[i], em1, tj[i]);
+    x[i] = __hiloint2double(__double2hiint(p) + (n[i] << 20), __double2loint(p));
+  }
 }
 
 // Fire-and-forget FP64 add to GLOBAL memory.  atomicAdd() on a pointer whose address space the compiler cannot prove
@@ -152,6 +173,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // column-group (16 columns) owned by `warp` as its i-th group: zig-zag so that the
 // triangular work (proportional to the group index) is balanced across the 8 warps.
+// NCW = number of column warps of the tile (8; 4 for the two-CTAs-per-SM shapes).
+template <int NCW>
 __device__ __forceinline__ int group_index(int warp, int i) {
-  return (i & 1) ? (i * FFVD_NWARPS + (FFVD_NWARPS - 1 - warp)) : (i * FFVD_NWARPS + warp);
+  return (i & 1) ? (i * NCW + (NCW - 1 - warp)) : (i * NCW + warp);
 }

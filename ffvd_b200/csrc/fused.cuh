@@ -44,6 +44,7 @@ struct Smem {
   double* xn2h;     // 64: SE: -1/2 |x~_r|^2 of the scaled rows
   double* sc;       // 8: per-item scalars v, Q, 1/Q, log Q
   double* red;      // 40: block-level reductions (smem atomics)
+  double* exptab;   // 64: 2^(j/64), the table of exp_nonpos_n
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -55,85 +56,90 @@ struct Smem {
 // (element, input dim); exp through the branch-free, lock-step exp_nonpos_n.  Linear: ZTd = Z~^T unscaled.
 // The ZTd rows stream from L2 through a 4- or 8-slot register ring (that many input dims ahead); the first rows of the next column
 // group are requested before the exp / store work of the current one.
-template <int KIND, int RB, int NGW, bool SCR>
+template <int KIND, int RB, int NGW, bool SCR, int NCW>
 __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __restrict__ ZTd, int Mp, int Din, double v,
                                                int wc, int g, int q, int M, int row0, int lda, double* __restrict__ kscr) {
-  // ring depth in input dims: one step is 4 RB FMAs per lane, so fewer rows per warp need a deeper ring to cover L2 latency
-  constexpr int RING = RB >= 8 ? 4 : 8;
-  double2 ring[RING][2], hz[2];
-  // SE: the scaled copy has zero rows after the Din real ones (and x~ has zero columns there), so the step loop runs in
-  // whole trips of RING steps with no per-step branch -- the trip is one basic block and the scheduler can request the x
-  // values of later steps while the FMAs of earlier ones issue.  Linear reads Z~^T itself (row Din is the ones row) and
-  // keeps the guarded loop.
+  // The tile of a warp (8 RB rows x 16 NGW columns) is formed in passes of RBB row blocks x one 16-column group: 4 RBB
+  // accumulators per lane.  The pass loop is NOT unrolled: fully unrolled this phase was 38 KB of code (2.4k instructions
+  // for RB = 8, NGW = 2), and the whole item loop (218 KB) then misses the instruction cache on every item (ncu: 16% of
+  // the phase's stall samples were no-instruction).
+  constexpr int RBB = RB >= 4 ? 4 : RB;
+  constexpr int NPASS = RB / RBB;
+  // The ZTd rows of a pass stream from L2 through an 8-slot register ring, 8 input dims ahead.  SE: the scaled copy has
+  // zero rows after the Din real ones (and x~ has zero columns there), so the steps run in half-trips of 4 with no
+  // per-step branch; the loop leaves after the half-trip that covers Din.  Linear reads Z~^T itself (row Din is the ones
+  // row) and guards every step.
+  double2 ring[8][2], hz[2];
   auto prologue = [&](int jb) {
 #pragma unroll
-    for (int u = 0; u < RING; ++u) {
+    for (int u = 0; u < 8; ++u) {
       ring[u][0] = ring[u][1] = make_double2(0.0, 0.0);
-      if (KIND == 0 || u < Din) ldg256_nc(ZTd + (size_t)u * Mp + jb, ring[u][0], ring[u][1]);
+      if (KIND == 0 ? (u < 4 || Din > 4) : (u < Din)) ldg256_nc(ZTd + (size_t)u * Mp + jb, ring[u][0], ring[u][1]);
     }
     if (KIND == 0) ldg256_nc(ZTd + (size_t)(FFVD_ZTS_ROWS - 1) * Mp + jb, hz[0], hz[1]);
   };
-  prologue(16 * group_index(wc, 0) + 4 * q);
-  const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + g) * FFVD_XLD;
-#pragma unroll
-  for (int ng = 0; ng < NGW; ++ng) {
-    const int jb = 16 * group_index(wc, ng) + 4 * q;
-    double s[RB][4];
+  prologue(16 * group_index<NCW>(wc, 0) + 4 * q);
+#pragma unroll 1
+  for (int pass = 0; pass < NGW * NPASS; ++pass) {
+    const int ng = pass / NPASS, rbase = (pass % NPASS) * RBB;
+    const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
+    const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + 8 * rbase + g) * FFVD_XLD;
+    double s[RBB][4];
     {
       const double h[4] = {hz[0].x, hz[0].y, hz[1].x, hz[1].y};
 #pragma unroll
-      for (int rb = 0; rb < RB; ++rb) {
-        const double hx = (KIND == 0) ? sm.xn2h[row0 + 8 * rb + g] : 0.0;
+      for (int rb = 0; rb < RBB; ++rb) {
+        const double hx = (KIND == 0) ? sm.xn2h[row0 + 8 * (rbase + rb) + g] : 0.0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[rb][c] = (KIND == 0) ? hx + h[c] : 0.0;
       }
     }
-    for (int j0 = 0; j0 < (FFVD_ABLATE == 6 ? 0 : Din); j0 += RING) {
+    for (int j0 = 0; j0 < (FFVD_ABLATE == 6 ? 0 : Din); j0 += 8) {
 #pragma unroll
-      for (int u = 0; u < RING; ++u) {
-        const int jd = j0 + u;
-        if (KIND == 0 || jd < Din) {
-          const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
-          if (KIND == 0) {
-            if (j0 + RING < Din) ldg256_nc(ZTd + (size_t)(jd + RING) * Mp + jb, ring[u][0], ring[u][1]);   // uniform per trip
-          } else if (jd + RING < Din) {
-            ldg256_nc(ZTd + (size_t)(jd + RING) * Mp + jb, ring[u][0], ring[u][1]);
-          }
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1 && j0 + 4 >= Din) break;          // uniform
 #pragma unroll
-          for (int rb = 0; rb < RB; ++rb) {
-            const double x = xsrc[8 * rb * FFVD_XLD + jd];
+        for (int uu = 0; uu < 4; ++uu) {
+          const int u = 4 * half + uu, jd = j0 + u;
+          if (KIND == 0 || jd < Din) {
+            const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
+            if (KIND == 0) {
+              if (j0 + 8 + 4 * half < Din) ldg256_nc(ZTd + (size_t)(jd + 8) * Mp + jb, ring[u][0], ring[u][1]);   // uniform per half-trip
+            } else if (jd + 8 < Din) {
+              ldg256_nc(ZTd + (size_t)(jd + 8) * Mp + jb, ring[u][0], ring[u][1]);
+            }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) s[rb][c] = fma(x, z[c], s[rb][c]);
+            for (int rb = 0; rb < RBB; ++rb) {
+              const double x = xsrc[8 * rb * FFVD_XLD + jd];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) s[rb][c] = fma(x, z[c], s[rb][c]);
+            }
           }
         }
       }
     }
-    if (ng + 1 < NGW) prologue(16 * group_index(wc, ng + 1) + 4 * q);
+    // the first rows of the next pass are requested before the exp / store work of this one
+    if (pass + 1 < NGW * NPASS) prologue(16 * group_index<NCW>(wc, (pass + 1) / NPASS) + 4 * q);
     double vc[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) vc[c] = (jb + c < M) ? v : 0.0;
-    // exp in lock-step batches of RBB rows x 4 columns
-    constexpr int RBB = RB >= 4 ? 4 : (RB >= 2 ? 2 : 1);
+    double kv[RBB * 4];
 #pragma unroll
-    for (int rb0 = 0; rb0 < RB; rb0 += RBB) {
-      double kv[RBB * 4];
+    for (int i = 0; i < RBB; ++i)
 #pragma unroll
-      for (int i = 0; i < RBB; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) kv[4 * i + c] = s[rb0 + i][c];
+      for (int c = 0; c < 4; ++c) kv[4 * i + c] = s[i][c];
 #if FFVD_ABLATE != 5
-      if (KIND == 0) exp_nonpos_n<RBB * 4>(kv);
+    if (KIND == 0) exp_nonpos_n<RBB * 4>(kv, sm.exptab);
 #endif
 #pragma unroll
-      for (int i = 0; i < RBB; ++i) {
-        const int row = row0 + 8 * (rb0 + i) + g;
+    for (int i = 0; i < RBB; ++i) {
+      const int row = row0 + 8 * (rbase + i) + g;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) kv[4 * i + c] *= vc[c];
-        double* p = sm.tile + row * lda + jb;
-        *reinterpret_cast<double2*>(p) = make_double2(kv[4 * i], kv[4 * i + 1]);
-        *reinterpret_cast<double2*>(p + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
-        if (SCR && FFVD_ABLATE != 4) stg256(kscr + (size_t)row * Mp + jb, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
-      }
+      for (int c = 0; c < 4; ++c) kv[4 * i + c] *= vc[c];
+      double* p = sm.tile + row * lda + jb;
+      *reinterpret_cast<double2*>(p) = make_double2(kv[4 * i], kv[4 * i + 1]);
+      *reinterpret_cast<double2*>(p + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
+      if (SCR && FFVD_ABLATE != 4) stg256(kscr + (size_t)row * Mp + jb, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
     }
   }
 }
@@ -203,13 +209,13 @@ __device__ __forceinline__ void gemm_segments(double (&acc)[NG][RB][4], double2 
   }
 }
 
-template <int RB, int NGW, int TRI, class AOp>
+template <int RB, int NGW, int TRI, int NCW, class AOp>
 __device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const double* tile, int lda,
                                                 const double* __restrict__ B, int Mp, int warp, int ng0, int g, int q, AOp aop) {
   int joff[NGW];
 #pragma unroll
   for (int ng = 0; ng < NGW; ++ng) {
-    joff[ng] = 16 * group_index(warp, ng0 + ng);
+    joff[ng] = 16 * group_index<NCW>(warp, ng0 + ng);
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
@@ -239,27 +245,27 @@ __device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const
 
 // Column groups are processed at most 4 at a time so that the B-fragment prefetch ring and the running
 // pointers stay in registers for large M (NGW up to 16); the A fragments are re-read from shared memory per chunk.
-template <int RB, int NGW, int TRI, class AOp>
+template <int RB, int NGW, int TRI, int NCW, class AOp>
 __device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const double* tile, int lda,
                                           const double* __restrict__ B, int Mp, int warp, int g, int q, AOp aop) {
   if constexpr (NGW <= 4) {
-    tile_gemm_chunk<RB, NGW, TRI>(acc, tile, lda, B, Mp, warp, 0, g, q, aop);
+    tile_gemm_chunk<RB, NGW, TRI, NCW>(acc, tile, lda, B, Mp, warp, 0, g, q, aop);
   } else {
     static_assert(NGW % 2 == 0, "large NGW must be even");
     constexpr int CH = (NGW % 4 == 0) ? 4 : 2;
 #pragma unroll
     for (int c0 = 0; c0 < NGW; c0 += CH)
-      tile_gemm_chunk<RB, CH, TRI>(reinterpret_cast<double(&)[CH][RB][4]>(acc[c0]), tile, lda, B, Mp, warp, c0, g, q, aop);
+      tile_gemm_chunk<RB, CH, TRI, NCW>(reinterpret_cast<double(&)[CH][RB][4]>(acc[c0]), tile, lda, B, Mp, warp, c0, g, q, aop);
   }
 }
 
 // store the distributed (BT x Mp) fragment set into the shared tile
-template <int RB, int NGW>
+template <int RB, int NGW, int NCW>
 __device__ __forceinline__ void store_tile(const double (&acc)[NGW][RB][4], double* tile, int lda, int warp, int g,
                                            int q) {
 #pragma unroll
   for (int ng = 0; ng < NGW; ++ng) {
-    const int jb = 16 * group_index(warp, ng) + 4 * q;
+    const int jb = 16 * group_index<NCW>(warp, ng) + 4 * q;
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
       double* p = tile + (8 * rb + g) * lda + jb;
@@ -330,7 +336,7 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
   // The two warps that share an SM sub-partition (w and w+4) walk their lists in opposite directions: one starts with
   // full tiles, the other with its (shorter) diagonal tiles, so their flushes -- during which a warp issues no DMMA --
   // do not coincide and the partner keeps the tensor pipe busy.
-  const bool rev = (warp & 4) != 0;
+  const bool rev = NW >= 8 && (warp & 4) != 0;
   for (int ii = 0; ii < nu; ++ii) {
     const int i = rev ? nu - 1 - ii : ii;
     const int u = i * NW + ((i & 1) ? (NW - 1 - warp) : warp);
@@ -370,9 +376,11 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
   constexpr int BT = 8 * RB;
   const double* tile = sm.tile;
   // ---- W^T X~ : 8 warps own m-blocks w, w+8, ...  (NW == 16: warps 8..15, concurrently with W Z~ on warps 0..7)
-  if (NW == 8 || warp >= 8) {
-    const int wA = warp & 7;
-    constexpr int NMB = 2 * NGW;                 // m-blocks per warp = (Mp/8)/8
+  constexpr int NCW = NW < 8 ? NW : 8;         // column warps of the tile (Mp = 16 NGW NCW)
+  constexpr int NA = NCW;                      // warps that share each of the two products
+  if (NW <= 8 || warp >= 8) {
+    const int wA = warp % NA;
+    constexpr int NMB = 2 * NGW;                 // m-blocks per warp = (Mp/8)/NA
     constexpr int MCH = NMB < 4 ? NMB : 4;       // processed MCH at a time
     const int nbc = Din >> 3, qc = (Din & 7) >> 1, ec = Din & 1;   // where column Din (the ones) sits in a C fragment
     double lacc[NBM][2];
@@ -389,14 +397,14 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           for (int nb = 0; nb < NBM; ++nb)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              zr[u][nb][e] = (nb < nbx) ? __ldg(P.ZT + (size_t)(8 * nb + 2 * q + e) * Mp + 8 * (wA + 8 * (i0 + u)) + g) : 0.0;
+              zr[u][nb][e] = (nb < nbx) ? __ldg(P.ZT + (size_t)(8 * nb + 2 * q + e) * Mp + 8 * (wA + NA * (i0 + u)) + g) : 0.0;
       }
       double c[MCH][NBM][2];
 #pragma unroll
       for (int u = 0; u < MCH; ++u)
 #pragma unroll
         for (int nb = 0; nb < NBM; ++nb) c[u][nb][0] = c[u][nb][1] = 0.0;
-      const double* arow = tile + q * lda + 8 * (wA + 8 * i0) + g;
+      const double* arow = tile + q * lda + 8 * (wA + NA * i0) + g;
       const double* brow = sm.xs + q * FFVD_XLD + g;
 #pragma unroll 2
       for (int k0 = 0; k0 < BT; k0 += 4) {
@@ -405,7 +413,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
         for (int nb = 0; nb < NBM; ++nb) b[nb] = (nb < nbx) ? brow[k0 * FFVD_XLD + 8 * nb] : 0.0;
 #pragma unroll
         for (int u = 0; u < MCH; ++u) {
-          const double a = arow[k0 * lda + 64 * u];
+          const double a = arow[k0 * lda + 8 * NA * u];
 #pragma unroll
           for (int nb = 0; nb < NBM; ++nb)
             if (nb < nbx) dmma884(c[u][nb][0], c[u][nb][1], a, b[nb]);
@@ -419,7 +427,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
         for (int nb = 0; nb < NBM; ++nb)
           if (nb == nbc) csv = ec ? c[u][nb][1] : c[u][nb][0];
         const double cs = __shfl_sync(0xffffffffu, csv, g * 4 + qc);
-        const int m = 8 * (wA + 8 * (i0 + u)) + g;
+        const int m = 8 * (wA + NA * (i0 + u)) + g;
 #pragma unroll
         for (int nb = 0; nb < NBM; ++nb) {
           if (nb < nbx) {
@@ -462,13 +470,13 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
   //      Zf, requested PF trips (of 4 k-steps) ahead; each fragment feeds RPW DMMAs.
   constexpr int RPW = RB >= 2 ? 2 : 1;
   constexpr int RG = RB / RPW;                 // row groups
-  constexpr int KS = 8 / RG;                   // k slices (RB = 8: 2, 4: 4, 2: 8, 1: 8)
-  constexpr int KLEN = 128 * NGW / KS;         // columns of W per slice
+  constexpr int KS = NA / RG;                  // k slices (8 warps: RB = 8: 2, 4: 4, 2: 8, 1: 8)
+  constexpr int KLEN = 16 * NCW * NGW / KS;    // columns of W per slice
   constexpr int TRIPS = KLEN / 16;
   constexpr int PF = 2;
   constexpr int PW = 8 * NBM;                  // row stride of part
   static_assert(KS * BT <= 128, "part holds 128 rows");
-  if (warp < 8) {
+  if (warp < NA) {
     const int rg = warp % RG, ks = warp / RG;
     double c[RPW][NBM][2];
 #pragma unroll
@@ -560,14 +568,20 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
   extern __shared__ __align__(16) double smem_raw[];
   constexpr int BT = 8 * RB;
   constexpr int NTH = 32 * NW;
-  constexpr int RBW = RB / (NW / 8);
-  static_assert(RBW >= 1 && RBW * (NW / 8) == RB, "RB must be divisible by the row split");
+  constexpr int NCW = NW < 8 ? NW : 8;        // column warps; NW = 4: a half-width CTA built to run two per SM (MINB = 2)
+  constexpr int RBW = RB / (NW / NCW);
+  static_assert(RBW >= 1 && RBW * (NW / NCW) == RB, "RB must be divisible by the row split");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int wc = warp & 7, row0 = (warp >> 3) * 8 * RBW;
+  const int wc = warp % NCW, row0 = (warp / NCW) * 8 * RBW;
   double* kscr = kscr_base + (size_t)blockIdx.x * BT * probs[0].Mp;     // per-CTA K-tile scratch (BT x Mp)
 
   __shared__ DevProblem sP;
   int cur_pi = -1;
+  if (KIND == 0 && tid < 64) {      // exp table (read after the first CTA barrier of the item loop)
+    const int Mp0 = probs[0].Mp, Din0 = probs[0].Din;
+    double* tab = smem_raw + fused_smem_bytes(RB, Mp0, NW, (Din0 + 1 + 7) >> 3) / sizeof(double) - 64;
+    tab[tid] = g_exp2_tab[tid];
+  }
 #ifdef FFVD_PHASE_TIMING
   long long _phase_last = clock64();
 #endif
@@ -595,23 +609,39 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     const DevProblem& P = sP;
     const long long li = item - P.item_begin;
     // Work-item order inside a problem: blocks of `dblk` output dims (slowest), then (sample, tile), then d inside the
-    // block (fastest).  The dblk items of one (sample, tile) run on neighbouring CTAs at the same time, so the x tile
-    // is fetched from HBM once per block and its x-bar contributions meet in L2 (d slowest re-read X and re-wrote
-    // x-bar once per output dim: 8x the algorithmic DRAM bytes at C3); dblk is chosen by the host so that the L^{-1}
-    // / L^{-T} operands of one block (dblk * 16 Mp^2 bytes, streamed by every tile) stay a small part of L2.
-    int d, tile_i, s;
+    // block.  Two forms (chosen per problem by the host, DevProblem::dl):
+    //   dl == 1: one work item per (sample, tile, d), d fastest: the dblk items of one (sample, tile) run on neighbouring
+    //            CTAs at the same time, so the x tile is fetched from HBM once per block and its x-bar contributions meet
+    //            in L2 (small problems: as many items as possible for the persistent grid);
+    //   dl  > 1: one work item per (sample, tile, block of dblk dims): the CTA stages the x tile ONCE and loops over the
+    //            dims of the block (large problems: the staging latency -- an HBM round trip plus two barriers, 5% of an
+    //            item at C3 -- is paid once per dblk dims).
+    // Either way the L^{-1} / L^{-T} operands in flight at any time are those of one block (dblk * 16 Mp^2 bytes, chosen
+    // by the host to stay a small part of L2).
+    int d0, nd, tile_i, s;
     {
       const int DB = P.dblk;
-      const long long per_blk = (long long)P.S * P.ntiles * DB;
-      const int nfull = P.D / DB;
-      const long long blk = li / per_blk;
-      long long rem = li - blk * per_blk;
-      int bs = DB, d0 = (int)blk * DB;
-      if (blk >= nfull) { rem = li - (long long)nfull * per_blk; bs = P.D - nfull * DB; d0 = nfull * DB; }
-      d = d0 + (int)(rem % bs);
-      const long long st = rem / bs;
-      tile_i = (int)(st % P.ntiles);
-      s = (int)(st / P.ntiles);
+      if (P.dl > 1) {
+        const long long per = (long long)P.S * P.ntiles;
+        const long long blk = li / per;
+        const long long st = li - blk * per;
+        d0 = (int)blk * DB;
+        nd = min(DB, P.D - d0);
+        tile_i = (int)(st % P.ntiles);
+        s = (int)(st / P.ntiles);
+      } else {
+        const long long per_blk = (long long)P.S * P.ntiles * DB;
+        const int nfull = P.D / DB;
+        const long long blk = li / per_blk;
+        long long rem = li - blk * per_blk;
+        int bs = DB, db0 = (int)blk * DB;
+        if (blk >= nfull) { rem = li - (long long)nfull * per_blk; bs = P.D - nfull * DB; db0 = nfull * DB; }
+        d0 = db0 + (int)(rem % bs);
+        nd = 1;
+        const long long st = rem / bs;
+        tile_i = (int)(st % P.ntiles);
+        s = (int)(st / P.ntiles);
+      }
     }
     const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, Mp = P.Mp, nc = P.nc;
     const int lda = Mp + 4;
@@ -633,25 +663,14 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       sm.small = p; p += 64;
       sm.xn2h = p; p += 64;
       sm.sc = p; p += 8;
-      sm.red = p;
+      sm.red = p; p += 40;
+      sm.exptab = p;
     }
-    const int dh = d * P.hs;
 
     __syncthreads();   // previous item fully done with shared memory
-    // ---- P0: stage the x tile and per-d vectors.  The per-evaluation scalars (1/l, 1/l^2, v, Q, ...) and U^T come
-    //      precomputed from hyper_kernel; the scaled rows x~ = x/l and -1/2 |x~|^2 are formed in the same pass as the
-    //      raw rows: two CTA barriers instead of three.
-    const double* hyp = P.hyp + (size_t)dh * 72;
-    if (tid < 64) {
-      if (tid < 32) { sm.small[tid] = hyp[tid]; sm.small[32 + tid] = hyp[32 + tid]; }
-      if (tid < 40) sm.red[tid] = 0.0;
-      if (tid == 40) sm.sc[0] = hyp[64];
-      if (tid >= 41 && tid < 44) sm.sc[tid - 40] = P.hq[(size_t)d * 4 + (tid - 41)];
-    }
+    // ---- P0a: stage the raw x tile, once per work item.  All global loads of the tile are issued before the first one
+    //      is consumed (a load -> store loop pays one L2 / HBM latency per trip: ~5k clk per work item at C3).
     {
-      const double silc = (KIND == 0 && lane < Din) ? hyp[32 + lane] : 0.0;
-      // all global loads of the tile are issued before the first one is consumed (a load -> store loop pays one
-      // L2 / HBM latency per trip: ~5k clk per work item at C3)
       constexpr int NIT = ((BT + 1) * FFVD_XCOLS + NTH - 1) / NTH;
       double xv[NIT];
 #pragma unroll
@@ -670,25 +689,48 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       for (int it = 0; it < NIT; ++it) {
         const int idx = tid + it * NTH;
         const int r = idx >> 5, c = idx & 31;
-        if (r <= BT) {
-          const double sv = xv[it] * silc;             // 0 for c >= Din
-          sm.xs[r * FFVD_XLD + c] = (c == Din) ? ((r < nvalid) ? 1.0 : 0.0) : xv[it];
-          if (KIND == 0 && r < BT) sm.xsc[r * FFVD_XLD + c] = sv;
-        }
+        if (r <= BT) sm.xs[r * FFVD_XLD + c] = (c == Din) ? ((r < nvalid) ? 1.0 : 0.0) : xv[it];
       }
-      if (KIND == 0 && tid >= NTH - BT) {
-        // -1/2 |x~_r|^2, one thread per row, straight from global memory (the same lines the loop above just
-        // requested: L1 hits) so that it needs no barrier of its own; same rounded products as xsc
-        const int r = tid - (NTH - BT), t = t0 + r;
+    }
+  for (int di = 0; di < nd; ++di) {
+    const int d = d0 + di;
+    const int dh = d * P.hs;
+    // ---- P0b: per-d vectors.  The per-evaluation scalars (1/l, 1/l^2, v, Q, ...) and U^T come precomputed from
+    //      hyper_kernel; the scaled rows x~ = x/l and -1/2 |x~|^2 are formed from the staged tile.
+    const double* hyp = P.hyp + (size_t)dh * 72;
+    // requests for this d's vectors go out before the barrier that retires the previous d's use of shared memory
+    const double silc = (KIND == 0 && lane < Din) ? __ldg(hyp + 32 + lane) : 0.0;
+    double hv0 = 0.0, hv1 = 0.0, scv = 0.0;
+    if (tid < 32) { hv0 = __ldg(hyp + tid); hv1 = __ldg(hyp + 32 + tid); }
+    if (tid == 40) scv = __ldg(hyp + 64);
+    if (tid >= 41 && tid < 44) scv = __ldg(P.hq + (size_t)d * 4 + (tid - 41));
+    __syncthreads();   // x tile staged (di == 0) / previous d fully done with shared memory (di > 0)
+    if (tid < 64) {
+      if (tid < 32) { sm.small[tid] = hv0; sm.small[32 + tid] = hv1; }
+      if (tid < 40) sm.red[tid] = 0.0;
+      if (tid == 40) sm.sc[0] = scv;
+      if (tid >= 41 && tid < 44) sm.sc[tid - 40] = scv;
+    }
+    if (KIND == 0) {
+      // x~ = x / l (same rounded products in xsc and in -1/2 |x~|^2)
+      for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
+        const int r = idx >> 5;                         // column == lane
+        sm.xsc[r * FFVD_XLD + lane] = sm.xs[r * FFVD_XLD + lane] * silc;
+      }
+      // -1/2 |x~_r|^2: a quarter-warp per row (8 lanes x 4 columns), rows dealt to the warps
+      for (int r = (tid >> 3); r < BT; r += NTH / 8) {
+        const int l8 = tid & 7;
         double a = 0.0;
-        if (r <= nvalid && t < P.xrows) {
-          for (int c = 0; c < Din; ++c) {
-            const double x = (c < Dx) ? Xs[(size_t)t * Dx + c] : ((t < T) ? P.ctrl[(size_t)t * nc + (c - Dx)] : 0.0);
-            const double sv = x * hyp[32 + c];
-            a = fma(sv, sv, a);
-          }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int c = l8 + 8 * c4;
+          const double sv = sm.xs[r * FFVD_XLD + c] * ((c < Din) ? __ldg(hyp + 32 + c) : 0.0);
+          a = fma(sv, sv, a);
         }
-        sm.xn2h[r] = -0.5 * a;
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (l8 == 0) sm.xn2h[r] = -0.5 * a;
       }
     }
     for (int j = tid; j < Mp; j += NTH) {
@@ -704,7 +746,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     FFVD_MARK(0);
 
     // ---- P1: K tile -> shared (SE uncollapsed: also to this CTA's L2-resident scratch, needed again for W = Kbar o K)
-    compute_k_tile<KIND, RBW, NGW, (KIND == 0 && MODE == MODE_UNCOLLAPSED)>(
+    compute_k_tile<KIND, RBW, NGW, (KIND == 0 && MODE == MODE_UNCOLLAPSED), NCW>(
         sm, (KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT, Mp, Din, v, wc, g, q, M, row0, lda, kscr);
     if (nvalid < BT) {
       // partial last tile of a sample: rows >= nvalid must be inert (exact zeros)
@@ -721,7 +763,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 
     if (MODE != MODE_COLLAPSED_P2) {
       // ---- P2: A = K L^{-T}   (rows a_t = L^{-1} k_t)
-      tile_gemm<RBW, NGW, +1>(acc, wtile, lda, LinvT, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, +1, NCW>(acc, wtile, lda, LinvT, Mp, wc, g, q,
                               [](double x, int, int) { return x; });
       // row partial sums: a.u and a.a
       {
@@ -730,7 +772,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         for (int rb = 0; rb < RBW; ++rb) su[rb] = sa[rb] = sq[rb] = 0.0;
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
-          const int jb = 16 * group_index(wc, ng) + 4 * q;
+          const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const double u = sm.us[jb + c];
@@ -765,7 +807,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
       __syncthreads();          // everyone is done reading K from the tile
       FFVD_MARK(2);
-      if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
+      if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);
       // ---- per-row statistics (threads 0..BT-1)
       if (tid < 64) {
         double jxq = 0.0, jtr = 0.0, gq = 0.0, gvd = 0.0;
@@ -775,7 +817,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
           if (r < nvalid) {
             double su = 0.0, sa = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < NCW; ++w) {
               su += sm.rowpart[(0 * 8 + w) * BT + r];
               sa += sm.rowpart[(1 * 8 + w) * BT + r];
             }
@@ -791,7 +833,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
               // conditionals_multi_output.py:41,48 : fvar = Knn - sum A^2 ; fmean = A^T f ; :50-52 q_sqrt (M,R) term
               double sq = 0.0;
 #pragma unroll
-              for (int w = 0; w < 8; ++w) sq += sm.rowpart[(2 * 8 + w) * BT + r];
+              for (int w = 0; w < NCW; ++w) sq += sm.rowpart[(2 * 8 + w) * BT + r];
               // REUSE_KZZ content guard (hyper_kernel): factors that do not belong to this Z poison the result
               const bool stale = P.guard && P.guard[3] != 0;
               P.cond_mean[(size_t)(t0 + r) * D + d] = stale ? __longlong_as_double(0x7ff8000000000000ll) : su;
@@ -864,9 +906,9 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_COND && P.qmode == 3) {
       // conditionals_multi_output.py:53-62 (q_sqrt R x M x M): fvar += sum_m (Q^T a_t)_m^2, a second contraction of the A
       // tile (still in registers) with the dense zero-padded factor
-      store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
+      store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);
       __syncthreads();
-      tile_gemm<RBW, NGW, 0>(acc, wtile, lda, P.qmat + (size_t)(P.nq == 1 ? 0 : d) * Mp * Mp, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, 0, NCW>(acc, wtile, lda, P.qmat + (size_t)(P.nq == 1 ? 0 : d) * Mp * Mp, Mp, wc, g, q,
                              [](double x, int, int) { return x; });
       double sq[RBW];
 #pragma unroll
@@ -887,7 +929,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       if (tid < nvalid) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sm.rowpart[(2 * 8 + w) * BT + tid];
+        for (int w = 0; w < NCW; ++w) t += sm.rowpart[(2 * 8 + w) * BT + tid];
         P.cond_var[(size_t)(t0 + tid) * D + d] += t;      // written by this same thread above
       }
     }
@@ -908,7 +950,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g];
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
-          const int jb = 16 * group_index(wc, ng) + 4 * q;
+          const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             double t = 0.0;
@@ -932,14 +974,14 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_UNCOLLAPSED) {
       // ---- P4: Kbar = Abar L^{-1} with abar_r = e_r u + a_r / Q.  By linearity Kbar = (A L^{-1})/Q + e w^T with
       //      w = L^{-T} u (ltu_kernel, once per evaluation), so the contraction reads A unmodified.
-      tile_gemm<RBW, NGW, -1>(acc, wtile, lda, Linv, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, -1, NCW>(acc, wtile, lda, Linv, Mp, wc, g, q,
                               [](double x, int, int) { return x; });
       double er[RBW];
 #pragma unroll
       for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g];
 #pragma unroll
       for (int ng = 0; ng < NGW; ++ng) {
-        const int jb = 16 * group_index(wc, ng) + 4 * q;
+        const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const double w = sm.ws[jb + c];
@@ -949,7 +991,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
     } else if (MODE == MODE_COLLAPSED_P2) {
       // ---- Kbar = K N + delta w'^T ; also dbar_r = k_r . w'
-      tile_gemm<RBW, NGW, 0>(acc, wtile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, 0, NCW>(acc, wtile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, g, q,
                              [](double x, int, int) { return x; });
     }
 
@@ -995,7 +1037,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       {
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
-          const int jb = 16 * group_index(wc, ng) + 4 * q;
+          const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
           double kv[RBW][4];
           if (KIND == 0) {
             if (MODE == MODE_COLLAPSED_P2) {
@@ -1023,7 +1065,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             }
         }
         __syncthreads();        // all warps done reading A (GEMM2 / SYRK) or K (pass 2)
-        store_tile<RBW, NGW>(acc, wtile, lda, wc, g, q);
+        store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);
       }
       __syncthreads();
       FFVD_MARK(6);
@@ -1054,7 +1096,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         if (MODE != MODE_COLLAPSED_P1) red_add(P.gv + d, (sm.red[3] + sm.red[7]) + (sm.red[8] + sm.red[9]));
       }
     }
-  }
+  }   // d loop
+  }   // item loop
 }
 
 }  // namespace ffvd

@@ -52,9 +52,24 @@ def unpack(flat, outputs: Dict[str, object], present: Sequence[str]):
         o += k
 
 
-def allreduce_shared(outputs: Dict[str, object], group=None, names: Sequence[str] = SHARED):
-    """Sum the shared-parameter gradients over ranks in ONE collective (packed buffer)."""
+def init_native_comm(ctx, group=None):
+    """Create the context's own NCCL communicator (`ffvd_comm_init`, the collective behind the C ABI): rank 0 makes the
+    128-byte unique id, `torch.distributed` (any backend) only ships it.  Afterwards `ctx.allreduce_shared(outputs)` packs,
+    reduces and unpacks in three launches on the context's stream, with no torch op on the path."""
     import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(box[0], rank, world)
+    return rank, world
+
+
+def allreduce_shared(outputs: Dict[str, object], group=None, names: Sequence[str] = SHARED, ctx=None):
+    """Sum the shared-parameter gradients over ranks in ONE collective (packed buffer).  With `ctx` (a context whose
+    native communicator was set up by `init_native_comm`) the C-ABI collective is used; otherwise torch.distributed."""
+    import torch.distributed as dist
+    if ctx is not None and ctx.comm_info()[1] > 1:
+        return ctx.allreduce_shared(outputs)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return outputs
     flat, present = pack(outputs, names)

@@ -16,9 +16,15 @@ class Gaussian(object):
         self.trainable = bool(likelihood_traning) and not hyperparameter_sampling
         self.CC = np.ones((X_output_dim, Y_dim)) if CC is None else as_f64(CC)              # :12-24
         self.DD = np.zeros((Y_dim,)) if DD is None else as_f64(DD)
+        self._fixed_R = None
         if Y_dim != 1:
-            raise NotImplementedError("Y_dim > 1 uses a non-trainable masked Cholesky in the reference (likelihoods.py:56-61); "
-                                      "the bundled data are all Y_dim == 1")
+            # likelihoods.py:56-61: a NON-trainable factor, ones below the diagonal and exp(log 1.5) on it; RR_chol is ignored
+            # and there is no log_Rchols attribute (so, as in the reference, a DGPSSM cannot be built on top of it:
+            # dgp_model.py:250,333 read likelihood.Rchols[0] / likelihood.log_Rchols)
+            self.Rchols_initial = np.ones((Y_dim, Y_dim))
+            self.Rchols_diag = np.ones(Y_dim) * np.log(1.5)
+            self._Rchols_full = self.Rchols_initial * np.tril(np.ones((Y_dim, Y_dim)), -1) + np.diag(np.exp(self.Rchols_diag))
+            return
         if RR_chol is None:
             self.log_Rchols = np.ones((Y_dim, Y_dim)) * np.log(0.1)                              # :50-52
         else:
@@ -28,6 +34,8 @@ class Gaussian(object):
 
     @property
     def Rchols(self):
+        if getattr(self, "_Rchols_full", None) is not None:
+            return self._Rchols_full
         L = self.log_Rchols
         return L.exp() if is_torch(L) else np.exp(L)
 
@@ -66,11 +74,16 @@ def logdensity_norm_diag(y, ymean, Rchols):
 
 
 def logdensity_norm(y, ymean, Rchols):
-    """`likelihoods.py:114-127` with a full lower-triangular factor.  Only used by the out-of-scope
-    particle-Gibbs sampler; served here for diagonal factors (Dy == 1 in all bundled data)."""
-    R = as_f64(Rchols)
-    Rn = R.detach().cpu().numpy() if is_torch(R) else R
-    if Rn.ndim == 2 and np.count_nonzero(Rn - np.diag(np.diag(Rn))) != 0:
-        raise NotImplementedError("non-diagonal noise Cholesky is only used by the particle-Gibbs sampler (out of scope)")
-    diag = np.diag(Rn) if Rn.ndim == 2 else Rn
-    return _ld(y, ymean, diag, True)
+    """`likelihoods.py:114-127` with a full lower-triangular factor (forward substitution on the device; the strictly
+    upper triangle is ignored, as by `tf.linalg.triangular_solve(lower=True)`).  `y` may be a single row broadcast against
+    the rows of `ymean` (the reference's `self.Y[tt] - y_t_mu`, base_model.py:62-66).  Returns (N,)."""
+    ymean = as_f64(ymean)
+    if ymean.ndim == 1:
+        ymean = ymean[None, :]
+    y = to_lib(ymean, as_f64(y))
+    R = to_lib(ymean, as_f64(Rchols))
+    Dy = ymean.shape[1]
+    if R.ndim != 2:
+        R = R.reshape(Dy, Dy)
+    out = empty_like_lib(ymean, (ymean.shape[0],))
+    return context_for(ymean).logdensity_norm(y, ymean, R, out)

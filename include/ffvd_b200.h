@@ -110,6 +110,10 @@ int ffvd_ctx_fused_time(ffvd_ctx* ctx, int reset, double* total_ms, int64_t* cou
  * Only in builds made with -DFFVD_PHASE_TIMING (tools/phase_timing.py); FFVD_E_UNSUPPORTED otherwise. */
 int ffvd_debug_phase_clocks(ffvd_ctx* ctx, int reset, uint64_t* out16);
 
+/* Diagnostic: out[i] = the fused kernels' branch-free exp routine at x[i] <= 0 (kernels_multi_output.py:246-247 K_r2 is
+ * exp(-r2/2); accuracy test against libm). */
+int ffvd_debug_exp(ffvd_ctx* ctx, DLManagedTensor* x, DLManagedTensor* out);
+
 /* kernels_multi_output.py:202-214,246-247 / kernels.py:270-276  K(X, X2) -> out (N,N2).
  * X2 may be NULL (K(X,X)).  logv: () ; logl: (Din) for SE, NULL for Linear. */
 int ffvd_kernel_K(ffvd_ctx*, int kind, DLManagedTensor* X, DLManagedTensor* X2,
@@ -157,6 +161,12 @@ int ffvd_collapse_u_mean(ffvd_ctx*, int kind, const ffvd_problem* p, double jitt
 int ffvd_logdensity_norm_diag(ffvd_ctx*, DLManagedTensor* y, DLManagedTensor* ymean,
                               DLManagedTensor* Rchols, int vec, DLManagedTensor* out);
 
+/* likelihoods.py:114-127 logdensity_norm with a full lower-triangular factor Rchols (Dy,Dy): out[n] =
+ * -1/2 |L^{-1}(y_n - ymean_n)|^2 - sum log L_ii (no -0.5 log 2pi).  y is (N,Dy) or ONE row (Dy) broadcast over the N rows
+ * of ymean (the particle-Gibbs weights, base_model.py:62-66).  Dy <= 64. */
+int ffvd_logdensity_norm(ffvd_ctx*, DLManagedTensor* y, DLManagedTensor* ymean, DLManagedTensor* Rchols,
+                         DLManagedTensor* out);
+
 /* dgp_model.py:248-297 + tf.gradients (base_model.py:148): uncollapsed q(u) (cases 1,2,3,6,7;
  * regularizer :337-359) and collapsed-u bound (cases 4,5; conditionals_multi_output.py:230-257). */
 int ffvd_nll_grads_uncollapsed(ffvd_ctx*, int kind, const ffvd_problem* p, int flags, double jitter,
@@ -167,6 +177,23 @@ int ffvd_nll_grads_collapsed(ffvd_ctx*, int kind, const ffvd_problem* p, int fla
  * BASELINE config 4 (many small chains). */
 int ffvd_nll_grads_batched(ffvd_ctx*, int kind, int collapsed, int nprob, const ffvd_problem* p,
                            int flags, double jitter, const ffvd_outputs* o);
+
+/* ---- multi-GPU (the reference is single-process, so these replace nothing in it: they are what a sharded
+ * caller of dgp_model.py:248-297 needs).  One NCCL communicator per context; NCCL is loaded at run time (libnccl.so.2, or
+ * FFVD_NCCL_LIB) and shared with whatever already loaded it (PyTorch).  All collectives run on the context's stream. */
+/* rank 0: fill a 128-byte NCCL unique id; the caller ships it to the other ranks (MPI, torch.distributed, a file) */
+int ffvd_comm_unique_id(void* id128);
+int ffvd_comm_init(ffvd_ctx*, const void* id128, int rank, int nranks);
+int ffvd_comm_destroy(ffvd_ctx*);
+int ffvd_comm_info(ffvd_ctx*, int* rank, int* nranks, int* nccl_version);
+/* In-place sum over the ranks of the shared-parameter gradients of one evaluation (g_Z, g_U, g_logv, g_logl, g_logQ, g_C,
+ * g_d, g_logR; with_scalars != 0: also nll and terms, for time-sharded evaluations) in ONE ncclAllReduce on a packed
+ * buffer; g_X is never communicated.  Device tensors only.  A context without a communicator (or nranks == 1) returns
+ * immediately. */
+int ffvd_allreduce_shared(ffvd_ctx*, const ffvd_outputs* o, int with_scalars);
+/* In-place sum over the ranks of one device tensor (the collapsed bound's F^T F / F^T delta statistics under time
+ * sharding, conditionals_multi_output.py:246-254). */
+int ffvd_allreduce(ffvd_ctx*, DLManagedTensor* t);
 
 /* base_model.py:143-179 generate_update_step: one adaptive SG-HMC update, in place, Jacobi
  * semantics.  All tensors same shape.  noise ~ N(0,1) supplied by the caller (base_model.py:171).

@@ -829,3 +829,51 @@ def test_device_data_generator(env):
     d = bench.make_device_data(500, 64, 3, 2, seed=1, dev=env["dev"])
     assert tuple(d["X"].shape) == (2, 501, 3) and tuple(d["Y"].shape) == (500, 1) and tuple(d["ctrl"].shape) == (500, 1)
     assert abs(float(d["X"].std()) - 1.0) < 0.3
+
+
+def test_logdensity_norm_full_factor_and_multi_output_gaussian(env):
+    """likelihoods.py:114-127 with a full lower-triangular factor (device forward substitution) vs the reference-source
+    golden; a single y row broadcast over ymean (base_model.py:62-66); Gaussian(Y_dim > 1) carries the reference's fixed
+    masked factor (likelihoods.py:56-61)."""
+    import torch as th
+    from ffvd_b200 import likelihoods
+    g = load_golden()
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    y, ym, Rc = g["op/ld/y"], g["op/ld/ymean"], g["op/ld/Rfull"]
+    out = likelihoods.logdensity_norm(t(y), t(ym), t(Rc))
+    assert_close(g["op/ld/full"], out.cpu().numpy(), 1e-13, "logdensity_norm full factor")
+    assert_close(g["op/ld/full"], likelihoods.logdensity_norm(y, ym, Rc), 1e-13, "host tensors")       # NumPy in, NumPy out
+    # garbage above the diagonal is ignored (triangular_solve(lower=True))
+    Rg = Rc.copy(); Rg[0, 1] = 123.0
+    assert_close(g["op/ld/full"], likelihoods.logdensity_norm(t(y), t(ym), t(Rg)).cpu().numpy(), 1e-13)
+    # one row of y against many rows of ymean
+    ref = np.array([-0.5 * np.sum(np.linalg.solve(np.tril(Rc), (y[3] - ym[n])) ** 2) - np.sum(np.log(np.diag(Rc))) for n in range(ym.shape[0])])
+    assert_close(ref, likelihoods.logdensity_norm(t(y[3]), t(ym), t(Rc)).cpu().numpy(), 1e-12, "broadcast row")
+    # a 5-output factor
+    rng = np.random.default_rng(3)
+    L5 = np.tril(rng.standard_normal((5, 5))) + 3.0 * np.eye(5)
+    y5, m5 = rng.standard_normal((40, 5)), rng.standard_normal((40, 5))
+    ref5 = -0.5 * np.sum(np.linalg.solve(L5, (y5 - m5).T) ** 2, axis=0) - np.sum(np.log(np.diag(L5)))
+    assert_close(ref5, likelihoods.logdensity_norm(t(y5), t(m5), t(L5)).cpu().numpy(), 1e-12, "Dy=5")
+    lik = likelihoods.Gaussian(3, 4)
+    assert lik.Rchols.shape == (3, 3) and np.allclose(np.diag(lik.Rchols), 1.5) and lik.Rchols[1, 0] == 1.0 and lik.Rchols[0, 1] == 0.0
+    assert not hasattr(lik, "log_Rchols")
+    pm = lik.predict_mean(t(rng.standard_normal((7, 4))))
+    assert tuple(pm.shape) == (7, 3)
+
+
+def test_device_exp_routine_accuracy(env):
+    """The branch-free table exp of the K tile (kernels_multi_output.py:246-247: K_r2 = exp(-r2/2)) against libm: <= 2 ulp
+    over the whole range the SE argument can take, exact 1 at 0, saturation (not garbage) for hugely negative arguments."""
+    torch, ctx = env["torch"], env["ctx"]
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-rng.uniform(0, 50, 200000), -rng.uniform(0, 1e-3, 20000), -rng.uniform(50, 700, 50000), [0.0, -1e-300, -0.5, -708.0]])
+    xd = torch.as_tensor(x, device=env["dev"])
+    out = ctx.debug_exp(xd, torch.empty_like(xd)).cpu().numpy()
+    ref = np.exp(x)
+    ulp = np.abs(out - ref) / np.spacing(ref)
+    assert ulp.max() <= 2.0, ulp.max()
+    assert out[-4] == 1.0
+    big = torch.as_tensor(np.array([-746.0, -1e4, -1e9, -1e15, -1e300, -np.inf]), device=env["dev"])
+    sat = ctx.debug_exp(big, torch.empty_like(big)).cpu().numpy()
+    assert np.all(np.isfinite(sat)) and np.all(sat >= 0) and np.all(sat < 1e-300)
