@@ -24,6 +24,9 @@ FLAG_NO_X0_PRIOR = 32
 FLAG_REUSE_KZZ = 64
 FLAG_NO_GRADS = 4
 FLAG_ASYNC = 8
+FLAG_COLLAPSED_P1_ONLY = 128
+FLAG_COLLAPSED_RESUME = 256
+FLAG_NO_REPLICATED = 512
 
 _PROBLEM_FIELDS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR", "Y", "ctrl")
 _OUTPUT_FIELDS = ("nll", "terms", "g_X", "g_Z", "g_U", "g_logv", "g_logl", "g_logQ", "g_C", "g_d", "g_logR")
@@ -95,6 +98,16 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_comm_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.ffvd_allreduce_shared.argtypes = [vp, ctypes.POINTER(_Outputs), ci]
     lib.ffvd_allreduce.argtypes = [vp, vp]
+    lib.ffvd_graph_capture_begin.argtypes = [vp]
+    lib.ffvd_graph_capture_end.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.ffvd_graph_launch.argtypes = [vp, vp]
+    lib.ffvd_graph_kernel_count.argtypes = [vp]
+    lib.ffvd_graph_kernel_count.restype = cll
+    lib.ffvd_graph_destroy.argtypes = [vp, vp]
+    lib.ffvd_collapsed_stats_shape.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.ffvd_collapsed_stats_allreduce.argtypes = [vp]
+    lib.ffvd_collapsed_stats_get.argtypes = [vp, vp, vp]
+    lib.ffvd_collapsed_stats_set.argtypes = [vp, vp, vp]
     lib.ffvd_nll_grads_uncollapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
     lib.ffvd_nll_grads_collapsed.argtypes = [vp, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
     lib.ffvd_nll_grads_batched.argtypes = [vp, ci, ci, ci, ctypes.POINTER(_Problem), ci, cd, ctypes.POINTER(_Outputs)]
@@ -104,7 +117,9 @@ def load_library() -> ctypes.CDLL:
                  "ffvd_kernel_pre_cal", "ffvd_conditional", "ffvd_logdensity_norm_diag", "ffvd_nll_grads_uncollapsed",
                  "ffvd_nll_grads_collapsed", "ffvd_nll_grads_batched", "ffvd_sghmc_update", "ffvd_adam_update",
                  "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks", "ffvd_conditional_ex", "ffvd_logdensity_norm", "ffvd_debug_exp", "ffvd_comm_unique_id", "ffvd_comm_init",
-                 "ffvd_comm_destroy", "ffvd_comm_info", "ffvd_allreduce_shared", "ffvd_allreduce"):
+                 "ffvd_comm_destroy", "ffvd_comm_info", "ffvd_allreduce_shared", "ffvd_allreduce", "ffvd_collapsed_stats_shape",
+                 "ffvd_collapsed_stats_allreduce", "ffvd_collapsed_stats_get", "ffvd_collapsed_stats_set", "ffvd_graph_capture_begin",
+                 "ffvd_graph_capture_end", "ffvd_graph_launch", "ffvd_graph_destroy"):
         getattr(lib, name).restype = ci
     _lib = lib
     return lib
@@ -175,6 +190,33 @@ class PreparedCall:
 
     def close(self):
         self._b.release()
+
+
+class Graph:
+    """A captured sequence of evaluations / updates (`Context.capture`); `launch()` replays it as one CUDA-graph launch.
+    Keeps the tensors of the captured calls alive."""
+
+    def __init__(self, ctx, handle, keep):
+        self._ctx, self._h, self._keep = ctx, handle, keep
+
+    @property
+    def kernels(self) -> int:
+        return int(self._ctx._lib.ffvd_graph_kernel_count(self._h))
+
+    def launch(self):
+        _check(self._ctx._lib.ffvd_graph_launch(self._ctx._h, self._h))
+
+    def close(self):
+        if self._h:
+            self._ctx._lib.ffvd_graph_destroy(self._ctx._h, self._h)
+            self._h = None
+        self._keep = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -274,6 +316,23 @@ class Context:
             b.release()
         return out
 
+    # ---- CUDA graphs
+    def capture(self, fn, keep=None) -> "Graph":
+        """Run `fn()` (calls of nll_grads / sghmc_update / adam_update on this context, FLAG_ASYNC, device tensors) under
+        stream capture and return the instantiated graph.  Make the same calls once BEFORE capturing (workspace layout).
+        `keep`: objects (tensors) that must stay alive as long as the graph."""
+        _check(self._lib.ffvd_graph_capture_begin(self._h))
+        h = ctypes.c_void_p()
+        try:
+            fn()
+        except BaseException:
+            self._lib.ffvd_graph_capture_end(self._h, ctypes.byref(h))
+            if h:
+                self._lib.ffvd_graph_destroy(self._h, h)
+            raise
+        _check(self._lib.ffvd_graph_capture_end(self._h, ctypes.byref(h)))
+        return Graph(self, h, keep)
+
     # ---- multi-GPU: NCCL communicator behind the C ABI
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -313,6 +372,30 @@ class Context:
         finally:
             b.release()
         return tensor
+
+    # ---- collapsed bound under time sharding: statistics of a pending FLAG_COLLAPSED_P1_ONLY evaluation
+    def collapsed_stats_shape(self):
+        nb, Mp = ctypes.c_int(0), ctypes.c_int(0)
+        _check(self._lib.ffvd_collapsed_stats_shape(self._h, ctypes.byref(nb), ctypes.byref(Mp)))
+        return nb.value, Mp.value
+
+    def collapsed_stats_allreduce(self):
+        _check(self._lib.ffvd_collapsed_stats_allreduce(self._h))
+
+    def collapsed_stats_get(self, S_out, b_out):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_collapsed_stats_get(self._h, b.ptr(S_out), b.ptr(b_out)))
+        finally:
+            b.release()
+        return S_out, b_out
+
+    def collapsed_stats_set(self, S_in, b_in):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_collapsed_stats_set(self._h, b.ptr(S_in), b.ptr(b_in)))
+        finally:
+            b.release()
 
     def debug_exp(self, x, out):
         b = _Borrow()

@@ -70,10 +70,60 @@ class BaseModel(object):
         # base_model.py:188-194: always the full batch; decayed Adam learning rate
         return [0, self.X_N], 0.003 * (0.95 ** (global_step / 1000))
 
+    def enable_graph(self, enable: bool = True):
+        """Run `sghmc_step` as ONE CUDA-graph launch: the reference's 21 `session.run` calls (base_model.py:919-925) are 21
+        evaluations x ~10 kernels + 21 x len(vars) updates; captured once, replayed per step.  The injected noise lives in
+        fixed buffers refilled before every launch (graphs capture addresses, not values)."""
+        self._use_graph = bool(enable)
+        g = getattr(self, "_graph", None)
+        if g is not None:
+            g.close()
+        self._graph = None
+
+    def _sghmc_step_graph(self, noise_fn=None):
+        import torch
+        from . import _capi
+        ctx = self.ctx
+        if getattr(self, "_graph", None) is None:
+            self.evaluate()                               # lays out the workspace and the output tensors (capture needs both)
+            self._gnoise = {n: torch.empty((21,) + tuple(self.params[n].shape), dtype=torch.float64, device=self.device) for n in self.vars}
+            prob = dict(self.params); prob.update(self.data); prob.setdefault("logl", None)
+            fixed_kzz = not any(n in ("Z", "logv", "logl") for n in self.vars)
+            X_N = float(self.X_N)
+
+            def body():
+                for k in range(21):
+                    burn_in = (k == 0) or (k % 2 == 1)    # burn-in, then 10 x (burn-in, sample): base_model.py:919-925
+                    fl = self.flags | _capi.FLAG_ASYNC | (_capi.FLAG_REUSE_KZZ if (k > 0 and fixed_kzz) else 0)
+                    ctx.nll_grads(self.kind, self.U_collapse, prob, self._out, flags=fl, jitter=1e-5)
+                    for n in self.vars:
+                        st = self.sghmc_state[n]
+                        ctx.sghmc_update(self.params[n], self._out["g_" + n], self._gnoise[n][k], st["xi"], st["g"], st["g2"], st["p"],
+                                         self.epsilon, self.mdecay, X_N, burn_in)
+            self._graph = ctx.capture(body, keep=(prob, self._out, self._gnoise, self.sghmc_state))
+        for n in self.vars:
+            if noise_fn is None:
+                self._gnoise[n].normal_()
+            else:
+                for k in range(21):
+                    nz = noise_fn(k)[n]
+                    self._gnoise[n][k].copy_(nz if torch.is_tensor(nz) else torch.as_tensor(np.asarray(nz), dtype=torch.float64, device=self.device))
+        self._graph.launch()
+        self._kzz_clean = False
+        if not bool(torch.isfinite(self._out["nll"]).all()):     # no status read-back inside a graph: NaN is the failure signal
+            raise FloatingPointError("sghmc_step (CUDA graph): non-finite nll -- K(Z,Z) + jitter not positive definite, or a diverged chain")
+
     # ---- base_model.py:915-933
     def sghmc_step(self, noise_fn=None):
         """1 burn-in update, then 10 x (burn-in, sample); snapshot the sampled variables into the
         window (21 nll+gradient evaluations)."""
+        if getattr(self, "_use_graph", False) and self.vars:
+            self._sghmc_step_graph(noise_fn)
+            sample = {name: self.params[name].clone() for name in self.vars}
+            self.window.append(sample)
+            if len(self.window) > self.window_size:
+                self.window = self.window[-self.window_size:]
+            return
         k = 0
 
         def nz():

@@ -35,6 +35,13 @@ static int fail(int code, const std::string& msg) {
       return fail(FFVD_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
   } while (0)
 
+struct ffvd_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<void*> pinned;      // descriptor copies the captured H2D nodes read at every replay
+  int64_t kernels = 0;            // kernel nodes (launch accounting)
+};
+
 struct ffvd_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -55,6 +62,9 @@ struct ffvd_ctx {
   std::vector<long long> kzz_key;
   size_t last_off_cvec = 0, last_off_HxT = 0;
   int last_Mp = 0, last_nb = 0;
+  bool p1_pending = false;         // FFVD_FLAG_COLLAPSED_P1_ONLY left its statistics in the arena; FFVD_FLAG_COLLAPSED_RESUME consumes them
+  std::vector<long long> p1_key;
+  size_t p1_off_S = 0, p1_bytes = 0; int p1_nb = 0, p1_Mp = 0;
   int cur_rb = 0;                  // tile height (row blocks of 8) chosen for the call in flight, 0 = fused_cfg's default
   int probs_cap = 0;
   int* h_status = nullptr;     // pinned
@@ -63,6 +73,10 @@ struct ffvd_ctx {
   static const int kRing = 256;
   cudaEvent_t ev0[kRing], ev1[kRing];
   long long ev_count = 0;
+  // CUDA-graph capture (ffvd_graph_capture_begin / _end): work is captured on cap_stream, replayed into the caller's stream
+  bool capturing = false;
+  cudaStream_t user_stream = nullptr, cap_stream = nullptr;
+  struct ffvd_graph* cur_graph = nullptr;
   // NCCL communicator (ffvd_comm_init) and the packed all-reduce buffer
   NcclComm comm = nullptr;
   int comm_rank = 0, comm_nranks = 1;
@@ -120,6 +134,7 @@ extern "C" int ffvd_ctx_destroy(ffvd_ctx* c) {
   if (c->d_probs) cudaFree(c->d_probs);
   if (c->d_outs) cudaFree(c->d_outs);
   if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->comm) { if (const NcclApi* a = nccl_api(nullptr)) a->CommDestroy(c->comm); c->comm = nullptr; }
   if (c->pack_buf) cudaFree(c->pack_buf);
   for (int i = 0; i < ffvd_ctx::kRing; ++i) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
@@ -164,6 +179,75 @@ extern "C" int ffvd_debug_phase_clocks(ffvd_ctx* c, int reset, uint64_t* out16) 
   (void)c; (void)reset; (void)out16;
   return fail(FFVD_E_UNSUPPORTED, "library was not built with -DFFVD_PHASE_TIMING");
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA graphs: the reference drives 22 session.run calls per outer iteration (base_model.py:915-933, :944-950); on small
+// problems (the bundled data: T <= 512, M = 100) an evaluation is ~10 launches of a few microseconds each, so launch gaps
+// and the per-call host work dominate.  A captured sequence of ffvd_nll_grads_* / ffvd_sghmc_update / ffvd_adam_update
+// calls replays as ONE launch.  Capture happens on a stream owned by the context (torch's legacy default stream cannot be
+// captured); the graph is launched into the context's own stream.
+extern "C" int ffvd_graph_capture_begin(ffvd_ctx* c) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (c->capturing) return fail(FFVD_E_BADARG, "a capture is already in progress");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));            // everything issued so far is done before the capture starts
+  c->cur_graph = new ffvd_graph();
+  cudaError_t e = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) { delete c->cur_graph; c->cur_graph = nullptr; return fail(FFVD_E_CUDA, cudaGetErrorString(e)); }
+  c->user_stream = c->stream;
+  c->stream = c->cap_stream;
+  c->capturing = true;
+  return FFVD_OK;
+}
+
+static void graph_free(ffvd_graph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  for (void* p : g->pinned) cudaFreeHost(p);
+  delete g;
+}
+
+extern "C" int ffvd_graph_capture_end(ffvd_ctx* c, ffvd_graph** out) {
+  if (!c || !out) return fail(FFVD_E_BADARG, "null argument");
+  if (!c->capturing) return fail(FFVD_E_BADARG, "no capture in progress");
+  ffvd_graph* g = c->cur_graph;
+  cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g->graph);
+  c->stream = c->user_stream;
+  c->capturing = false;
+  c->cur_graph = nullptr;
+  if (e != cudaSuccess || !g->graph) { graph_free(g); cudaGetLastError(); return fail(FFVD_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) { graph_free(g); return fail(FFVD_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  size_t n = 0;
+  cudaGraphGetNodes(g->graph, nullptr, &n);
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) cudaGraphGetNodes(g->graph, nodes.data(), &n);
+  for (auto& nd : nodes) {
+    cudaGraphNodeType ty;
+    if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) g->kernels++;
+  }
+  *out = g;
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_graph_launch(ffvd_ctx* c, ffvd_graph* g) {
+  if (!c || !g || !g->exec) return fail(FFVD_E_BADARG, "null argument");
+  if (c->capturing) return fail(FFVD_E_BADARG, "cannot launch a graph while capturing");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaGraphLaunch(g->exec, c->stream));
+  c->launches += g->kernels;
+  return FFVD_OK;
+}
+
+extern "C" int64_t ffvd_graph_kernel_count(ffvd_graph* g) { return g ? g->kernels : 0; }
+
+extern "C" int ffvd_graph_destroy(ffvd_ctx* c, ffvd_graph* g) {
+  if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+  graph_free(g);
+  return FFVD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,6 +356,7 @@ struct Call {
     if (dl.device.device_type != kDLCPU && dl.device.device_type != kDLCUDAHost)
       return fail(FFVD_E_DEVICE, std::string(name) + ": unsupported DLPack device type");
     // host tensor: explicit staging copy (a transfer, not a compute fallback)
+    if (c->capturing) return fail(FFVD_E_DEVICE, std::string(name) + ": host tensors cannot be used while a CUDA graph is being captured");
     t.staged = true;
     t.host = base;
     touched_host = true;
@@ -355,7 +440,7 @@ static Layout make_layout(const ffvd_ctx* c, int nprob, int nb, int nk, int D, i
   L.zero_begin = o;
   L.off_Sacc = take(need_acc ? (size_t)nprob * nb * mm : 0);
   L.off_ubar = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
-  L.small_per = (size_t)M * Din + (size_t)D * Din + D + D + (size_t)D * Dy + Dy + Dy;
+  L.small_per = (size_t)M * Din + (size_t)D * Din + D + D + D + (size_t)D * Dy + Dy + Dy;
   L.off_small = take((size_t)nprob * L.small_per * 8);
   L.off_terms = take((size_t)sumS * FFVD_NTERMS_RAW * 8);
   L.off_status = take((size_t)nprob * (nb > nk ? nb : nk) * sizeof(int));
@@ -367,6 +452,8 @@ static Layout make_layout(const ffvd_ctx* c, int nprob, int nb, int nk, int D, i
 
 static int ensure_arena(ffvd_ctx* c, const Layout& L) {
   std::vector<long long> key = {L.nprob, L.nb, L.nk, L.D, L.M, L.Mp, L.Din, L.Dy, L.sumS, L.collapsed ? 1 : 0, (long long)L.total};
+  if (c->capturing && (L.total > c->arena_bytes || key != c->arena_key || c->probs_cap < L.nprob))
+    return fail(FFVD_E_BADARG, "CUDA-graph capture: make the same call once outside the capture first (the workspace must already be laid out)");
   if (L.total > c->arena_bytes) {
     if (c->arena) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->arena)); c->arena = nullptr; c->arena_bytes = 0; }
     CUDA_TRY(cudaMalloc((void**)&c->arena, L.total));
@@ -419,6 +506,7 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   P.gl = sm; sm += (size_t)L.D * L.Din;
   P.gv = sm; sm += L.D;
   P.gQ = sm; sm += L.D;
+  P.gQrep = sm; sm += L.D;
   P.gC = sm; sm += (size_t)L.D * L.Dy;
   P.gd = sm; sm += L.Dy;
   P.gR = sm;
@@ -433,6 +521,9 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
 // Tile configuration of the fused kernel for a padded inducing-point count.  Overridable for experiments with
 // FFVD_RB / FFVD_NW / FFVD_MINB (only the combinations instantiated below exist).
 struct FusedCfg { int rb, nw, minb; };
+#ifndef FFVD_DUAL_DEFAULT
+#define FFVD_DUAL_DEFAULT 0
+#endif
 // supported padded sizes: 128 * {1,2,3,4,6,8,12,16}
 static int pad_M(int M) {
   static const int sizes[] = {128, 256, 384, 512, 768, 1024, 1536, 2048};
@@ -446,6 +537,13 @@ static FusedCfg fused_cfg(int Mp) {
   cfg.rb = (ngw <= 2) ? 8 : (ngw <= 4 ? 4 : (ngw <= 8 ? 2 : 1));
   cfg.nw = (ngw == 1) ? 16 : 8;
   cfg.minb = 1;
+  // Half-width CTAs (4 warps x 255 registers, BT x Mp tile of half the rows), TWO per SM: the non-tensor phases of one CTA
+  // (K tile, staging, statistics, flushes) run under the contraction phases of the other.  Only where the B-operand
+  // stream from L2 can afford half the reuse (Mp <= 256).  FFVD_DUAL=0/1 overrides.
+  bool dual = FFVD_DUAL_DEFAULT != 0;
+  if (const char* e = getenv("FFVD_DUAL")) dual = atoi(e) != 0;
+  if (dual && ngw == 2) { cfg.rb = 4; cfg.nw = 4; cfg.minb = 2; }
+  if (dual && ngw == 1) { cfg.rb = 8; cfg.nw = 4; cfg.minb = 2; }
   if (const char* e = getenv("FFVD_RB")) cfg.rb = atoi(e);
   if (const char* e = getenv("FFVD_NW")) cfg.nw = atoi(e);
   if (const char* e = getenv("FFVD_MINB")) cfg.minb = atoi(e);
@@ -454,9 +552,9 @@ static FusedCfg fused_cfg(int Mp) {
 
 template <int KIND, int MODE>
 static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs, int nprob, long long total_items) {
-  const int ngw = Mp / 128;
   FusedCfg cfg = fused_cfg(Mp);
   if (c->cur_rb) cfg.rb = c->cur_rb;
+  const int ngw = Mp / (16 * (cfg.nw < 8 ? cfg.nw : 8));       // 16-column groups per column warp
 #ifdef FFVD_SPLIT_BUILD
   ffvd_fused_fn kern = ffvd_fused_lookup(KIND, MODE, cfg.rb, ngw, cfg.nw, cfg.minb);    // instantiated in fused_inst.cu objects
 #else
@@ -476,10 +574,9 @@ static int launch_fused(ffvd_ctx* c, int Mp, int Din, const DevProblem* d_probs,
   long long grid = total_items < cap ? total_items : cap;
   if (grid < 1) return FFVD_OK;
   const int slot = (int)(c->ev_count % ffvd_ctx::kRing);
-  cudaEventRecord(c->ev0[slot], c->stream);
+  if (!c->capturing) cudaEventRecord(c->ev0[slot], c->stream);
   kern<<<(int)grid, 32 * cfg.nw, smem, c->stream>>>(d_probs, nprob, total_items, c->kscr);
-  cudaEventRecord(c->ev1[slot], c->stream);
-  c->ev_count++;
+  if (!c->capturing) { cudaEventRecord(c->ev1[slot], c->stream); c->ev_count++; }
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return FFVD_OK;
@@ -491,7 +588,7 @@ static int rb_of(int Mp) { return fused_cfg(Mp).rb; }
 // is nearly half the latency (C1: fused kernel 38 -> 24 us).
 static int rb_for_call(const ffvd_ctx* c, int Mp, long long pairs, long long rows) {
   const int rb = rb_of(Mp);
-  if (Mp != 128 || rb != 8 || getenv("FFVD_RB")) return rb;
+  if (Mp != 128 || rb != 8 || getenv("FFVD_RB") || fused_cfg(Mp).nw == 4) return rb;
   const long long items4 = pairs * ((rows + 31) / 32);
   return items4 <= c->num_sms ? 4 : rb;
 }
@@ -738,30 +835,53 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     s_begin += t.S;
     if (t.gX.present) P.gX = t.gX.d;
     else if (!no_grads || collapsed) {   // collapsed pass 1 always accumulates the emission gradient
+      if (c->capturing) return fail(FFVD_E_BADARG, "CUDA-graph capture: pass g_X (no scratch allocation inside a graph)");
       CUDA_TRY(cudaMallocAsync((void**)&t.gx_scratch, t.X.numel * 8, c->stream));
       P.gX = t.gx_scratch;
     }
-    if (P.gX && nprob <= 4) CUDA_TRY(cudaMemsetAsync(P.gX, 0, t.X.numel * 8, c->stream));
+    if (P.gX && nprob <= 4 && !(flags & FFVD_FLAG_COLLAPSED_RESUME)) CUDA_TRY(cudaMemsetAsync(P.gX, 0, t.X.numel * 8, c->stream));
     OutPtrs& O = ho[p];
     O.nll = t.nll.d; O.terms = t.terms.d; O.g_Z = t.gZ.d; O.g_U = t.gU.d; O.g_logv = t.glogv.d; O.g_logl = t.glogl.d;
     O.g_logQ = t.glogQ.d; O.g_C = t.gC.d; O.g_d = t.gd.d; O.g_logR = t.glogR.d;
   }
   const long long total_items = item;
   c->last_off_cvec = L.off_cvec; c->last_off_HxT = L.off_HxT; c->last_Mp = Mp; c->last_nb = nb;
-  CUDA_TRY(cudaMemcpyAsync(c->d_probs, hp.data(), sizeof(DevProblem) * nprob, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->d_outs, ho.data(), sizeof(OutPtrs) * nprob, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
-  if (nprob > 4) {           // many small problems: one launch instead of nprob memsets
-    size_t maxn = 0;
-    for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
-    zero_gx_kernel<<<dim3(grid1d(maxn, 256, 64), nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+  const bool p1_only = (flags & FFVD_FLAG_COLLAPSED_P1_ONLY) != 0, resume = (flags & FFVD_FLAG_COLLAPSED_RESUME) != 0;
+  if ((p1_only || resume) && (!collapsed || no_grads || nprob != 1)) return fail(FFVD_E_BADARG, "COLLAPSED_P1_ONLY / COLLAPSED_RESUME need one collapsed problem with gradients");
+  if ((p1_only || resume) && !pt[0].gX.present) return fail(FFVD_E_BADARG, "COLLAPSED_P1_ONLY / COLLAPSED_RESUME need g_X (pass 1 leaves the emission gradient in it)");
+  if (p1_only && resume) return fail(FFVD_E_BADARG, "COLLAPSED_P1_ONLY and COLLAPSED_RESUME are two calls");
+  std::vector<long long> callkey = c->arena_key;
+  for (auto& t : pt) for (const double* q : {t.X.d, t.Z.d, t.gX.d}) callkey.push_back((long long)(uintptr_t)q);
+  if (resume && !(c->p1_pending && callkey == c->p1_key))
+    return fail(FFVD_E_BADARG, "COLLAPSED_RESUME without a matching COLLAPSED_P1_ONLY call on this context");
+  c->p1_pending = false;
+  if (c->capturing && !(flags & FFVD_FLAG_ASYNC)) return fail(FFVD_E_BADARG, "CUDA-graph capture needs FFVD_FLAG_ASYNC (no status read-back inside a graph)");
+  {
+    const void *srcP = hp.data(), *srcO = ho.data();
+    if (c->capturing) {       // the captured copy nodes read their source at every replay: give them memory that outlives this call
+      void *pp = nullptr, *po = nullptr;
+      CUDA_TRY(cudaMallocHost(&pp, sizeof(DevProblem) * nprob)); c->cur_graph->pinned.push_back(pp);
+      CUDA_TRY(cudaMallocHost(&po, sizeof(OutPtrs) * nprob)); c->cur_graph->pinned.push_back(po);
+      memcpy(pp, hp.data(), sizeof(DevProblem) * nprob); memcpy(po, ho.data(), sizeof(OutPtrs) * nprob);
+      srcP = pp; srcO = po;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_probs, srcP, sizeof(DevProblem) * nprob, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_outs, srcO, sizeof(OutPtrs) * nprob, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (!resume) {
+    CUDA_TRY(cudaMemsetAsync(c->arena + L.zero_begin, 0, L.zero_end - L.zero_begin, c->stream));
+    if (nprob > 4) {           // many small problems: one launch instead of nprob memsets
+      size_t maxn = 0;
+      for (auto& t : pt) maxn = t.X.numel > maxn ? t.X.numel : maxn;
+      zero_gx_kernel<<<dim3(grid1d(maxn, 256, 64), nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    }
   }
 
   long long ident = 1469598103934665603LL;      // FNV-1a over the addresses of Z / logv / logl of every problem: the factors in
   for (auto& t : pt)                             // the arena belong to exactly these tensors
     for (const double* q : {t.Z.d, t.logv.d, t.logl.d}) ident = (ident ^ (long long)(uintptr_t)q) * 1099511628211LL;
   bool ltu_done = false;
-  TRY(launch_prep<KIND>(c, L, jitter, (flags & FFVD_FLAG_REUSE_KZZ) != 0, ident, !collapsed && !no_grads, &ltu_done));
+  if (!resume) TRY(launch_prep<KIND>(c, L, jitter, (flags & FFVD_FLAG_REUSE_KZZ) != 0, ident, !collapsed && !no_grads, &ltu_done));
   const int nz = nprob * nb;
   const BatchMap idm = {1, 1, 1};                // z -> z
   const BatchMap lmap = {nb, D, D};              // z -> (z / nb) * D + z % D
@@ -777,8 +897,22 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, Din, c->d_probs, nprob, total_items)));
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 0); c->launches++;
   } else {
-    TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, Din, c->d_probs, nprob, total_items)));
-    symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 1); c->launches++;
+    if (!resume) {
+      TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, Din, c->d_probs, nprob, total_items)));
+      symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 1); c->launches++;
+    }
+    if (p1_only) {
+      // time-sharded collapsed bound (conditionals_multi_output.py:246-254 sums over ALL transitions): the caller now
+      // all-reduces the statistics S = F^T F and b = F^T delta (ffvd_collapsed_stats_allreduce / _get / _set) and calls
+      // again with FFVD_FLAG_COLLAPSED_RESUME
+      c->p1_pending = true; c->p1_key = callkey;
+      c->p1_off_S = L.off_Sacc; c->p1_bytes = (L.off_ubar - L.off_Sacc) + (size_t)nprob * nb * Mp * 8; c->p1_nb = nb; c->p1_Mp = Mp;
+      CUDA_TRY(cudaGetLastError());
+      int st1 = FFVD_OK;
+      if (!(flags & 8)) st1 = check_status(c, L);
+      TRY(call.finish());
+      return st1;
+    }
     if (use_blocked(c, M, Mp)) {
       collapsed_fill_kernel<<<dim3((unsigned)(((size_t)Mp * Mp + 255) / 256), nb, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
       TRY(blocked_factor_invert(c, Wk, (double*)(c->arena + L.off_Dinv), Hx, HxT, (int*)(c->arena + L.off_status2), nz, M, Mp));
@@ -803,7 +937,9 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       collapsed_vec_kernel<<<dim3(nb, nprob), 1024, 0, c->stream>>>(c->d_probs); c->launches++;
     }
   }
-  if (!no_grads) {
+  if (!no_grads && !(collapsed && (flags & FFVD_FLAG_NO_REPLICATED))) {
+    // (time-sharded collapsed bound: G = Mat' S + c b^T is built from the all-reduced statistics, identical on every rank,
+    //  so only the rank without FFVD_FLAG_NO_REPLICATED pushes it through the Cholesky backward)
     TRY(launch_bgemm(c, Wk, Sacc, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Gs L^{-1}
     TRY(launch_bgemm(c, Sacc, LinvT, Wk, Mp, -0.5, nz, idm, lmap, idm));      // Kbar_zz = -1/2 L^{-T} Gs L^{-1}
     const dim3 grow((M + 7) / 8, nb, nprob);
@@ -837,6 +973,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
 // One all-reduce (sum, float64) of a list of device tensors packed into one buffer.
 static int allreduce_list(ffvd_ctx* c, Call& call, DLManagedTensor* const* list, const char* const* names, int n) {
   if (!c->comm || c->comm_nranks == 1) return FFVD_OK;          // single rank: the sum is the value
+  if (c->capturing) return fail(FFVD_E_UNSUPPORTED, "collectives are not captured in CUDA graphs");
   const NcclApi* a = nccl_api(nullptr);
   if (!a) return fail(FFVD_E_UNSUPPORTED, "NCCL is not loaded");
   PackList pl;
@@ -898,6 +1035,52 @@ extern "C" int ffvd_nll_grads_collapsed(ffvd_ctx* c, int kind, const ffvd_proble
   if (kind == FFVD_KERNEL_LINEAR) return run_nll<1>(c, 1, 1, p, flags, jitter, o);
   return fail(FFVD_E_BADARG, "unknown kernel kind");
 }
+// ---- statistics of a pending collapsed pass 1 (time sharding): S = F^T F (nb,Mp,Mp) and b = F^T delta (nb,Mp)
+extern "C" int ffvd_collapsed_stats_shape(ffvd_ctx* c, int* nb, int* Mp) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (!c->p1_pending) return fail(FFVD_E_BADARG, "no pending FFVD_FLAG_COLLAPSED_P1_ONLY evaluation on this context");
+  if (nb) *nb = c->p1_nb;
+  if (Mp) *Mp = c->p1_Mp;
+  return FFVD_OK;
+}
+
+extern "C" int ffvd_collapsed_stats_allreduce(ffvd_ctx* c) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (!c->p1_pending) return fail(FFVD_E_BADARG, "no pending FFVD_FLAG_COLLAPSED_P1_ONLY evaluation on this context");
+  if (!c->comm || c->comm_nranks == 1) return FFVD_OK;
+  const NcclApi* a = nccl_api(nullptr);
+  if (!a) return fail(FFVD_E_UNSUPPORTED, "NCCL is not loaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  // S and b are adjacent in the arena (b follows S after alignment padding, which is zero on every rank)
+  double* base = (double*)(c->arena + c->p1_off_S);
+  NCCL_TRY(a, a->AllReduce(base, base, c->p1_bytes / sizeof(double), kNcclFloat64, kNcclSum, c->comm, c->stream));
+  return FFVD_OK;
+}
+
+static int collapsed_stats_copy(ffvd_ctx* c, DLManagedTensor* S, DLManagedTensor* b, bool set) {
+  if (!c || !S || !b) return fail(FFVD_E_BADARG, "null argument");
+  if (!c->p1_pending) return fail(FFVD_E_BADARG, "no pending FFVD_FLAG_COLLAPSED_P1_ONLY evaluation on this context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tS, tb;
+  TRY(call.import(S, !set, tS, "S"));
+  TRY(call.import(b, !set, tb, "b"));
+  const size_t nS = (size_t)c->p1_nb * c->p1_Mp * c->p1_Mp, nb_ = (size_t)c->p1_nb * c->p1_Mp;
+  if (tS.numel != nS || tb.numel != nb_) return fail(FFVD_E_SHAPE, "S must be (nb,Mp,Mp) and b (nb,Mp): see ffvd_collapsed_stats_shape");
+  double* dS = (double*)(c->arena + c->p1_off_S);
+  double* db = (double*)(c->arena + c->p1_off_S + c->p1_bytes) - nb_;
+  if (set) {
+    CUDA_TRY(cudaMemcpyAsync(dS, tS.d, nS * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(db, tb.d, nb_ * 8, cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(tS.d, dS, nS * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(tb.d, db, nb_ * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return call.finish();
+}
+extern "C" int ffvd_collapsed_stats_get(ffvd_ctx* c, DLManagedTensor* S_out, DLManagedTensor* b_out) { return collapsed_stats_copy(c, S_out, b_out, false); }
+extern "C" int ffvd_collapsed_stats_set(ffvd_ctx* c, DLManagedTensor* S_in, DLManagedTensor* b_in) { return collapsed_stats_copy(c, S_in, b_in, true); }
+
 // (S,D,Mp) -> U_mean (S,M,D) and (S,D,Mp,Mp) -> LHinvT (S,D,M,M)
 __global__ void extract_collapsed_kernel(const double* __restrict__ cvec, const double* __restrict__ HxT, double* __restrict__ Umean,
                                          double* __restrict__ LHinvT, int S, int D, int M, int Mp) {
@@ -1008,6 +1191,7 @@ extern "C" int ffvd_kernel_Kdiag(ffvd_ctx* c, int kind, DLManagedTensor* X, DLMa
 // shared prep for kernel_pre_cal / conditional: one DevProblem with only the Z-side fields.
 static int setup_zside(ffvd_ctx* c, int kind, const Tens& tZ, const Tens& tv, const Tens& tl, int nk, int R, double jitter,
                        Layout& L, DevProblem& P, bool need_scratch = false, bool reuse = false) {
+  if (c->capturing) return fail(FFVD_E_UNSUPPORTED, "only ffvd_nll_grads_*, ffvd_sghmc_update and ffvd_adam_update can be captured in a CUDA graph");
   const int M = (int)tZ.shape[0], Din = (int)tZ.shape[1];
   if (Din > FFVD_MAX_DIN) return fail(FFVD_E_LIMIT, "Din > 31");
   const int Mp = pad_M(M);

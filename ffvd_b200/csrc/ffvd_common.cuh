@@ -40,6 +40,7 @@ struct DevProblem {
   double *gl;          // [D][Din]    raw dJ/dlogl
   double *gv;          // [D]
   double *gQ;          // [D]
+  double *gQrep;       // [D]   collapsed: the part of dJ/dlogQ that depends on H = F^T F / Q + I as a whole (replicated under time sharding)
   double *gC;          // [D][Dy]
   double *gd;          // [Dy]
   double *gR;          // [Dy]   (row 0 of logR)

@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(1024) collapsed_vec_kernel(const DevProblem* _
   __syncthreads();
   if (tid == 0) {
     red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
-    red_add(P.gQ + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
+    red_add(P.gQrep + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
   }
   // Mat' in place: four rows per warp in flight (loads of all four first, then the stores)
   for (int m0 = 4 * warp; m0 < M; m0 += 4 * nw)
@@ -1164,6 +1164,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
   const int M = P.M, Mp = P.Mp, D = P.D, Din = P.Din, Dy = P.Dy, S = P.S, T = P.T;
   const double sc = -1.0 / (double)T;
   const bool shared_priors = (flags & 16) == 0, x0_prior = (flags & 32) == 0;
+  const bool replicated = (flags & 512) == 0;      // FFVD_FLAG_NO_REPLICATED: the H-dependent terms are counted by another rank
   const double npri = !shared_priors ? 0.0 : ((flags & 2) ? 1.0 : (double)S);
   const bool zprior = (flags & 1) != 0;
   const double log005 = log(0.05);
@@ -1222,8 +1223,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
       t[1] = sc * r[FFVD_RAW_EMIS];
       t[2] = sc * r[FFVD_RAW_XQ];
       t[3] = sc * r[FFVD_RAW_TRACE];
-      t[4] = collapsed ? sc * r[FFVD_RAW_LOGDET] : 0.0;
-      t[5] = collapsed ? sc * r[FFVD_RAW_QUAD] : 0.0;
+      t[4] = (collapsed && replicated) ? sc * r[FFVD_RAW_LOGDET] : 0.0;
+      t[5] = (collapsed && replicated) ? sc * r[FFVD_RAW_QUAD] : 0.0;
       if (stale) {                  // FFVD_FLAG_REUSE_KZZ with a Z / hyper-parameter content that the cached factors were not built from
 #pragma unroll
         for (int k = 0; k < 6; ++k) t[k] = __longlong_as_double(0x7ff8000000000000ll);
@@ -1240,7 +1241,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
   }
   if (O.g_logv) for (int i = tid; i < D; i += nth) O.g_logv[i] = sc * (P.gv[i] - npri * (P.logv[i] - log005));
   if (KIND == 0 && O.g_logl) for (int i = tid; i < D * Din; i += nth) O.g_logl[i] = sc * (P.gl[i] - npri * P.logl[i]);
-  if (O.g_logQ) for (int i = tid; i < D; i += nth) O.g_logQ[i] = sc * (P.gQ[i] - npri * P.logQ[i]);
+  if (O.g_logQ) for (int i = tid; i < D; i += nth) O.g_logQ[i] = sc * (P.gQ[i] + ((collapsed && replicated) ? P.gQrep[i] : 0.0) - npri * P.logQ[i]);
   if (O.g_C) for (int i = tid; i < D * Dy; i += nth) O.g_C[i] = sc * (P.gC[i] - npri * P.C[i]);
   if (O.g_d) for (int i = tid; i < Dy; i += nth) O.g_d[i] = sc * (P.gd[i] - npri * P.dvec[i]);
   if (O.g_logR) for (int i = tid; i < Dy * Dy; i += nth) O.g_logR[i] = sc * ((i < Dy ? P.gR[i] : 0.0) - npri * P.logR[i]);

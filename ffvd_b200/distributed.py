@@ -138,6 +138,59 @@ def evaluate_time_sharded(evaluate, problem: Dict[str, object], outputs: Dict[st
     return outputs
 
 
+def evaluate_time_sharded_collapsed(ctx, kind: int, problem: Dict[str, object], outputs: Dict[str, object], rank: int, world: int,
+                                    flags: int = 1, jitter: float = 1e-5, group=None, stats_transport: str = "native"):
+    """The COLLAPSED bound (conditionals_multi_output.py:230-257, the CLI-default case 4) of ONE trajectory whose T
+    transitions are split over `world` ranks.  H = F^T F / Q + I needs the statistics of ALL transitions, so the
+    evaluation is split in two (include/ffvd_b200.h):
+      pass 1 over the own block (FLAG_COLLAPSED_P1_ONLY) -> all-reduce of S = F^T F and b = F^T delta
+      (`stats_transport` "native": the context's NCCL communicator; "torch": torch.distributed on copies)
+      -> resume (FLAG_COLLAPSED_RESUME); every rank but 0 sets FLAG_NO_REPLICATED so that what depends on the global
+      statistics only (log det H, the quadratic form, their log Q gradient, the Cholesky backward of G) is counted once.
+    Then, as for the uncollapsed blocks: rescale by T_block / T, one packed all-reduce of nll / terms / shared gradients,
+    one-row halo for g_X.  `outputs` as in `evaluate_time_sharded` (g_X with the block's b - a + 1 rows)."""
+    import torch
+    import torch.distributed as dist
+    from . import _capi
+    T = problem["X"].shape[0] - 1
+    blk, a, b = time_block(problem, rank, world)
+    blk = {k: (v.contiguous() if v is not None and hasattr(v, "contiguous") else v) for k, v in blk.items()}
+    fl = int(flags) | time_block_flags(rank)
+    ctx.nll_grads(kind, True, blk, outputs, flags=fl | _capi.FLAG_COLLAPSED_P1_ONLY, jitter=jitter)
+    multi = world > 1 and dist.is_available() and dist.is_initialized()
+    if multi:
+        if stats_transport == "native" and ctx.comm_info()[1] > 1:
+            ctx.collapsed_stats_allreduce()
+        else:
+            nb, Mp = ctx.collapsed_stats_shape()
+            X = problem["X"]
+            S = torch.empty((nb, Mp, Mp), dtype=torch.float64, device=X.device)
+            bv = torch.empty((nb, Mp), dtype=torch.float64, device=X.device)
+            ctx.collapsed_stats_get(S, bv)
+            dist.all_reduce(S, group=group); dist.all_reduce(bv, group=group)
+            ctx.collapsed_stats_set(S, bv)
+    ctx.nll_grads(kind, True, blk, outputs, flags=fl | _capi.FLAG_COLLAPSED_RESUME | (_capi.FLAG_NO_REPLICATED if rank > 0 else 0),
+                  jitter=jitter)
+    scale = float(b - a) / float(T)
+    for k, v in outputs.items():
+        if v is not None:
+            v.mul_(scale)
+    if not multi:
+        return outputs
+    names = ("nll", "terms") + SHARED
+    flat, present = pack(outputs, names)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    unpack(flat, outputs, present)
+    gX = outputs.get("g_X")
+    if gX is not None:
+        last = gX[-1].clone().contiguous()
+        rows = [torch.empty_like(last) for _ in range(world)]
+        dist.all_gather(rows, last, group=group)
+        if rank > 0:
+            gX[0].add_(rows[rank - 1])
+    return outputs
+
+
 def exchange_halo_row(X_block, rank: int, world: int, group=None):
     """After the owners updated their rows (SG-HMC / Adam), refresh every block's halo row x_b from the next rank's
     first row (one all-gather of D doubles per rank)."""

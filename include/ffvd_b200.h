@@ -73,6 +73,18 @@ typedef struct DLManagedTensor {
 #define FFVD_FLAG_NO_SHARED_PRIORS 16 /* drop the priors on Z, U, kernel hypers, logQ, C, d, logR (blocks other than the first) */
 #define FFVD_FLAG_NO_X0_PRIOR      32 /* drop -1/2 |X_0|^2 (dgp_model.py:252): the block does not start at t = 0 */
 
+/* Collapsed bound under TIME sharding (one trajectory split over ranks; conditionals_multi_output.py:246-254 needs
+ * F^T F and F^T delta summed over ALL transitions before H^{-1} can be formed):
+ *   1. every rank: ffvd_nll_grads_collapsed(block, flags | FFVD_FLAG_COLLAPSED_P1_ONLY)      -- pass 1 over its block
+ *   2. every rank: ffvd_collapsed_stats_allreduce(ctx)   (or _get / sum / _set by other means)
+ *   3. every rank: ffvd_nll_grads_collapsed(same tensors, flags | FFVD_FLAG_COLLAPSED_RESUME [| FFVD_FLAG_NO_REPLICATED])
+ * FFVD_FLAG_NO_REPLICATED (every rank but one) drops what is a function of the global statistics only and therefore
+ * identical on every rank: the log det H and quadratic terms, their dJ/dlogQ part, and the Cholesky backward of
+ * G = Mat' S + c b^T.  Results are then rescaled by T_block / T and summed like the uncollapsed blocks. */
+#define FFVD_FLAG_COLLAPSED_P1_ONLY 128
+#define FFVD_FLAG_COLLAPSED_RESUME  256
+#define FFVD_FLAG_NO_REPLICATED     512
+
 typedef struct ffvd_ctx ffvd_ctx;
 
 /* One GPSSM problem (SURVEY section 8 batch-axis contract).  Shapes:
@@ -177,6 +189,26 @@ int ffvd_nll_grads_collapsed(ffvd_ctx*, int kind, const ffvd_problem* p, int fla
  * BASELINE config 4 (many small chains). */
 int ffvd_nll_grads_batched(ffvd_ctx*, int kind, int collapsed, int nprob, const ffvd_problem* p,
                            int flags, double jitter, const ffvd_outputs* o);
+
+/* The statistics FFVD_FLAG_COLLAPSED_P1_ONLY left in the context: S = F^T F as (nb, Mp, Mp) and b = F^T delta as (nb, Mp),
+ * nb = S*D matrices, zero padded to Mp (ffvd_collapsed_stats_shape).  _allreduce sums them over the ranks in place (one
+ * ncclAllReduce); _get / _set copy them out / in for callers with their own transport.  conditionals_multi_output.py:246-251. */
+int ffvd_collapsed_stats_shape(ffvd_ctx*, int* nb, int* Mp);
+int ffvd_collapsed_stats_allreduce(ffvd_ctx*);
+int ffvd_collapsed_stats_get(ffvd_ctx*, DLManagedTensor* S_out, DLManagedTensor* b_out);
+int ffvd_collapsed_stats_set(ffvd_ctx*, DLManagedTensor* S_in, DLManagedTensor* b_in);
+
+/* ---- CUDA graphs.  The reference issues 22 session.run calls per outer iteration (base_model.py:915-933, 944-950); a
+ * captured sequence of ffvd_nll_grads_* / ffvd_sghmc_update / ffvd_adam_update calls replays as ONE launch, which is what
+ * matters on the bundled data (an evaluation there is ~10 launches of a few microseconds).  Rules while capturing: device
+ * tensors only, FFVD_FLAG_ASYNC on every evaluation, g_X present, and the same call made once before the capture (so the
+ * workspace exists).  Tensors are captured by ADDRESS: update their contents in place between launches. */
+typedef struct ffvd_graph ffvd_graph;
+int ffvd_graph_capture_begin(ffvd_ctx*);
+int ffvd_graph_capture_end(ffvd_ctx*, ffvd_graph** out);
+int ffvd_graph_launch(ffvd_ctx*, ffvd_graph*);            /* into the context's stream */
+int64_t ffvd_graph_kernel_count(ffvd_graph*);             /* kernels one launch replays */
+int ffvd_graph_destroy(ffvd_ctx*, ffvd_graph*);
 
 /* ---- multi-GPU (the reference is single-process, so these replace nothing in it: they are what a sharded
  * caller of dgp_model.py:248-297 needs).  One NCCL communicator per context; NCCL is loaded at run time (libnccl.so.2, or

@@ -877,3 +877,99 @@ def test_device_exp_routine_accuracy(env):
     big = torch.as_tensor(np.array([-746.0, -1e4, -1e9, -1e15, -1e300, -np.inf]), device=env["dev"])
     sat = ctx.debug_exp(big, torch.empty_like(big)).cpu().numpy()
     assert np.all(np.isfinite(sat)) and np.all(sat >= 0) and np.all(sat < 1e-300)
+
+
+@pytest.mark.parametrize("M", (70, 150))
+def test_collapsed_time_blocks_reassemble_full_trajectory(env, M):
+    """The collapsed bound under TIME sharding (cmo:246-254 sums F^T F over all transitions): three blocks, each on its
+    own context (the ranks), pass 1 -> summed statistics (ffvd_collapsed_stats_get / _set) -> resume with
+    FFVD_FLAG_NO_REPLICATED on all but the first -> the T_b/T-weighted sum equals the single evaluation of the whole
+    trajectory (nll, all six terms, every gradient)."""
+    from oracle import fixtures
+    from ffvd_b200 import distributed
+    torch, F = env["torch"], env["ffvd"]
+    prob = fixtures.synthetic_problem(T=211, M=M, D=3, S=1)
+    p = dev_problem(env, prob)
+    full = alloc_out(env, p)
+    env["ctx"].nll_grads(0, True, p, full)
+    T = prob.Y.shape[0]
+    world = 3
+    ctxs = [F.Context(0, torch.cuda.current_stream(0).cuda_stream) for _ in range(world)]
+    blks, outs = [], []
+    for rank in range(world):
+        blk, a, b = distributed.time_block(p, rank, world)
+        blk = {k: (v.contiguous() if v is not None else None) for k, v in blk.items()}
+        o = alloc_out(env, blk)
+        fl = F.FLAG_PRIOR_Z_NORMAL | distributed.time_block_flags(rank)
+        ctxs[rank].nll_grads(0, True, blk, o, flags=fl | F.FLAG_COLLAPSED_P1_ONLY)
+        blks.append((blk, a, b, fl)); outs.append(o)
+    nb, Mp = ctxs[0].collapsed_stats_shape()
+    assert nb == 3
+    Ssum = torch.zeros((nb, Mp, Mp), dtype=torch.float64, device=env["dev"]); bsum = torch.zeros((nb, Mp), dtype=torch.float64, device=env["dev"])
+    for rank in range(world):
+        S = torch.empty_like(Ssum); bv = torch.empty_like(bsum)
+        ctxs[rank].collapsed_stats_get(S, bv)
+        Ssum += S; bsum += bv
+    acc = {k: torch.zeros_like(v) for k, v in full.items() if k != "g_X"}
+    gX = torch.zeros_like(full["g_X"])
+    for rank in range(world):
+        blk, a, b, fl = blks[rank]
+        ctxs[rank].collapsed_stats_set(Ssum, bsum)
+        ctxs[rank].nll_grads(0, True, blk, outs[rank], flags=fl | F.FLAG_COLLAPSED_RESUME | (F.FLAG_NO_REPLICATED if rank else 0))
+        sc = (b - a) / T
+        for k in acc:
+            acc[k] += sc * outs[rank][k]
+        gX[a:b + 1] += sc * outs[rank]["g_X"]
+    torch.cuda.synchronize()
+    for k in acc:
+        assert_close(full[k].cpu().numpy(), acc[k].cpu().numpy(), 1e-10, k)
+    assert_close(full["g_X"].cpu().numpy(), gX.cpu().numpy(), 1e-10, "g_X")
+    # protocol errors are reported, not silently computed
+    with pytest.raises(ValueError):
+        ctxs[0].nll_grads(0, True, blks[0][0], outs[0], flags=blks[0][3] | F.FLAG_COLLAPSED_RESUME)       # nothing pending any more
+    with pytest.raises(ValueError):
+        ctxs[0].nll_grads(0, False, blks[0][0], outs[0], flags=blks[0][3] | F.FLAG_COLLAPSED_P1_ONLY)     # uncollapsed
+
+
+def test_cuda_graph_sghmc_step_and_capture_rules(env):
+    """CUDA-graph form of `sghmc_step` (21 evaluations + updates as ONE launch, base_model.py:915-933): identical result to
+    the launch-by-launch step with the same injected noise, for case 7 (X and U sampled, factors reused inside the graph)
+    and case 2 (kernel hyper-parameters sampled: full preparation in every evaluation); replay after an in-place
+    parameter change; the capture rules are enforced."""
+    torch, F = env["torch"], env["ffvd"]
+    fx = env["byname"]["drive/0"]
+    for case_val in (7, 2):
+        res = []
+        for graph in (False, True):
+            m, _ = _model_from_problem(env, fx, case_val, iterations=0)
+            model = m.fit(fx.Y)
+            rng = np.random.default_rng(9)
+            noises = [[{n: rng.standard_normal(tuple(model.params[n].shape)) for n in model.vars} for _ in range(21)] for _ in range(2)]
+            if graph:
+                model.enable_graph(True)
+            for it in range(2):                          # second step = a replay of the captured graph
+                model.sghmc_step(noise_fn=lambda k, _it=it: noises[_it][k])
+            if graph:
+                assert model._graph.kernels >= 21 * 5
+            res.append({n: model.params[n].cpu().numpy().copy() for n in model.vars})
+            assert len(model.window) == 2
+        for n in res[0]:
+            assert_close(res[0][n], res[1][n], 1e-9, "case %d %s" % (case_val, n))
+    # capture rules
+    from oracle import fixtures
+    ctx = F.Context(0, torch.cuda.current_stream(0).cuda_stream)
+    p = dev_problem(env, fixtures.synthetic_problem(T=40, M=20, D=2, S=1))
+    o = alloc_out(env, p)
+    with pytest.raises(ValueError):                      # no warm-up call: the workspace does not exist yet
+        ctx.capture(lambda: ctx.nll_grads(0, False, p, o, flags=F.FLAG_PRIOR_Z_NORMAL | F.FLAG_ASYNC))
+    ctx.nll_grads(0, False, p, o)
+    with pytest.raises(ValueError):                      # status read-back inside a graph
+        ctx.capture(lambda: ctx.nll_grads(0, False, p, o, flags=F.FLAG_PRIOR_Z_NORMAL))
+    g = ctx.capture(lambda: ctx.nll_grads(0, False, p, o, flags=F.FLAG_PRIOR_Z_NORMAL | F.FLAG_ASYNC))
+    ref = {k: v.clone() for k, v in o.items()}
+    for v in o.values():
+        v.fill_(float("nan"))
+    g.launch(); torch.cuda.synchronize()
+    for k in ref:
+        assert_close(ref[k].cpu().numpy(), o[k].cpu().numpy(), 1e-10, k)
+    g.close()

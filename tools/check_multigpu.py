@@ -2,7 +2,9 @@
   (1) sample sharding: every rank evaluates its block of trajectories, ONE packed NCCL all-reduce of the shared-parameter
       gradients -> equals the single-GPU evaluation of all S trajectories;
   (2) time sharding of one trajectory (S < #GPUs): blocks of transitions with a one-row halo -> equals the single-GPU
-      evaluation of the whole trajectory.
+      evaluation of the whole trajectory;
+  (3) the same two through the library's OWN NCCL communicator (ffvd_comm_init / ffvd_allreduce_shared, C ABI);
+  (4) the COLLAPSED bound under time sharding (pass 1 -> ffvd_collapsed_stats_allreduce -> resume).
 usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/check_multigpu.py"""
 import os, sys
 import numpy as np
@@ -73,6 +75,26 @@ for k in ("nll", "terms") + fd.SHARED:
     worst = max(worst, rel(one_o[k].reshape(-1), out[k].reshape(-1)))
 rows = slice(0, b - a + (1 if rank == world - 1 else 0))
 worst = max(worst, rel(one_o["g_X"][a:a + rows.stop], out["g_X"][rows]))
+# ---- (3) the library's own communicator
+fd.init_native_comm(ctx)
+assert ctx.comm_info()[1] == world
+o2 = alloc(mine)
+ctx.nll_grads(0, False, mine, o2)
+ctx.allreduce_shared(o2)
+for k in fd.SHARED:
+    worst = max(worst, rel(full_o[k], o2[k]))
+# ---- (4) collapsed bound, time sharded, statistics all-reduced by the native communicator and by torch
+col_o = alloc(one_p)
+ctx.nll_grads(0, True, one_p, col_o)
+for transport in ("native", "torch"):
+    outc = {"nll": torch.zeros(1, dtype=torch.float64, device=dev), "terms": torch.zeros(1, 6, dtype=torch.float64, device=dev),
+            "g_X": torch.zeros(b - a + 1, 3, dtype=torch.float64, device=dev)}
+    for k in GK[1:]:
+        outc["g_" + k] = torch.zeros_like(one_p[k])
+    fd.evaluate_time_sharded_collapsed(ctx, 0, one_p, outc, rank, world, flags=ffvd_b200.FLAG_PRIOR_Z_NORMAL, stats_transport=transport)
+    for k in ("nll", "terms") + fd.SHARED:
+        worst = max(worst, rel(col_o[k].reshape(-1), outc[k].reshape(-1)))
+    worst = max(worst, rel(col_o["g_X"][a:a + rows.stop], outc["g_X"][rows]))
 w = torch.tensor([worst], dtype=torch.float64, device=dev)
 dist.all_reduce(w, op=dist.ReduceOp.MAX)
 if rank == 0:

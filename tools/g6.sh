@@ -1,0 +1,7 @@
+export FFVD_B200_LIB=$PWD/ffvd_b200/lib/libffvd_b200_dev.so
+for dual in 1 0; do
+echo "=== FFVD_DUAL=$dual"
+FFVD_DUAL=$dual python tools/dev_check.py dev 2>&1 | tail -9 | cut -c1-200
+FFVD_DUAL=$dual python tools/phase_timing.py 20000 256 8 16
+FFVD_DUAL=$dual python tools/phase_timing.py 20000 100 4 16
+done
