@@ -56,7 +56,7 @@ def algorithmic_flops_per_unit(M, Din):
 
 
 def padded_M(M):
-    return next(s for s in (128, 256, 384, 512, 768, 1024, 1536, 2048) if M <= s)
+    return next(s for s in (64, 128, 256, 384, 512, 768, 1024, 1536, 2048) if M <= s)
 
 
 def executed_flops_per_unit(M, Din):

@@ -524,9 +524,9 @@ struct FusedCfg { int rb, nw, minb; };
 #ifndef FFVD_DUAL_DEFAULT
 #define FFVD_DUAL_DEFAULT 0
 #endif
-// supported padded sizes: 128 * {1,2,3,4,6,8,12,16}
+// supported padded sizes: 64 and 128 * {1,2,3,4,6,8,12,16}
 static int pad_M(int M) {
-  static const int sizes[] = {128, 256, 384, 512, 768, 1024, 1536, 2048};
+  static const int sizes[] = {64, 128, 256, 384, 512, 768, 1024, 1536, 2048};
   for (int s : sizes)
     if (M <= s) return s;
   return -1;
@@ -537,6 +537,11 @@ static FusedCfg fused_cfg(int Mp) {
   cfg.rb = (ngw <= 2) ? 8 : (ngw <= 4 ? 4 : (ngw <= 8 ? 2 : 1));
   cfg.nw = (ngw == 1) ? 16 : 8;
   cfg.minb = 1;
+  if (Mp == 64) {            // M <= 64: four column warps (one 16-column group each), two CTAs per SM; padding to 128 would
+    cfg.rb = 8; cfg.nw = 4; cfg.minb = 2;      // quadruple the tensor work of both contractions and of the SYRK
+    if (const char* e = getenv("FFVD_RB")) cfg.rb = atoi(e);
+    return cfg;
+  }
   // Half-width CTAs (4 warps x 255 registers, BT x Mp tile of half the rows), TWO per SM: the non-tensor phases of one CTA
   // (K tile, staging, statistics, flushes) run under the contraction phases of the other.  Only where the B-operand
   // stream from L2 can afford half the reuse (Mp <= 256).  FFVD_DUAL=0/1 overrides.
@@ -588,7 +593,7 @@ static int rb_of(int Mp) { return fused_cfg(Mp).rb; }
 // is nearly half the latency (C1: fused kernel 38 -> 24 us).
 static int rb_for_call(const ffvd_ctx* c, int Mp, long long pairs, long long rows) {
   const int rb = rb_of(Mp);
-  if (Mp != 128 || rb != 8 || getenv("FFVD_RB") || fused_cfg(Mp).nw == 4) return rb;
+  if (Mp != 128 || rb != 8 || getenv("FFVD_RB") || fused_cfg(Mp).nw == 4) return rb;      // (Mp = 64 keeps full-height tiles)
   const long long items4 = pairs * ((rows + 31) / 32);
   return items4 <= c->num_sms ? 4 : rb;
 }

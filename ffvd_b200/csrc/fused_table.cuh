@@ -23,12 +23,14 @@ static ffvd_fused_fn ffvd_fused_pick(int rb, int ngw, int nw, int minb) {
     FFVD_PICK(8, 1, 16, 1) FFVD_PICK(8, 2, 8, 1) FFVD_PICK(4, 4, 8, 1) FFVD_PICK(8, 1, 8, 1)
     FFVD_PICK(4, 1, 16, 1)
     FFVD_PICK(4, 4, 4, 2) FFVD_PICK(8, 2, 4, 2)       // half-width CTAs, two per SM: Mp = 256 (BT = 32), Mp = 128 (BT = 64)
+    FFVD_PICK(8, 1, 4, 2)                             // Mp = 64
   }
 #else
   FFVD_PICK(8, 1, 16, 1) FFVD_PICK(8, 2, 8, 1) FFVD_PICK(4, 3, 8, 1) FFVD_PICK(4, 4, 8, 1)
   FFVD_PICK(2, 6, 8, 1) FFVD_PICK(2, 8, 8, 1) FFVD_PICK(1, 12, 8, 1) FFVD_PICK(1, 16, 8, 1)
   FFVD_PICK(4, 1, 16, 1)                     // half-height tiles at Mp = 128 for launches with fewer work items than SMs
   FFVD_PICK(4, 4, 4, 2) FFVD_PICK(8, 2, 4, 2)   // half-width CTAs (4 warps, 255 registers), two per SM: Mp = 256 (BT = 32), Mp = 128
+  FFVD_PICK(8, 1, 4, 2)                         // Mp = 64 (M <= 64): one 16-column group per warp
 #endif
 #undef FFVD_PICK
   return kern;
