@@ -34,7 +34,12 @@ dev:
 dev-timing:
 	$(NVCC) $(NVFLAGS) -shared -DFFVD_DEV_MINIMAL -DFFVD_PHASE_TIMING -o ffvd_b200/lib/libffvd_b200_dev.so $(SRC)/capi.cu
 
+# diagnostic build with the index assertions of the fused kernels (compute-sanitizer is closed on the development pool);
+# exercised by tools/bounds_check.py and tests/test_gpu_parity.py::test_bounds_checked_build
+check:
+	$(NVCC) $(NVFLAGS) -shared -DFFVD_DEV_MINIMAL -DFFVD_BOUNDS_CHECK -o ffvd_b200/lib/libffvd_b200_check.so $(SRC)/capi.cu
+
 clean:
 	rm -rf build ffvd_b200/lib/*.so
 
-.PHONY: all dev dev-timing clean
+.PHONY: all dev dev-timing check clean

@@ -88,6 +88,7 @@ def load_library() -> ctypes.CDLL:
     lib.ffvd_kernel_pre_cal.argtypes = [vp, ci, vp, vp, vp, cd, vp]
     lib.ffvd_conditional.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, vp, vp]
     lib.ffvd_conditional_ex.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, ci, vp, vp]
+    lib.ffvd_conditional_dense.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, vp, vp, vp]
     lib.ffvd_collapse_u_mean.argtypes = [vp, ci, ctypes.POINTER(_Problem), cd, vp, vp]
     lib.ffvd_logdensity_norm_diag.argtypes = [vp, vp, vp, vp, ci, vp]
     lib.ffvd_logdensity_norm.argtypes = [vp, vp, vp, vp, vp]
@@ -119,7 +120,7 @@ def load_library() -> ctypes.CDLL:
                  "ffvd_collapse_u_mean", "ffvd_debug_phase_clocks", "ffvd_conditional_ex", "ffvd_logdensity_norm", "ffvd_debug_exp", "ffvd_comm_unique_id", "ffvd_comm_init",
                  "ffvd_comm_destroy", "ffvd_comm_info", "ffvd_allreduce_shared", "ffvd_allreduce", "ffvd_collapsed_stats_shape",
                  "ffvd_collapsed_stats_allreduce", "ffvd_collapsed_stats_get", "ffvd_collapsed_stats_set", "ffvd_graph_capture_begin",
-                 "ffvd_graph_capture_end", "ffvd_graph_launch", "ffvd_graph_destroy"):
+                 "ffvd_graph_capture_end", "ffvd_graph_launch", "ffvd_graph_destroy", "ffvd_conditional_dense"):
         getattr(lib, name).restype = ci
     _lib = lib
     return lib
@@ -297,6 +298,16 @@ class Context:
         finally:
             b.release()
         return mean_out, var_out
+
+    def conditional_dense(self, kind, shared_kernel, Xnew, Z, logv, logl, f, q_sqrt, white, full_cov, jitter, mean_out, var_out, Lm_out=None):
+        b = _Borrow()
+        try:
+            _check(self._lib.ffvd_conditional_dense(self._h, kind, int(bool(shared_kernel)), b.ptr(Xnew), b.ptr(Z), b.ptr(logv), b.ptr(logl),
+                                                    b.ptr(f), b.ptr(q_sqrt), int(bool(white)), int(bool(full_cov)), float(jitter),
+                                                    b.ptr(mean_out), b.ptr(var_out), b.ptr(Lm_out)))
+        finally:
+            b.release()
+        return mean_out, var_out, Lm_out
 
     def collapse_u_mean(self, kind: int, problem: dict, U_mean_out, LHinvT_out=None, jitter: float = 1e-5):
         b = _Borrow()

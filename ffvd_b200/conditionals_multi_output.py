@@ -48,16 +48,25 @@ def conditional(Xnew, X, kern, f, *, full_cov=False, q_sqrt=None, white=False, r
     reference's ValueError."""
     if return_Lm:
         raise ValueError("too many values to unpack (expected 2)")      # cmo:115, reference quirk Q8
-    if full_cov:
-        raise NotImplementedError("full_cov=True (N x N covariances) is not built; FFVD_Main.py:267 sets full_cov=False")
-    if q_sqrt is not None and not white:
-        raise NotImplementedError("q_sqrt with white=False is not built")
     Xnew, X, f = as_f64(Xnew), as_f64(X), as_f64(f)
     X = to_lib(Xnew, X); f = to_lib(Xnew, f)
     kind, logv, logl = _stack_hypers(kern, Xnew)
     Xs = Xnew[..., : kern[0].input_dim]
     Xs = Xs.contiguous() if is_torch(Xs) else np.ascontiguousarray(Xs)
     q = None if q_sqrt is None else _q_sqrt_first_output(q_sqrt, Xnew, len(kern))
+    if full_cov or (q is not None and not white):
+        # the op-for-op dense path (ffvd_conditional_dense), with the reference's own output shapes: every per-kernel call
+        # returns (1,N,N) covariances, and `tf.transpose(tf.convert_to_tensor(f_var)[:, :, 0])` (cmo:119-120) keeps ROW 0 of
+        # each: the result is (N,1,D) -- a quirk of the reference (its driver never sets full_cov, FFVD_Main.py:267)
+        D, N = len(kern), Xnew.shape[0]
+        mean = empty_like_lib(Xnew, (N, D))
+        var = empty_like_lib(Xnew, (D, N, N) if full_cov else (N, D))
+        context_for(Xnew).conditional_dense(kind, False, Xs, X, logv, logl, f, q, white, full_cov, JITTER, mean, var, None)
+        if full_cov:
+            row0 = var[:, 0, :]                                   # (D,N)
+            var = (row0.T if not is_torch(row0) else row0.t())[:, None, :]
+            var = var.contiguous() if is_torch(var) else np.ascontiguousarray(var)
+        return mean, var
     mean = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
     var = empty_like_lib(Xnew, (Xnew.shape[0], len(kern)))
     context_for(Xnew).conditional(kind, False, Xs, X, logv, logl, f, q, white, False, JITTER, mean, var)
@@ -75,6 +84,21 @@ def conditional_after_kernel_precalculation(Lm_inverse_seq, Xnew, Z, kern, f, *,
     if return_Lm:
         raise ValueError("too many values to unpack (expected 2)")      # cmo:317, same unpack as Q8
     st = getattr(Lm_inverse_seq, "stacked", None)
+    if st is None and Lm_inverse_seq is not None:
+        # plain matrices: they must BE the factors of (Z, kern) -- the fused path recomputes them (checked once per list)
+        if not getattr(Lm_inverse_seq, "_ffvd_checked", False):
+            ref = kernel_pre_cal(to_lib(as_f64(Xnew), as_f64(Z)), kern)
+            for a, b in zip(Lm_inverse_seq, ref):
+                a = to_lib(b, as_f64(a))
+                if tuple(a.shape) != tuple(b.shape) or float(abs(a - b).max()) > 1e-6 * max(float(abs(b).max()), 1e-300):
+                    raise ValueError("conditional_after_kernel_precalculation: Lm_inverse_seq is not chol(K(Z) + 1e-5 I)^{-T} of the "
+                                     "given Z / kernels; the fused path recomputes the factors and would silently ignore it")
+            try:
+                Lm_inverse_seq._ffvd_checked = True
+            except AttributeError:
+                pass
+    elif st is not None and not _same_array(st[1], Z):
+        raise ValueError("conditional_after_kernel_precalculation: Lm_inverse_seq was computed by kernel_pre_cal for different inducing inputs")
     if st is None or full_cov or not is_torch(Xnew) or not is_torch(st[1]):
         return conditional(Xnew, Z, kern, f, full_cov=full_cov, q_sqrt=q_sqrt, white=True)
     # factors precalculated by kernel_pre_cal on this device: same Z / hyper tensors, Cholesky preparation skipped
@@ -90,12 +114,57 @@ def conditional_after_kernel_precalculation(Lm_inverse_seq, Xnew, Z, kern, f, *,
     return mean, var
 
 
+def _same_array(a, b):
+    """True if a and b are the same memory (cheap) or hold equal values (one device comparison)."""
+    if a is b:
+        return True
+    if tuple(a.shape) != tuple(b.shape):
+        return False
+    if is_torch(a) and is_torch(b) and a.device == b.device and a.data_ptr() == b.data_ptr() and a.stride() == b.stride():
+        return True
+    return bool((to_lib(a, as_f64(b)) == a).all())
+
+
+def _check_consistent_inputs(Lm_inverse_seq, X_combine, X, Z, kern, what):
+    """The fused path recomputes the factors of K(Z,Z) + 1e-5 I on the device and rebuilds the inputs [x_t, c_t] from X
+    itself, so two of the reference's arguments carry no new information -- PROVIDED the caller passes what the reference
+    passes.  Anything else used to be silently ignored; now it is an error:
+      * the state columns of `X_combine` must be X[:-1] (dgp_model.py:254-262, base_model.py:241-245);
+      * `Lm_inverse_seq` must be the factors of (Z, kern): the `PrecalculatedFactors` that `kernel_pre_cal` returned for
+        these very tensors, or plain matrices equal to them (checked numerically, one extra factorisation)."""
+    Xc = to_lib(X, as_f64(X_combine))
+    D = X.shape[1]
+    if Xc.ndim != 2 or Xc.shape[0] != X.shape[0] - 1 or Xc.shape[1] < D:
+        raise ValueError("%s: X_combine must be (T, D + n_ctrl) with T = X.shape[0] - 1" % what)
+    same = bool((Xc[:, :D] == X[:-1]).all())
+    if not same:
+        raise ValueError("%s: the state columns of X_combine differ from X[:-1]; the fused path evaluates the reference's "
+                         "own call pattern (inputs [x_t, c_t] built from X) and would silently ignore them" % what)
+    if Lm_inverse_seq is None:
+        return
+    st = getattr(Lm_inverse_seq, "stacked", None)
+    if st is not None:
+        if not _same_array(st[1], Z):
+            raise ValueError("%s: Lm_inverse_seq was computed by kernel_pre_cal for different inducing inputs" % what)
+        return
+    ref = kernel_pre_cal(to_lib(X, as_f64(Z)), kern)
+    if len(Lm_inverse_seq) != len(ref):
+        raise ValueError("%s: Lm_inverse_seq must hold one factor per kernel" % what)
+    for a, b in zip(Lm_inverse_seq, ref):
+        a = to_lib(b, as_f64(a))
+        if tuple(a.shape) != tuple(b.shape) or float(abs(a - b).max()) > 1e-6 * max(float(abs(b).max()), 1e-300):
+            raise ValueError("%s: Lm_inverse_seq is not chol(K(Z) + 1e-5 I)^{-T} of the given Z / kernels; the fused path "
+                             "recomputes the factors and would silently ignore it" % what)
+
+
 def collapse_u_mean_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, Q):
     """`conditionals_multi_output.py:206-227`: the optimal collapsed q(u).  Returns (U_mean, Lm_inverse_dd_seq) with
     the reference's shapes: U_mean (1,M,D) (= tf.transpose of the (D,M,1) stack; callers take `[0]`,
-    base_model.py:249-250) and the (D,M,M) stack of chol(H_d)^{-T}.  `Lm_inverse_seq` is accepted for signature
-    parity (recomputed on the device)."""
+    base_model.py:249-250) and the (D,M,M) stack of chol(H_d)^{-T}.  `Lm_inverse_seq` and the state columns of
+    `X_combine` must be consistent with (Z, kern) and X (`_check_consistent_inputs`); the factors are recomputed on the
+    device."""
     X = as_f64(X)
+    _check_consistent_inputs(Lm_inverse_seq, X_combine, X, Z, kern, "collapse_u_mean_after_kernel_precalculation")
     D = X.shape[1]
     T = X.shape[0] - 1
     M = Z.shape[0]
@@ -141,6 +210,7 @@ def collapse_after_kernel_precalculation(Lm_inverse_seq, X_combine, X, Z, kern, 
     if float(batch_size) != float(Y_N):
         raise NotImplementedError("mini-batching is disabled in the reference (base_model.py:188-194)")
     X = as_f64(X)
+    _check_consistent_inputs(Lm_inverse_seq, X_combine, X, Z, kern, "collapse_after_kernel_precalculation")
     D = X.shape[1]
     T = X.shape[0] - 1
     Xc = to_lib(X, as_f64(X_combine))

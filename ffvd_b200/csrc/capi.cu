@@ -20,6 +20,7 @@
 #include "prep_post.cuh"
 #include "blocked_chol.cuh"
 #include "comm.cuh"
+#include "dense_small.cuh"
 
 using namespace ffvd;
 
@@ -62,6 +63,7 @@ struct ffvd_ctx {
   std::vector<long long> kzz_key;
   size_t last_off_cvec = 0, last_off_HxT = 0;
   int last_Mp = 0, last_nb = 0;
+  bool force_blocked = false;      // keep the Cholesky factor L itself (blocked path): conditional(return_Lm=True)
   bool p1_pending = false;         // FFVD_FLAG_COLLAPSED_P1_ONLY left its statistics in the arena; FFVD_FLAG_COLLAPSED_RESUME consumes them
   std::vector<long long> p1_key;
   size_t p1_off_S = 0, p1_bytes = 0; int p1_nb = 0, p1_Mp = 0;
@@ -310,17 +312,35 @@ extern "C" int ffvd_comm_info(ffvd_ctx* c, int* rank, int* nranks, int* nccl_ver
 // ---------------------------------------------------------------------------------------------
 // tensor import / staging
 struct Tens {
-  double* d = nullptr;     // device pointer
-  void* host = nullptr;    // host pointer if staged
+  double* d = nullptr;     // device pointer the kernels use (always float64)
+  void* host = nullptr;    // host pointer if the tensor lives on the host
+  float* dev32 = nullptr;  // float32 tensors: the float32 device copy (the caller's own memory for device tensors)
+  bool own32 = false;      // dev32 was allocated by the call (host float32 tensor)
+  bool f32 = false;
   size_t numel = 0;
   int ndim = 0;
   int64_t shape[4] = {1, 1, 1, 1};
   bool staged = false, is_out = false, present = false;
 };
 
+// float32 mode (BASELINE north star: <= 1e-4 in float32): tensors may cross the ABI as float32; they are widened on the device
+// into float64 workspace copies, ALL arithmetic stays float64 (the reference has no float32 path), and
+// outputs are rounded back once.  What float32 buys is half the HBM / PCIe footprint of the caller's X, x-bar and SG-HMC
+// state; the tensor-pipe work is unchanged.
+__global__ void cvt_f32_to_f64_kernel(const float* __restrict__ src, double* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+__global__ void cvt_f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+static int cvt_grid(size_t n) {
+  size_t b = (n + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
 struct Call {
   ffvd_ctx* c;
-  std::vector<Tens> staged;    // copies of staged tensors (for copy-back / free)
+  std::vector<Tens> staged;    // tensors that need work after the kernels: host copies back, float32 narrowing, frees
   bool touched_host = false;
   explicit Call(ffvd_ctx* ctx) : c(ctx) {}
   int import(DLManagedTensor* mt, bool is_out, Tens& t, const char* name, bool optional = false) {
@@ -330,8 +350,9 @@ struct Call {
       return fail(FFVD_E_BADARG, std::string(name) + " is null");
     }
     const DLTensor& dl = mt->dl_tensor;
-    if (dl.dtype.code != 2 || dl.dtype.bits != 64 || dl.dtype.lanes != 1)
-      return fail(FFVD_E_DTYPE, std::string(name) + " must be float64");
+    const bool is64 = dl.dtype.code == 2 && dl.dtype.bits == 64 && dl.dtype.lanes == 1;
+    const bool is32 = dl.dtype.code == 2 && dl.dtype.bits == 32 && dl.dtype.lanes == 1;
+    if (!is64 && !is32) return fail(FFVD_E_DTYPE, std::string(name) + " must be float64 (or float32: widened on the device)");
     if (dl.ndim > 4) return fail(FFVD_E_SHAPE, std::string(name) + ": rank > 4");
     t.ndim = dl.ndim;
     t.numel = 1;
@@ -346,39 +367,66 @@ struct Call {
     }
     t.present = true;
     t.is_out = is_out;
+    t.f32 = is32;
     char* base = (char*)dl.data + dl.byte_offset;
-    if (dl.device.device_type == kDLCUDA || dl.device.device_type == kDLCUDAManaged) {
+    const size_t esz = is32 ? 4 : 8;
+    const bool on_dev = dl.device.device_type == kDLCUDA || dl.device.device_type == kDLCUDAManaged;
+    if (on_dev) {
       if (dl.device.device_type == kDLCUDA && dl.device.device_id != c->device)
         return fail(FFVD_E_DEVICE, std::string(name) + " lives on another GPU");
-      t.d = (double*)base;
-      return FFVD_OK;
+      if (!is32) { t.d = (double*)base; return FFVD_OK; }
+      t.dev32 = (float*)base;
+    } else {
+      if (dl.device.device_type != kDLCPU && dl.device.device_type != kDLCUDAHost)
+        return fail(FFVD_E_DEVICE, std::string(name) + ": unsupported DLPack device type");
+      // host tensor: explicit staging copy (a transfer, not a compute fallback)
+      if (c->capturing) return fail(FFVD_E_DEVICE, std::string(name) + ": host tensors cannot be used while a CUDA graph is being captured");
+      t.host = base;
+      touched_host = true;
     }
-    if (dl.device.device_type != kDLCPU && dl.device.device_type != kDLCUDAHost)
-      return fail(FFVD_E_DEVICE, std::string(name) + ": unsupported DLPack device type");
-    // host tensor: explicit staging copy (a transfer, not a compute fallback)
-    if (c->capturing) return fail(FFVD_E_DEVICE, std::string(name) + ": host tensors cannot be used while a CUDA graph is being captured");
+    if (c->capturing) return fail(FFVD_E_DTYPE, std::string(name) + ": float32 tensors cannot be used while a CUDA graph is being captured");
     t.staged = true;
-    t.host = base;
-    touched_host = true;
     if (t.numel == 0) return FFVD_OK;
-    CUDA_TRY(cudaMallocAsync((void**)&t.d, t.numel * sizeof(double), c->stream));
-    if (!is_out) CUDA_TRY(cudaMemcpyAsync(t.d, t.host, t.numel * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    void* raw = nullptr;                                   // device copy in the tensor's own dtype
+    if (t.host) {
+      CUDA_TRY(cudaMallocAsync(&raw, t.numel * esz, c->stream));
+      if (!is_out) CUDA_TRY(cudaMemcpyAsync(raw, t.host, t.numel * esz, cudaMemcpyHostToDevice, c->stream));
+      if (is32) { t.dev32 = (float*)raw; t.own32 = true; }
+    }
+    if (is32) {
+      CUDA_TRY(cudaMallocAsync((void**)&t.d, t.numel * sizeof(double), c->stream));
+      if (!is_out) { cvt_f32_to_f64_kernel<<<cvt_grid(t.numel), 256, 0, c->stream>>>(t.dev32, t.d, t.numel); c->launches++; }
+    } else {
+      t.d = (double*)raw;
+    }
     staged.push_back(t);
     return FFVD_OK;
   }
   int finish(bool force_sync = false) {
-    for (auto& t : staged)
-      if (t.is_out && t.numel) CUDA_TRY(cudaMemcpyAsync(t.host, t.d, t.numel * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    for (auto& t : staged)
-      if (t.d) CUDA_TRY(cudaFreeAsync(t.d, c->stream));
+    for (auto& t : staged) {
+      if (!t.is_out || !t.numel) continue;
+      if (t.f32) { cvt_f64_to_f32_kernel<<<cvt_grid(t.numel), 256, 0, c->stream>>>(t.d, t.dev32, t.numel); c->launches++; }
+      if (t.host) CUDA_TRY(cudaMemcpyAsync(t.host, t.f32 ? (void*)t.dev32 : (void*)t.d, t.numel * (t.f32 ? 4 : 8), cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (auto& t : staged) {
+      if (t.d && (t.host || t.f32)) CUDA_TRY(cudaFreeAsync(t.d, c->stream));
+      if (t.own32 && t.dev32) CUDA_TRY(cudaFreeAsync(t.dev32, c->stream));
+    }
     staged.clear();
     if (touched_host || force_sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaGetLastError());
     return FFVD_OK;
   }
   ~Call() {
-    for (auto& t : staged)
-      if (t.d) cudaFreeAsync(t.d, c->stream);
+    for (auto& t : staged) {
+      if (t.d && (t.host || t.f32)) cudaFreeAsync(t.d, c->stream);
+      if (t.own32 && t.dev32) cudaFreeAsync(t.dev32, c->stream);
+    }
+  }
+  // in-place tensors (SG-HMC / Adam state) are imported as inputs; mark them for the copy / narrowing back
+  void mark_inout(const Tens& t) {
+    for (auto& s : staged)
+      if (s.d == t.d) s.is_out = true;
   }
 };
 #define TRY(expr)            \
@@ -622,6 +670,7 @@ static int blocked_factor_invert(ffvd_ctx* c, double* A, double* Dinv, double* X
                                  int M, int Mp);
 
 static bool use_blocked(const ffvd_ctx* c, int M, int Mp) {
+  if (c->force_blocked) return true;
   if (const char* e = getenv("FFVD_BLOCKED_CHOL")) return atoi(e) != 0;
   if (chol_fast_fits(M, Mp, (size_t)c->max_smem)) return false;     // register-resident single-CTA path (M <= 119)
   // Above it the multi-kernel blocked path (whose 64 x 64 diagonal blocks go through the same register-resident
@@ -1343,6 +1392,125 @@ extern "C" int ffvd_conditional_ex(ffvd_ctx* c, int kind, int shared_kernel, DLM
   return st;
 }
 
+// conditionals.py:6-107 / conditionals_multi_output.py:6-120 on explicit matrices: every option of base_conditional
+// (full_cov, q_sqrt 2-d / 3-d, white or not, return_Lm).  For a handful of prediction points; the hot-path branch
+// (white, diagonal variances) is ffvd_conditional_ex.
+static void launch_gemm_small(ffvd_ctx* c, double* C, int ldc, const double* A, int lda, int ta, const double* B, int ldb, int tb,
+                              int m, int n, int k, double alpha, double beta) {
+  dgemm_small_kernel<<<dim3((n + 31) / 32, (m + 31) / 32), dim3(32, 8), 0, c->stream>>>(C, ldc, A, lda, ta, B, ldb, tb, m, n, k, alpha, beta);
+  c->launches++;
+}
+
+extern "C" int ffvd_conditional_dense(ffvd_ctx* c, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                                      DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
+                                      int white, int full_cov, double jitter, DLManagedTensor* mean_out, DLManagedTensor* var_out,
+                                      DLManagedTensor* Lm_out) {
+  if (!c) return fail(FFVD_E_BADARG, "ctx is null");
+  if (kind != FFVD_KERNEL_SE && kind != FFVD_KERNEL_LINEAR) return fail(FFVD_E_BADARG, "unknown kernel kind");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Call call(c);
+  Tens tX, tZ, tv, tl, tf, tm, tvar, tq, tL;
+  TRY(call.import(q_sqrt, false, tq, "q_sqrt", true));
+  TRY(call.import(Xnew, false, tX, "Xnew"));
+  TRY(call.import(Z, false, tZ, "Z"));
+  TRY(call.import(logv, false, tv, "logv"));
+  TRY(call.import(logl, false, tl, "logl", kind != FFVD_KERNEL_SE));
+  TRY(call.import(f, false, tf, "f"));
+  TRY(call.import(mean_out, true, tm, "mean_out"));
+  TRY(call.import(var_out, true, tvar, "var_out"));
+  TRY(call.import(Lm_out, true, tL, "Lm_out", true));
+  if (tX.ndim != 2 || tZ.ndim != 2 || tf.ndim != 2) return fail(FFVD_E_SHAPE, "Xnew, Z, f must be 2-d");
+  const int N = (int)tX.shape[0], Din = (int)tZ.shape[1], M = (int)tZ.shape[0], R = (int)tf.shape[1];
+  if (tX.shape[1] != Din || tf.shape[0] != M) return fail(FFVD_E_SHAPE, "Xnew (N,Din), Z (M,Din), f (M,R) expected");
+  const int nk = shared_kernel ? 1 : R;
+  if (tv.numel != (size_t)nk) return fail(FFVD_E_SHAPE, "logv must have one entry per kernel");
+  if (kind == FFVD_KERNEL_SE && tl.numel != (size_t)nk * Din) return fail(FFVD_E_SHAPE, "logl must be (kernels,Din)");
+  if (tm.numel != (size_t)N * R) return fail(FFVD_E_SHAPE, "mean must be (N,R)");
+  if (tvar.numel != (full_cov ? (size_t)R * N * N : (size_t)N * R)) return fail(FFVD_E_SHAPE, "var must be (N,R), or (R,N,N) with full_cov");
+  if (tL.present && tL.numel != (size_t)nk * M * M) return fail(FFVD_E_SHAPE, "Lm_out must be (kernels,M,M)");
+  int qmode = 0, nq = 0;
+  if (tq.present) {
+    if (tq.ndim == 2) { if (tq.shape[0] != M || tq.shape[1] != R) return fail(FFVD_E_SHAPE, "2-d q_sqrt must be (M,R)"); qmode = 2; nq = R; }
+    else if (tq.ndim == 3) {
+      if (tq.shape[1] != M || tq.shape[2] != M || (tq.shape[0] != R && tq.shape[0] != 1)) return fail(FFVD_E_SHAPE, "3-d q_sqrt must be (R,M,M) or (1,M,M)");
+      qmode = 3; nq = (int)tq.shape[0];
+    } else return fail(FFVD_E_SHAPE, "Bad dimension for q_sqrt");
+  }
+  if (N == 0) return call.finish();
+  Layout L; DevProblem P;
+  c->force_blocked = tL.present;
+  int st0 = setup_zside(c, kind, tZ, tv, tl, nk, R, jitter, L, P, false, false);
+  c->force_blocked = false;
+  c->kzz_valid = false;                     // (a forced blocked factorisation must not be mistaken for the default path's)
+  if (st0 != FFVD_OK) return st0;
+  const int Mp = P.Mp;
+  double *Kmn = nullptr, *A = nullptr, *A2 = nullptr, *LTA = nullptr, *Knn = nullptr;
+  const size_t mn = (size_t)M * N;
+  CUDA_TRY(cudaMallocAsync((void**)&Kmn, mn * 8, c->stream));
+  CUDA_TRY(cudaMallocAsync((void**)&A, mn * 8, c->stream));
+  CUDA_TRY(cudaMallocAsync((void**)&A2, mn * 8, c->stream));
+  CUDA_TRY(cudaMallocAsync((void**)&LTA, mn * 8, c->stream));
+  CUDA_TRY(cudaMallocAsync((void**)&Knn, (full_cov ? (size_t)N * N : (size_t)N) * 8, c->stream));
+  const double* Ause = nullptr;
+  for (int r = 0; r < R; ++r) {
+    const int k = shared_kernel ? 0 : r;
+    double* var_r = full_cov ? tvar.d + (size_t)r * N * N : tvar.d + r;
+    const int ldv = full_cov ? N : R;
+    if (r == 0 || !shared_kernel) {
+      const double* lv = tv.d + k;
+      const double* ll = kind == FFVD_KERNEL_SE ? tl.d + (size_t)k * Din : nullptr;
+      const double* Li = P.Linv + (size_t)k * Mp * Mp;
+      const double* LiT = P.LinvT + (size_t)k * Mp * Mp;
+      if (kind == FFVD_KERNEL_SE) kernel_K_kernel<0><<<grid1d(mn), 256, 0, c->stream>>>(tZ.d, tX.d, M, N, Din, lv, ll, Kmn);
+      else kernel_K_kernel<1><<<grid1d(mn), 256, 0, c->stream>>>(tZ.d, tX.d, M, N, Din, lv, nullptr, Kmn);
+      c->launches++;
+      if (full_cov) {
+        if (kind == FFVD_KERNEL_SE) kernel_K_kernel<0><<<grid1d((size_t)N * N), 256, 0, c->stream>>>(tX.d, tX.d, N, N, Din, lv, ll, Knn);
+        else kernel_K_kernel<1><<<grid1d((size_t)N * N), 256, 0, c->stream>>>(tX.d, tX.d, N, N, Din, lv, nullptr, Knn);
+      } else {
+        if (kind == FFVD_KERNEL_SE) kernel_Kdiag_kernel<0><<<grid1d(N), 256, 0, c->stream>>>(tX.d, N, Din, lv, Knn);
+        else kernel_Kdiag_kernel<1><<<grid1d(N), 256, 0, c->stream>>>(tX.d, N, Din, lv, Knn);
+      }
+      c->launches++;
+      launch_gemm_small(c, A, N, Li, Mp, 0, Kmn, N, 0, M, N, M, 1.0, 0.0);                       // A = L^{-1} Kmn        (:37 / cmo:37)
+      Ause = A;
+      if (!white) { launch_gemm_small(c, A2, N, LiT, Mp, 0, A, N, 0, M, N, M, 1.0, 0.0); Ause = A2; }   // A = L^{-T} A (:45-46)
+    }
+    // fvar = Knn - A^T A with the FIRST A (before the non-white substitution), conditionals.py:39-44
+    if (full_cov) {
+      CUDA_TRY(cudaMemcpyAsync(var_r, Knn, (size_t)N * N * 8, cudaMemcpyDeviceToDevice, c->stream));
+      launch_gemm_small(c, var_r, N, A, N, 1, A, N, 0, N, N, M, -1.0, 1.0);
+    } else {
+      colsumsq_kernel<<<grid1d(N), 256, 0, c->stream>>>(var_r, ldv, Knn, A, M, N, nullptr, 0, -1.0, 0); c->launches++;
+    }
+    launch_gemm_small(c, tm.d + r, R, Ause, N, 1, tf.d + r, R, 0, N, 1, M, 1.0, 0.0);              // fmean = A^T f          (:48)
+    if (qmode == 3) {
+      const double* qr = tq.d + (size_t)(nq == 1 ? 0 : r) * M * M;
+      launch_gemm_small(c, LTA, N, qr, M, 1, Ause, N, 0, M, N, M, 1.0, 0.0);                       // LTA = q^T A            (:53-55)
+      if (full_cov) launch_gemm_small(c, var_r, N, LTA, N, 1, LTA, N, 0, N, N, M, 1.0, 1.0);
+      else { colsumsq_kernel<<<grid1d(N), 256, 0, c->stream>>>(var_r, ldv, nullptr, LTA, M, N, nullptr, 0, 1.0, 1); c->launches++; }
+    } else if (qmode == 2) {
+      if (full_cov) {
+        scale_rows_kernel<<<grid1d(mn), 256, 0, c->stream>>>(LTA, Ause, M, N, tq.d + r, R); c->launches++;   // LTA = A * q[:, r] (:51-52)
+        launch_gemm_small(c, var_r, N, LTA, N, 1, LTA, N, 0, N, N, M, 1.0, 1.0);
+      } else {
+        colsumsq_kernel<<<grid1d(N), 256, 0, c->stream>>>(var_r, ldv, nullptr, Ause, M, N, tq.d + r, R, 1.0, 1); c->launches++;
+      }
+    }
+  }
+  if (tL.present) {
+    const double* Lfac = (const double*)(c->arena + L.off_Lfac);
+    for (int k = 0; k < nk; ++k) {
+      tril_copy_kernel<<<grid1d((size_t)M * M), 256, 0, c->stream>>>(tL.d + (size_t)k * M * M, Lfac + (size_t)k * Mp * Mp, M, Mp); c->launches++;
+    }
+  }
+  for (double* p : {Kmn, A, A2, LTA, Knn}) CUDA_TRY(cudaFreeAsync(p, c->stream));
+  CUDA_TRY(cudaGetLastError());
+  int st = check_status(c, L);
+  TRY(call.finish());
+  return st;
+}
+
 extern "C" int ffvd_logdensity_norm_diag(ffvd_ctx* c, DLManagedTensor* y, DLManagedTensor* ymean, DLManagedTensor* Rchols,
                                          int vec, DLManagedTensor* out) {
   if (!c) return fail(FFVD_E_BADARG, "ctx is null");
@@ -1425,9 +1593,8 @@ extern "C" int ffvd_sghmc_update(ffvd_ctx* c, DLManagedTensor* theta, DLManagedT
   const size_t n = tt.numel;
   if (tg.numel != n || tn.numel != n || txi.numel != n || tgg.numel != n || tg2.numel != n || tp.numel != n)
     return fail(FFVD_E_SHAPE, "all SG-HMC tensors must have the same number of elements");
-  for (auto& s : call.staged)
-    if (s.host == tt.host || s.host == tp.host || (burn_in && (s.host == txi.host || s.host == tgg.host || s.host == tg2.host)))
-      s.is_out = true;
+  call.mark_inout(tt); call.mark_inout(tp);
+  if (burn_in) { call.mark_inout(txi); call.mark_inout(tgg); call.mark_inout(tg2); }
   if (n) {
     const double eps_scaled = epsilon / sqrt(X_N);
     const int grid = grid1d(n, 256, c->num_sms * 8);
@@ -1455,8 +1622,7 @@ extern "C" int ffvd_adam_update(ffvd_ctx* c, DLManagedTensor* theta, DLManagedTe
   TRY(call.import(v, false, tv, "v"));
   const size_t n = tt.numel;
   if (tg.numel != n || tm.numel != n || tv.numel != n) return fail(FFVD_E_SHAPE, "all Adam tensors must have the same size");
-  for (auto& s : call.staged)
-    if (s.host == tt.host || s.host == tm.host || s.host == tv.host) s.is_out = true;
+  call.mark_inout(tt); call.mark_inout(tm); call.mark_inout(tv);
   if (n) {
     const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
     const bool vec = ((((uintptr_t)tt.d | (uintptr_t)tg.d | (uintptr_t)tm.d | (uintptr_t)tv.d)) & 15) == 0;

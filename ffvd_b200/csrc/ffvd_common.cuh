@@ -3,6 +3,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Index checks of the fused kernels (make check: -DFFVD_BOUNDS_CHECK, tools/bounds_check.py).  compute-sanitizer is not
+// available on the development pool, so the checks the sanitizer would make on the hand-computed shared / global indices are
+// asserted in a diagnostic build instead: a violation prints the condition and traps (the call returns FFVD_E_CUDA).
+#ifdef FFVD_BOUNDS_CHECK
+#include <cstdio>
+#define FFVD_ASSERT(cond)                                                                                              \
+  do {                                                                                                                 \
+    if (!(cond)) {                                                                                                     \
+      printf("FFVD_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+#else
+#define FFVD_ASSERT(cond) do { } while (0)
+#endif
+
 #define FFVD_NTHREADS 256
 #define FFVD_NWARPS 8
 #define FFVD_XLD 36            // row stride of the x-tile arrays in shared memory (doubles); 36 = 4 mod 16 keeps the

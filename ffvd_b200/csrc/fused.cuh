@@ -30,6 +30,24 @@ __device__ unsigned long long g_phase_clocks[16];
 #include "fused_modes.cuh"
 namespace ffvd {
 
+// Four consecutive doubles of a tile row as two 16-byte shared-memory accesses.  A quarter-warp (the unit of a 16-byte
+// access) is lanes (g, g+1) x q = 0..3, and with lda = 4 mod 16 rows g and g+1 start 4 doubles (two 16-byte banks) apart:
+// if every lane touched columns {0,1} first, lane (g, q) and lane (g+1, q-1) would hit the same bank (ncu: 11% of the
+// kernel's shared wavefronts were such 2-way conflicts).  Odd rows therefore go {2,3} first, {0,1} second.
+__device__ __forceinline__ void st_tile4(double* p, int g, double a, double b, double c, double d) {
+  const bool odd = (g & 1) != 0;
+  *reinterpret_cast<double2*>(p + (odd ? 2 : 0)) = odd ? make_double2(c, d) : make_double2(a, b);
+  *reinterpret_cast<double2*>(p + (odd ? 0 : 2)) = odd ? make_double2(a, b) : make_double2(c, d);
+}
+__device__ __forceinline__ void ld_tile4(const double* p, int g, double& a, double& b, double& c, double& d) {
+  const bool odd = (g & 1) != 0;
+  const double2 u = *reinterpret_cast<const double2*>(p + (odd ? 2 : 0));
+  const double2 v = *reinterpret_cast<const double2*>(p + (odd ? 0 : 2));
+  a = odd ? v.x : u.x; b = odd ? v.y : u.y; c = odd ? u.x : v.x; d = odd ? u.y : v.y;
+}
+
+#define FFVD_TILE_ROWS_FACTOR 2      /* compute_k_tile sees RB = rows per warp / 8; a tile has at most twice that (NW = 16) */
+
 struct Smem {
   double* tile;     // BT x lda
   double* xs;       // (BT+1) x XLD : X~ rows t0..t0+BT  = [x_t, ctrl_t, 1, 0..]
@@ -137,8 +155,8 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
 #pragma unroll
       for (int c = 0; c < 4; ++c) kv[4 * i + c] *= vc[c];
       double* p = sm.tile + row * lda + jb;
-      *reinterpret_cast<double2*>(p) = make_double2(kv[4 * i], kv[4 * i + 1]);
-      *reinterpret_cast<double2*>(p + 2) = make_double2(kv[4 * i + 2], kv[4 * i + 3]);
+      FFVD_ASSERT(row >= 0 && row < 8 * RB * (FFVD_TILE_ROWS_FACTOR) && jb >= 0 && jb + 4 <= Mp && jb + 4 <= lda);
+      st_tile4(p, g, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
       if (SCR && FFVD_ABLATE != 4) stg256(kscr + (size_t)row * Mp + jb, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
     }
   }
@@ -176,7 +194,10 @@ __device__ __forceinline__ void gemm_segment(double (&acc)[NG][RB][4], double2 (
         if (TRI < 0 && ng == HI) doit = kl >= joff[ng];
         if (TRI <= 0) doit = doit && (kl < Mp);
         if ((ng >= LO && ng < HI) || (TRI < 0 && ng == HI)) {
-          if (doit) ring[(u + 3) & 3][ng] = ldg_stream2(bl + joff[ng]);
+          if (doit) {
+            FFVD_ASSERT(kl >= 0 && kl + q < Mp && joff[ng] >= 0 && joff[ng] + 16 <= Mp);
+            ring[(u + 3) & 3][ng] = ldg_stream2(bl + joff[ng]);
+          }
         }
       }
       double a[RB];
@@ -269,8 +290,8 @@ __device__ __forceinline__ void store_tile(const double (&acc)[NGW][RB][4], doub
 #pragma unroll
     for (int rb = 0; rb < RB; ++rb) {
       double* p = tile + (8 * rb + g) * lda + jb;
-      *reinterpret_cast<double2*>(p) = make_double2(acc[ng][rb][0], acc[ng][rb][1]);
-      *reinterpret_cast<double2*>(p + 2) = make_double2(acc[ng][rb][2], acc[ng][rb][3]);
+      FFVD_ASSERT(jb >= 0 && jb + 4 <= lda - 4);
+      st_tile4(p, g, acc[ng][rb][0], acc[ng][rb][1], acc[ng][rb][2], acc[ng][rb][3]);
     }
   }
 }
@@ -316,6 +337,7 @@ __device__ __forceinline__ void syrk_tile(const double* tile, int lda, int Mp, d
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
 #if FFVD_ABLATE != 1
+        FFVD_ASSERT(m0 + 8 * i + r < Mp && n0 + lane < Mp && n0 <= m0);
         red_add(S + (size_t)(m0 + 8 * i + r) * Mp + n0 + lane, stage_w[r * 40 + lane]);
 #else
         if (stage_w[r * 40 + lane] == 1.2345e300) red_add(S, 1.0);
@@ -443,6 +465,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
                 } else {
                   zb = v * c[u][nb][e];
                 }
+                FFVD_ASSERT(m < M && jd < Din);
                 red_add(P.gZ + (size_t)m * Din + jd, zb);
               }
             }
@@ -518,9 +541,11 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
       for (int nb = 0; nb < NBM; ++nb)
-        if (nb < nbx)
+        if (nb < nbx) {
+          FFVD_ASSERT((ks * BT + 8 * (RPW * rg + r) + g) < 128 && 8 * nb + 2 * q + 2 <= PW);
           *reinterpret_cast<double2*>(sm.part + (size_t)(ks * BT + 8 * (RPW * rg + r) + g) * PW + 8 * nb + 2 * q) =
               make_double2(c[r][nb][0], c[r][nb][1]);
+        }
   }
   FFVD_MARK(9);
   __syncthreads();
@@ -547,6 +572,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           xb = v * wz;
           vacc = fma(x, xb, vacc);                  // sum kbar*k
         }
+        FFVD_ASSERT(t0 + r < P.T);
         if (lane < D) red_add(gXs + (size_t)(t0 + r) * D + lane, xb);
       }
     }
@@ -645,6 +671,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
     const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, Mp = P.Mp, nc = P.nc;
     const int lda = Mp + 4;
+    FFVD_ASSERT(li >= 0 && li < P.nitems && d0 >= 0 && nd >= 1 && d0 + nd <= P.D && tile_i >= 0 && tile_i < P.ntiles && s >= 0 && s < P.S);
+    FFVD_ASSERT(Mp == 16 * NGW * NCW);
     const int t0 = tile_i * BT;
     const int nvalid = min(BT, T - t0);
     const double* Xs = P.X + (size_t)s * P.xrows * Dx;
@@ -851,6 +879,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
               jtr = -0.5 * sig2 * invQ;
               gq = 0.5 * res * res * invQ - 0.5 + 0.5 * sig2 * invQ;
               if (MODE == MODE_UNCOLLAPSED) {
+                FFVD_ASSERT(t0 + r + 1 <= T && d < D);
                 red_add(gXs + (size_t)(t0 + r) * D + d, e);
                 red_add(gXs + (size_t)(t0 + r + 1) * D + d, -e);
               }
@@ -1044,13 +1073,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 #pragma unroll
               for (int rb = 0; rb < RBW; ++rb) {
                 const double* p = wtile + (8 * rb + g) * lda + jb;
-                const double2 k01 = *reinterpret_cast<const double2*>(p);
-                const double2 k23 = *reinterpret_cast<const double2*>(p + 2);
-                kv[rb][0] = k01.x; kv[rb][1] = k01.y; kv[rb][2] = k23.x; kv[rb][3] = k23.y;
+                ld_tile4(p, g, kv[rb][0], kv[rb][1], kv[rb][2], kv[rb][3]);
               }
             } else {
 #pragma unroll
               for (int rb = 0; rb < RBW; ++rb) {
+                FFVD_ASSERT(row0 + 8 * rb + g < BT && jb + 4 <= Mp);
                 ldg256_cg(kscr + (size_t)(row0 + 8 * rb + g) * Mp + jb, kv[rb][0], kv[rb][1], kv[rb][2], kv[rb][3]);
               }
             }

@@ -145,7 +145,8 @@ int ffvd_kernel_pre_cal(ffvd_ctx*, int kind, DLManagedTensor* Z, DLManagedTensor
  * recomputed on the device, so Lm_inverse_seq is not an input.
  * mean_out, var_out (N,R).  q_sqrt (nullable): (M,R) per-point scales (cmo:51-52) or (R,M,M) /
  * (1,M,M) factors (cmo:53-62; (1,M,M) = one factor for every output, which is what the
- * reference's [:, :, 0] indexing computes); requires white=1.  full_cov=1 is not built. */
+ * reference's [:, :, 0] indexing computes); requires white=1.  full_cov=1, q_sqrt with white=0 and return_Lm:
+ * ffvd_conditional_dense. */
 int ffvd_conditional(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
                      DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f,
                      DLManagedTensor* q_sqrt, int white, int full_cov, double jitter,
@@ -160,6 +161,15 @@ int ffvd_conditional_ex(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor*
                         DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f,
                         DLManagedTensor* q_sqrt, int white, int full_cov, double jitter, int flags,
                         DLManagedTensor* mean_out, DLManagedTensor* var_out);
+
+/* Every option of base_conditional (conditionals.py:6-66, conditionals_multi_output.py:6-70) on explicit matrices, op for
+ * op: full_cov (var_out (R,N,N)), q_sqrt 2-d / 3-d with white or not, and return_Lm (Lm_out (kernels,M,M) = the Cholesky
+ * factor of K(Z,Z) + jitter I, nullable).  For a handful of prediction points: O(M N (M + N)) work in plain FP64 kernels;
+ * the hot-path branch (white, diagonal variances, any N) is ffvd_conditional_ex. */
+int ffvd_conditional_dense(ffvd_ctx*, int kind, int shared_kernel, DLManagedTensor* Xnew, DLManagedTensor* Z,
+                           DLManagedTensor* logv, DLManagedTensor* logl, DLManagedTensor* f, DLManagedTensor* q_sqrt,
+                           int white, int full_cov, double jitter, DLManagedTensor* mean_out, DLManagedTensor* var_out,
+                           DLManagedTensor* Lm_out);
 
 /* conditionals_multi_output.py:206-227 collapse_u_mean_after_kernel_precalculation: the optimal
  * collapsed q(u).  Per sample s and output d: F = K(Xc,Z) L^{-T}, H = F^T F / Q_d + I,

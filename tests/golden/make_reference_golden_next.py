@@ -191,8 +191,35 @@ def golden_f3(out):
         print(key, "evals", gr.evals, "nll_final %.12f" % out[key + "/nll_final"], "sampled vars", len(model.vars), flush=True)
 
 
+def golden_conditional_options(out):
+    """base_conditional's other branches (conditionals.py:27-66): full_cov, q_sqrt 2-d / 3-d whitened or not, return_Lm --
+    the single-kernel conditional on a small SE problem, and the multi-output one with full_cov (its (N,1,D) quirk)."""
+    from vfegpssm import conditionals
+    tf.reset_shim(9)
+    rng = np.random.default_rng(9)
+    M, R, N, Din = 23, 3, 11, 4
+    Zs = rng.standard_normal((M, Din)) * 1.5; Xn = rng.standard_normal((N, Din)); fm = rng.standard_normal((M, R))
+    q3 = np.tril(rng.standard_normal((R, M, M))) * 0.2; q2 = rng.uniform(0.1, 1.0, (M, R))
+    ls = rng.uniform(1.0, 3.0, Din)
+    se = G.BgpSE(Din, variance=0.7, lengthscales=ls, ARD=True)
+    out["cond/Z"] = Zs; out["cond/Xnew"] = Xn; out["cond/f"] = fm; out["cond/q3"] = q3; out["cond/q2"] = q2; out["cond/ls"] = ls
+    c = lambda a: tf.constant(a)
+    for tag, kw in (("full", dict(full_cov=True, white=True)), ("full_q3", dict(full_cov=True, white=True, q_sqrt=c(q3))),
+                    ("full_q2", dict(full_cov=True, white=True, q_sqrt=c(q2))), ("nonwhite_q3", dict(white=False, q_sqrt=c(q3))),
+                    ("nonwhite_q2", dict(white=False, q_sqrt=c(q2))), ("full_nonwhite_q3", dict(full_cov=True, white=False, q_sqrt=c(q3)))):
+        mu, var = conditionals.conditional(c(Xn), c(Zs), se, c(fm), **kw)
+        out["cond/%s/mean" % tag] = n(mu); out["cond/%s/var" % tag] = n(var)
+    mu, var, Lm = conditionals.conditional(c(Xn), c(Zs), se, c(fm), white=True, return_Lm=True)
+    out["cond/return_Lm/mean"] = n(mu); out["cond/return_Lm/var"] = n(var); out["cond/return_Lm/Lm"] = n(Lm)
+    se2 = G.BgpSE(Din, variance=0.3, lengthscales=ls[::-1].copy(), ARD=True)
+    mu, var = cmo.conditional(c(Xn), c(Zs), [se, se2], c(fm[:, :2]), white=True, full_cov=True)
+    out["cond/multi_full/mean"] = n(mu); out["cond/multi_full/var"] = n(var)
+    print("conditional options: multi full_cov var shape", out["cond/multi_full/var"].shape, flush=True)
+
+
 def main():
     out = {}
+    golden_conditional_options(out)
     golden_f2(out)
     golden_f4(out)
     golden_f3(out)

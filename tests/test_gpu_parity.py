@@ -973,3 +973,80 @@ def test_cuda_graph_sghmc_step_and_capture_rules(env):
     for k in ref:
         assert_close(ref[k].cpu().numpy(), o[k].cpu().numpy(), 1e-10, k)
     g.close()
+
+
+def test_mirrors_reject_inconsistent_precalculated_inputs(env):
+    """The fused path recomputes the K(Z,Z) factors and rebuilds [x_t, c_t] from X; `Lm_inverse_seq` / `X_combine` that do
+    not match (Z, kern) / X must raise instead of being silently ignored -- and consistent ones (a `kernel_pre_cal`
+    result, or plain matrices equal to it) are accepted."""
+    import torch as th
+    from ffvd_b200 import conditionals_multi_output as cmo
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    prob = env["byname"]["gas_furnace/0"]
+    T, D, Din = prob.Y.shape[0], prob.X.shape[1], prob.Z.shape[1]
+    kerns = [SquaredExponential(Din, variance=np.exp(prob.logv[k]), lengthscales=np.exp(prob.logl[k]), ARD=True) for k in range(D)]
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    X, Z, Q = t(prob.X), t(prob.Z), t(np.exp(prob.logQ))
+    Xc = t(np.concatenate([prob.X[:T], prob.ctrl], axis=1))
+    fac = cmo.kernel_pre_cal(Z, kerns)
+    base = cmo.collapse_after_kernel_precalculation(None, Xc, X, Z, kerns, Q, T, T)
+    for L in (fac, [a.clone() for a in fac], [a.cpu().numpy() for a in fac]):
+        got = cmo.collapse_after_kernel_precalculation(L, Xc, X, Z, kerns, Q, T, T)
+        for a, b in zip(base, got):
+            assert abs(float(a) - float(b)) <= 1e-12 * abs(float(a))
+    bad_fac = [a * 1.01 for a in fac]
+    Xc_bad = Xc.clone(); Xc_bad[3, 0] += 0.5
+    with pytest.raises(ValueError):
+        cmo.collapse_after_kernel_precalculation(bad_fac, Xc, X, Z, kerns, Q, T, T)
+    with pytest.raises(ValueError):
+        cmo.collapse_after_kernel_precalculation(fac, Xc_bad, X, Z, kerns, Q, T, T)
+    with pytest.raises(ValueError):
+        cmo.collapse_u_mean_after_kernel_precalculation(cmo.kernel_pre_cal(Z * 1.1, kerns), Xc, X, Z, kerns, Q)
+    with pytest.raises(ValueError):
+        cmo.conditional_after_kernel_precalculation(bad_fac, Xc[:5], Z, kerns, t(prob.U), white=True)
+    mu0, _ = cmo.conditional_after_kernel_precalculation(None, Xc[:5].contiguous(), Z, kerns, t(prob.U), white=True)
+    mu1, _ = cmo.conditional_after_kernel_precalculation([a.clone() for a in fac], Xc[:5].contiguous(), Z, kerns, t(prob.U), white=True)
+    assert_close(mu0.cpu().numpy(), mu1.cpu().numpy(), 1e-12)
+
+
+def test_bounds_checked_build():
+    """tools/bounds_check.py: the parity sweep on the -DFFVD_BOUNDS_CHECK library (device-side assertions on the fused
+    kernels' index arithmetic).  Skipped if `make check` was not run."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "ffvd_b200", "lib", "libffvd_b200_check.so")):
+        pytest.skip("make check not run")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bounds_check.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL OK" in r.stdout
+
+
+def test_conditional_option_branches_vs_reference_source(env, gold_next):
+    """The dense conditional (ffvd_conditional_dense): full_cov, q_sqrt 2-d / 3-d whitened or not, return_Lm
+    (conditionals.py:27-66) and the multi-output full_cov quirk shape (cmo:119-120) vs the reference source's outputs."""
+    import torch as th
+    from ffvd_b200 import conditionals, conditionals_multi_output as cmo
+    from ffvd_b200.kernels_multi_output import SquaredExponential
+    g = gold_next
+    t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+    Z, Xn, f, q3, q2 = (t(g["cond/" + k]) for k in ("Z", "Xnew", "f", "q3", "q2"))
+    se = SquaredExponential(Z.shape[1], variance=0.7, lengthscales=g["cond/ls"], ARD=True)
+    for tag, kw in (("full", dict(full_cov=True, white=True)), ("full_q3", dict(full_cov=True, white=True, q_sqrt=q3)),
+                    ("full_q2", dict(full_cov=True, white=True, q_sqrt=q2)), ("nonwhite_q3", dict(white=False, q_sqrt=q3)),
+                    ("nonwhite_q2", dict(white=False, q_sqrt=q2)), ("full_nonwhite_q3", dict(full_cov=True, white=False, q_sqrt=q3))):
+        mu, var = conditionals.conditional(Xn, Z, se, f, **kw)
+        assert tuple(var.shape) == tuple(g["cond/%s/var" % tag].shape)
+        assert_close(g["cond/%s/mean" % tag], mu.cpu().numpy(), TOL, tag)
+        assert_close(g["cond/%s/var" % tag], var.cpu().numpy(), TOL, tag)
+    mu, var, Lm = conditionals.conditional(Xn, Z, se, f, white=True, return_Lm=True)
+    assert_close(g["cond/return_Lm/mean"], mu.cpu().numpy(), TOL)
+    assert_close(g["cond/return_Lm/var"], var.cpu().numpy(), TOL)
+    assert_close(g["cond/return_Lm/Lm"], Lm.cpu().numpy(), 1e-11, "Lm")
+    se2 = SquaredExponential(Z.shape[1], variance=0.3, lengthscales=g["cond/ls"][::-1].copy(), ARD=True)
+    mu, var = cmo.conditional(Xn, Z, [se, se2], f[:, :2].contiguous(), white=True, full_cov=True)
+    assert tuple(var.shape) == (Xn.shape[0], 1, 2)
+    assert_close(g["cond/multi_full/mean"], mu.cpu().numpy(), TOL)
+    assert_close(g["cond/multi_full/var"], var.cpu().numpy(), TOL)
+    # NumPy tensors through the same path
+    mu_h, var_h = conditionals.conditional(g["cond/Xnew"], g["cond/Z"], se, g["cond/f"], full_cov=True, white=True)
+    assert_close(g["cond/full/var"], var_h, TOL)

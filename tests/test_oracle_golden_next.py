@@ -114,3 +114,22 @@ def test_outer_loop_vs_reference_source(gold, packed, case_val):
     # the loop moved every trainable parameter (this is a trajectory, not a fixed point)
     for k in loop.trainable_names(case_val):
         assert np.max(np.abs(res["params"][k] - getattr(prob, k))) > 0
+
+
+def test_conditional_option_branches_vs_reference_source(gold):
+    """base_conditional's full_cov / q_sqrt (2-d, 3-d; whitened or not) / return_Lm branches (conditionals.py:27-66)."""
+    g = gold
+    Z, Xn, f, q3, q2 = (tt(g["cond/" + k]) for k in ("Z", "Xnew", "f", "q3", "q2"))
+    se = O.SquaredExponential(Z.shape[1], variance=0.7, lengthscales=g["cond/ls"], ARD=True)
+    for tag, kw in (("full", dict(full_cov=True, white=True)), ("full_q3", dict(full_cov=True, white=True, q_sqrt=q3)),
+                    ("full_q2", dict(full_cov=True, white=True, q_sqrt=q2)), ("nonwhite_q3", dict(white=False, q_sqrt=q3)),
+                    ("nonwhite_q2", dict(white=False, q_sqrt=q2)), ("full_nonwhite_q3", dict(full_cov=True, white=False, q_sqrt=q3))):
+        mu, var = O.conditional(Xn, Z, se, f, **kw)
+        assert_close(g["cond/%s/mean" % tag], mu.numpy(), 1e-10, tag)
+        assert_close(g["cond/%s/var" % tag], var.numpy(), 1e-10, tag)
+    mu, var, Lm = O.conditional(Xn, Z, se, f, white=True, return_Lm=True)
+    assert_close(g["cond/return_Lm/Lm"], Lm.numpy(), 1e-12, "Lm")
+    se2 = O.SquaredExponential(Z.shape[1], variance=0.3, lengthscales=g["cond/ls"][::-1].copy(), ARD=True)
+    mu, var = O.conditional_multi_output(Xn, Z, [se, se2], f[:, :2], white=True, full_cov=True)
+    assert tuple(var.shape) == tuple(g["cond/multi_full/var"].shape) == (Xn.shape[0], 1, 2)
+    assert_close(g["cond/multi_full/var"], var.numpy(), 1e-10, "multi full_cov")
