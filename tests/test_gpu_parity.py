@@ -227,9 +227,12 @@ def test_host_numpy_tensors_are_staged(env):
 def test_error_statuses(env):
     ffvd, torch, ctx = env["ffvd"], env["torch"], env["ctx"]
     prob = copy.copy(env["byname"]["drive/0"])
-    # float32 input -> ValueError (dtype)
+    # float16 / integer input -> ValueError (dtype); float32 is the widened float32 mode (test_float32_tensor_mode)
     p = dev_problem(env, prob); o = alloc_out(env, p)
-    p["Z"] = p["Z"].to(torch.float32)
+    p["Z"] = p["Z"].to(torch.float16)
+    with pytest.raises(ValueError):
+        ctx.nll_grads(0, False, p, o)
+    p["Z"] = p["Z"].to(torch.int64)
     with pytest.raises(ValueError):
         ctx.nll_grads(0, False, p, o)
     # shape mismatch
@@ -1050,3 +1053,48 @@ def test_conditional_option_branches_vs_reference_source(env, gold_next):
     # NumPy tensors through the same path
     mu_h, var_h = conditionals.conditional(g["cond/Xnew"], g["cond/Z"], se, g["cond/f"], full_cov=True, white=True)
     assert_close(g["cond/full/var"], var_h, TOL)
+
+
+def test_float32_tensor_mode(env):
+    """float32 mode of the north star (<= 1e-4): every tensor crosses the ABI as float32 (device or host), is widened on the
+    device, computed in float64 and narrowed once.  Against the float64 oracle on the SAME (float32-representable) inputs:
+    nll + all gradients on a bundled warm start (both forms), the SG-HMC update in place, and mixed float32 / float64 calls."""
+    import torch as th
+    from oracle import ffvd_oracle as O
+    torch, ctx, F = env["torch"], env["ctx"], env["ffvd"]
+    prob = copy.deepcopy(env["byname"]["dryer/0"])
+    for k in PKEYS:
+        setattr(prob, k, np.asarray(getattr(prob, k), dtype=np.float32).astype(np.float64))      # float32-representable inputs
+    for collapsed in (False, True):
+        ref = O.nll_and_grads(prob, collapsed=collapsed)
+        p32 = {k: th.as_tensor(np.ascontiguousarray(getattr(prob, k)), dtype=th.float32, device=env["dev"]) for k in PKEYS}
+        o32 = {"nll": th.empty(1, dtype=th.float32, device=env["dev"]), "terms": th.empty(1, 6, dtype=th.float32, device=env["dev"])}
+        for k in GKEYS:
+            o32["g_" + k] = th.full_like(p32[k], float("nan"))
+        ctx.nll_grads(0, collapsed, p32, o32)
+        torch.cuda.synchronize()
+        for k, v in o32.items():
+            assert v.dtype == th.float32
+            r = ref[k] if k not in ("nll", "terms") else np.asarray(ref[k]).reshape(v.shape)
+            assert relerr(r, v.cpu().numpy().astype(np.float64)) <= 1e-4, (collapsed, k)
+            assert relerr(r, v.cpu().numpy().astype(np.float64)) <= 5e-7, (collapsed, k)      # in fact only the final rounding
+        # host float32 (NumPy) in and out, float64 outputs mixed in
+        ph = {k: np.ascontiguousarray(getattr(prob, k), dtype=np.float32) for k in PKEYS}
+        oh = {"nll": np.empty(1, dtype=np.float64), "g_X": np.empty(prob.X.shape, dtype=np.float32), "g_Z": np.empty(prob.Z.shape, dtype=np.float64)}
+        ctx.nll_grads(0, collapsed, ph, oh)
+        assert relerr(ref["g_X"], oh["g_X"].astype(np.float64)) <= 5e-7 and relerr(ref["g_Z"], oh["g_Z"]) <= 1e-9
+        assert abs(oh["nll"][0] - ref["nll"]) <= 1e-9 * abs(ref["nll"])
+    # SG-HMC update in place on float32 state
+    rng = np.random.default_rng(1)
+    n = 1001
+    arrs = [rng.standard_normal(n).astype(np.float32) for _ in range(3)] + [np.ones(n, np.float32), np.ones(n, np.float32),
+                                                                                np.full(n, 1.5, np.float32), (0.1 * rng.standard_normal(n)).astype(np.float32)]
+    ref = O.sghmc_update(*[a.astype(np.float64) for a in arrs], epsilon=0.01, mdecay=0.05, X_N=201, burn_in=True)
+    dev = [th.as_tensor(a, device=env["dev"]) for a in arrs]
+    ctx.sghmc_update(*dev, 0.01, 0.05, 201.0, True)
+    torch.cuda.synchronize()
+    th_, gr, nz, xi, g, g2, pm = dev
+    for a, b in zip(ref, (th_, xi, g, g2, pm)):
+        assert relerr(a, b.cpu().numpy().astype(np.float64)) <= 5e-7
+    with pytest.raises(ValueError):
+        ctx.sghmc_update(*[d.to(th.float16) for d in dev], 0.01, 0.05, 201.0, True)
