@@ -18,7 +18,8 @@ Besides the headline numbers the JSON line carries
            all-reduced shared gradients of a small sample-sharded problem against rank 0's single-GPU evaluation.
   extra  : BASELINE.json's other named configurations measured in the same run -- c4_95chains (configs[3]: the 95
            bundled warm starts dealt round-robin over the ranks) and, at N>=2, c3_strong (configs[2] with its S=64 split
-           over the ranks) and c5 (configs[4]: T=1M, M=512, D=16, 32 trajectories per rank = the full S=256 job at N=8).
+           over the ranks), time_sharded_chain (one trajectory split over time, uncollapsed and collapsed) and c5
+           (configs[4]: T=1M, M=512, D=16, 32 trajectories per rank = the full S=256 job at N=8).
 """
 import argparse
 import json
@@ -452,6 +453,50 @@ def extra_c4(ctx, dev, rank, world, barrier, K):
     return res
 
 
+def extra_time_sharded(ctx, dev, rank, world, barrier, K):
+    """ONE long trajectory (S = 1 < number of GPUs) sharded over TIME: contiguous blocks of transitions with a
+    one-row halo; uncollapsed (one packed all-reduce + halo gather) and collapsed (pass 1, all-reduce of F^T F / F^T delta
+    through the library's communicator, resume).  Evaluations only (nll + all gradients), device-generated data identical on
+    every rank (same seed), each rank takes its block."""
+    import torch
+    import torch.distributed as dist
+    import ffvd_b200
+    from ffvd_b200 import distributed as fd
+    T, M, D = 800_000, 256, 8
+    P = make_device_data(T, M, D, 1, seed=31337, dev=dev)
+    P["X"] = P["X"][0].contiguous()
+    a, b = fd.shard_range(T, rank, world)
+    out = {"nll": torch.empty(1, dtype=torch.float64, device=dev), "terms": torch.empty(1, 6, dtype=torch.float64, device=dev),
+           "g_X": torch.empty((b - a + 1, D), dtype=torch.float64, device=dev)}
+    for k in PARAMS[1:]:
+        out["g_" + k] = torch.empty_like(P[k])
+    FL = ffvd_b200.FLAG_PRIOR_Z_NORMAL
+
+    def ev(blk_p, blk_o, extra):
+        bp = {k: (v.contiguous() if v is not None else None) for k, v in blk_p.items()}
+        ctx.nll_grads(ffvd_b200.KERNEL_SE, False, bp, blk_o, flags=FL | extra | ffvd_b200.FLAG_ASYNC)
+
+    res = {}
+    for tag, fn in (("uncollapsed", lambda: fd.evaluate_time_sharded(ev, P, out, rank, world)),
+                    ("collapsed", lambda: fd.evaluate_time_sharded_collapsed(ctx, ffvd_b200.KERNEL_SE, P, out, rank, world, flags=FL | ffvd_b200.FLAG_ASYNC))):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        barrier()
+        tmax = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        res[tag] = {"ms_per_evaluation": float(tmax.item()), "T_D_per_s": T * D / (float(tmax.item()) * 1e-3), "nll": float(out["nll"][0].item())}
+    res["config"] = "one trajectory T=%d M=%d D=%d (S=1) split into %d time blocks, nll + all gradients per evaluation" % (T, M, D, world)
+    del P, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -652,6 +697,8 @@ def main():
             extra["c3_strong"] = extra_synthetic(ctx, dev, rank, world, barrier, "BASELINE configs[2] strong scaling: S=64 split over the ranks",
                                                  100_000, 256, 8, 64 // world, 3, 5, fp64_peak_tflops,
                                                  "total work fixed (S=64): compare value with the N=1 headline line")
+        if want_big and world >= 2:
+            extra["time_sharded_chain"] = extra_time_sharded(ctx, dev, rank, world, barrier, 5)
         if want_big:
             extra["c5"] = extra_synthetic(ctx, dev, rank, world, barrier,
                                           "BASELINE configs[4]: T=1M M=512 D=16, 32 trajectories per GPU%s"
