@@ -297,42 +297,43 @@ __device__ __forceinline__ void store_tile(const double (&acc)[NGW][RB][4], doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// S (lower 32x32 tiles) += tile^T tile  over the BT rows, flushed with coalesced RED.add.f64.
-// Work units: the nt(nt-1)/2 strictly-lower tiles (16 8x8 blocks each) followed by the nt diagonal tiles (only the
-// 10 blocks on or below the diagonal are formed), dealt to the warps in snake order so the per-warp block counts
-// differ by at most a few percent (Mp = 256: 64 vs 68 blocks).
-template <int RB, bool DIAG>
+// S (lower triangle, in 8x8 blocks) += tile^T tile  over the BT rows, flushed with coalesced RED.add.f64.
+// Work units: square tiles of NB x NB blocks (NB = 4: 32 x 32; NB = 2: 16 x 16 for Mp <= 128, where 32 x 32 tiles are too
+// few to go round -- 10 units for 16 warps at Mp = 128 left six warps idle and the phase at 48% of its DMMA floor): the
+// nt(nt-1)/2 strictly-lower tiles followed by the nt diagonal tiles (only the blocks on or below the diagonal are formed),
+// dealt to the warps in snake order so the per-warp block counts differ by at most a few percent (Mp = 256: 64 vs 68).
+template <int RB, bool DIAG, int NB>
 __device__ __forceinline__ void syrk_tile(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
                                           int m0, int n0, int lane) {
   const int g = lane >> 2, q = lane & 3;
-  double c[4][4][2];
+  double c[NB][NB][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    for (int j = 0; j < NB; ++j) c[i][j][0] = c[i][j][1] = 0.0;
 #pragma unroll 2
   for (int k0 = 0; k0 < 8 * RB; k0 += 4) {
-    double a[4], b[4];
+    double a[NB], b[NB];
     const double* row = tile + (k0 + q) * lda + g;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = row[m0 + 8 * i];
+    for (int i = 0; i < NB; ++i) a[i] = row[m0 + 8 * i];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = DIAG ? a[j] : row[n0 + 8 * j];
+    for (int j = 0; j < NB; ++j) b[j] = DIAG ? a[j] : row[n0 + 8 * j];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NB; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NB; ++j)
         if (!DIAG || j <= i) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
   }
   // transpose 8 rows at a time through the per-warp staging buffer (8 x 40 doubles), flush with coalesced REDs
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NB; ++i) {
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NB; ++j)
       *reinterpret_cast<double2*>(stage_w + g * 40 + 8 * j + 2 * q) = make_double2(c[i][j][0], c[i][j][1]);
     __syncwarp();
-    const int ncol = DIAG ? 8 * (i + 1) : 32;      // diagonal tiles: nothing right of block column i in block row i
+    const int ncol = DIAG ? 8 * (i + 1) : 8 * NB;  // diagonal tiles: nothing right of block column i in block row i
     if (lane < ncol) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -347,10 +348,10 @@ __device__ __forceinline__ void syrk_tile(const double* tile, int lda, int Mp, d
   }
 }
 
-template <int RB, int NW>
-__device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
+template <int RB, int NW, int NB>
+__device__ __forceinline__ void syrk_units(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
                                            int warp, int lane) {
-  const int nt = Mp >> 5;
+  const int nt = Mp / (8 * NB);
   const int nfull = nt * (nt - 1) / 2, nunits = nfull + nt;
   // units of this warp: i = 0 .. nu-1 with u(i) = i NW + (i odd ? NW-1-warp : warp) < nunits
   int nu = 0;
@@ -368,10 +369,10 @@ __device__ __forceinline__ void syrk_flush(const double* tile, int lda, int Mp, 
       while (ti * (ti - 1) / 2 > u) --ti;
       while ((ti + 1) * ti / 2 <= u) ++ti;
       const int tj = u - ti * (ti - 1) / 2;
-      syrk_tile<RB, false>(tile, lda, Mp, S, stage_w, 32 * ti, 32 * tj, lane);
+      syrk_tile<RB, false, NB>(tile, lda, Mp, S, stage_w, 8 * NB * ti, 8 * NB * tj, lane);
     } else {
       const int t = u - nfull;
-      syrk_tile<RB, true>(tile, lda, Mp, S, stage_w, 32 * t, 32 * t, lane);
+      syrk_tile<RB, true, NB>(tile, lda, Mp, S, stage_w, 8 * NB * t, 8 * NB * t, lane);
     }
   }
 }
@@ -598,7 +599,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
   constexpr int RBW = RB / (NW / NCW);
   static_assert(RBW >= 1 && RBW * (NW / NCW) == RB, "RB must be divisible by the row split");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int wc = warp % NCW, row0 = (warp / NCW) * 8 * RBW;
+  // Column warp of this warp.  With two row halves (NW = 16, NGW = 1) the second half owns the column groups in REVERSE
+  // order: a warp's triangular work is proportional to (group + 1), and the four warps of one SM sub-partition (w, w+4,
+  // w+8, w+12) then hold groups p, p+4, 7-p, 3-p -- 18 units on every sub-partition instead of 12 ... 24.
+  const int wr = warp / NCW;
+  const int wc = (wr & 1) ? (NCW - 1 - warp % NCW) : (warp % NCW);
+  const int row0 = wr * 8 * RBW;
   double* kscr = kscr_base + (size_t)blockIdx.x * BT * probs[0].Mp;     // per-CTA K-tile scratch (BT x Mp)
 
   __shared__ DevProblem sP;
@@ -995,7 +1001,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       // ---- S += A^T A
       double* Sd = P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp;
 #if FFVD_ABLATE != 2
-      syrk_flush<RB, NW>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
+      // unit size fixed at compile time (Mp = 16 NGW NCW): one SYRK variant per instantiation keeps the item loop's code small
+      syrk_units<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
 #endif
       FFVD_MARK(4);             // warp 0's own time: no barrier between the SYRK and the next contraction
     }
