@@ -1098,3 +1098,39 @@ def test_float32_tensor_mode(env):
         assert relerr(a, b.cpu().numpy().astype(np.float64)) <= 5e-7
     with pytest.raises(ValueError):
         ctx.sghmc_update(*[d.to(th.float16) for d in dev], 0.01, 0.05, 201.0, True)
+
+
+@pytest.mark.parametrize("collapsed,kind", ((False, 0), (True, 0), (False, 1), (True, 1)))
+def test_block_of_dims_work_items(env, collapsed, kind):
+    """The work-item form the large problems use (one item per (sample, tile, block of dims): x tile staged once, CTA
+    loops over the dims) is chosen by problem size; force it (FFVD_DL=1) on small problems, with blocks that do not divide D
+    (FFVD_DBLK=3, D=7), against the oracle -- both bounds, both kernels, and the conditional."""
+    import os
+    from oracle import fixtures, ffvd_oracle as O
+    old = {k: os.environ.get(k) for k in ("FFVD_DL", "FFVD_DBLK")}
+    try:
+        for dblk in ("3", "8"):
+            os.environ["FFVD_DL"] = "1"; os.environ["FFVD_DBLK"] = dblk
+            for (T, M, D, S) in ((150, 40, 7, 2), (70, 150, 5, 1)):
+                prob = fixtures.synthetic_problem(T=T, M=M, D=D, S=S, kind=kind, seed=3)
+                check(O.nll_and_grads(prob, collapsed=collapsed), run_cuda(env, prob, collapsed), what="dl dblk=%s T%d M%d D%d" % (dblk, T, M, D))
+        if kind == 0 and not collapsed:
+            import torch as th
+            from ffvd_b200 import conditionals_multi_output as cmo
+            from ffvd_b200.kernels_multi_output import SquaredExponential
+            prob = fixtures.synthetic_problem(T=90, M=50, D=7, S=1, seed=4)
+            Din = prob.Z.shape[1]
+            kerns = [SquaredExponential(Din, variance=np.exp(prob.logv[k]), lengthscales=np.exp(prob.logl[k]), ARD=True) for k in range(7)]
+            ok = O._make_kernels(th.as_tensor(prob.logv), th.as_tensor(prob.logl), 0, Din)
+            Xc = np.concatenate([prob.X[:-1], prob.ctrl], axis=1)
+            t = lambda a: th.as_tensor(np.ascontiguousarray(a), dtype=th.float64, device=env["dev"])
+            mu, var = cmo.conditional(t(Xc), t(prob.Z), kerns, t(prob.U), white=True)
+            rmu, rvar = O.conditional_multi_output(th.as_tensor(Xc), th.as_tensor(prob.Z), ok, th.as_tensor(prob.U), white=True)
+            assert_close(rmu.numpy(), mu.cpu().numpy(), TOL, "cond mean (dl)")
+            assert np.max(np.abs(rvar.numpy() - var.cpu().numpy())) <= TOL * float(np.max(np.exp(prob.logv)))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
