@@ -84,3 +84,38 @@ def test_create_dataset_and_case_table(tmp_path):
              Z_val=np.zeros((100, 5)))
     a = datasets.arguments_from_factnonlin(f)
     assert a["CC"].shape == (4, 1) and a["UU_ini"].shape == (100, 4) and a["x_initialization"].shape == (30, 4)
+
+
+def test_flag_and_status_constants_match_header():
+    """The Python constants are the header's (a drifted flag value would silently select another code path)."""
+    import os, re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ffvd_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(FFVD_[A-Z0-9_]+)\s+(-?\d+)\b", hdr)}
+    pairs = {"FFVD_FLAG_PRIOR_Z_NORMAL": _capi.FLAG_PRIOR_Z_NORMAL, "FFVD_FLAG_PRIOR_ONCE": _capi.FLAG_PRIOR_ONCE,
+             "FFVD_FLAG_NO_GRADS": _capi.FLAG_NO_GRADS, "FFVD_FLAG_ASYNC": _capi.FLAG_ASYNC,
+             "FFVD_FLAG_NO_SHARED_PRIORS": _capi.FLAG_NO_SHARED_PRIORS, "FFVD_FLAG_NO_X0_PRIOR": _capi.FLAG_NO_X0_PRIOR,
+             "FFVD_FLAG_REUSE_KZZ": _capi.FLAG_REUSE_KZZ, "FFVD_FLAG_COLLAPSED_P1_ONLY": _capi.FLAG_COLLAPSED_P1_ONLY,
+             "FFVD_FLAG_COLLAPSED_RESUME": _capi.FLAG_COLLAPSED_RESUME, "FFVD_FLAG_NO_REPLICATED": _capi.FLAG_NO_REPLICATED,
+             "FFVD_KERNEL_SE": _capi.KERNEL_SE, "FFVD_KERNEL_LINEAR": _capi.KERNEL_LINEAR}
+    for name, val in pairs.items():
+        assert defs[name] == val, name
+    flags = [v for k, v in defs.items() if k.startswith("FFVD_FLAG_")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)      # distinct single bits
+    assert defs["FFVD_E_STALE"] == -8
+
+
+def test_shared_noise_is_rank_independent_and_step_dependent():
+    a = distributed.shared_noise((3, 4), step=5, seed=2)
+    b = distributed.shared_noise((3, 4), step=5, seed=2)
+    c = distributed.shared_noise((3, 4), step=6, seed=2)
+    assert a.dtype.is_floating_point and a.shape == (3, 4)
+    assert bool((a == b).all()) and not bool((a == c).all())
+
+
+def test_oracle_loop_variable_sets_match_the_mirror():
+    """oracle/loop.py restates dgp_model.py:213-244 and the trainable flags independently of the product mirror."""
+    from oracle import loop
+    from ffvd_b200.datasets import CASE_TABLE
+    for case_val, (ko, uo, zo, uc, xpg) in CASE_TABLE.items():
+        assert loop.CASES[case_val] == (ko, uo, zo, uc)
+        assert loop.sampled_names(case_val) == sghmc_variable_names(_capi.KERNEL_SE, case_val, ko, True, uo, uc, zo)
