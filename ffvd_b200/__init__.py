@@ -8,8 +8,8 @@ CPU fallback.
 """
 from ._capi import (Context, FFVDError, NotPositiveDefinite, StaleFactorsError, KERNEL_SE, KERNEL_LINEAR, FLAG_PRIOR_Z_NORMAL,
                     FLAG_PRIOR_ONCE, FLAG_NO_GRADS, FLAG_ASYNC, FLAG_NO_SHARED_PRIORS, FLAG_NO_X0_PRIOR, FLAG_REUSE_KZZ, FLAG_COLLAPSED_P1_ONLY,
-                    FLAG_COLLAPSED_RESUME, FLAG_NO_REPLICATED, LIB_PATH, load_library)
+                    FLAG_COLLAPSED_RESUME, FLAG_NO_REPLICATED, FLAG_DETERMINISTIC, LIB_PATH, load_library)
 
 __all__ = ["Context", "FFVDError", "NotPositiveDefinite", "StaleFactorsError", "KERNEL_SE", "KERNEL_LINEAR", "FLAG_PRIOR_Z_NORMAL",
            "FLAG_PRIOR_ONCE", "FLAG_NO_GRADS", "FLAG_ASYNC", "FLAG_NO_SHARED_PRIORS", "FLAG_NO_X0_PRIOR", "FLAG_REUSE_KZZ", "FLAG_COLLAPSED_P1_ONLY", "FLAG_COLLAPSED_RESUME",
-           "FLAG_NO_REPLICATED", "LIB_PATH", "load_library"]
+           "FLAG_NO_REPLICATED", "FLAG_DETERMINISTIC", "LIB_PATH", "load_library"]

@@ -27,6 +27,7 @@ FLAG_ASYNC = 8
 FLAG_COLLAPSED_P1_ONLY = 128
 FLAG_COLLAPSED_RESUME = 256
 FLAG_NO_REPLICATED = 512
+FLAG_DETERMINISTIC = 1024
 
 _PROBLEM_FIELDS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR", "Y", "ctrl")
 _OUTPUT_FIELDS = ("nll", "terms", "g_X", "g_Z", "g_U", "g_logv", "g_logl", "g_logQ", "g_C", "g_d", "g_logR")

@@ -63,6 +63,8 @@ struct ffvd_ctx {
   std::vector<long long> kzz_key;
   size_t last_off_cvec = 0, last_off_HxT = 0;
   int last_Mp = 0, last_nb = 0;
+  char* det_buf = nullptr;         // FFVD_FLAG_DETERMINISTIC: private accumulator copies, x-bar planes, kzz_bwd partials (grow-only)
+  size_t det_cap = 0;
   bool force_blocked = false;      // keep the Cholesky factor L itself (blocked path): conditional(return_Lm=True)
   bool p1_pending = false;         // FFVD_FLAG_COLLAPSED_P1_ONLY left its statistics in the arena; FFVD_FLAG_COLLAPSED_RESUME consumes them
   std::vector<long long> p1_key;
@@ -136,6 +138,7 @@ extern "C" int ffvd_ctx_destroy(ffvd_ctx* c) {
   if (c->d_probs) cudaFree(c->d_probs);
   if (c->d_outs) cudaFree(c->d_outs);
   if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->det_buf) cudaFree(c->det_buf);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->comm) { if (const NcclApi* a = nccl_api(nullptr)) a->CommDestroy(c->comm); c->comm = nullptr; }
   if (c->pack_buf) cudaFree(c->pack_buf);
@@ -449,7 +452,7 @@ struct Layout {
   long long sumS;
   bool collapsed;
   size_t off_ZT, off_ZTs, off_hyp, off_hq, off_UT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
-      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, off_guard, total;
+      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, off_guard, off_collb, total;
   int nfac;                        // matrices in the blocked-factorisation pools: nprob * max(nk, nb)
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
   size_t small_per;                // doubles of small accumulators per problem
@@ -488,10 +491,11 @@ static Layout make_layout(const ffvd_ctx* c, int nprob, int nb, int nk, int D, i
   L.zero_begin = o;
   L.off_Sacc = take(need_acc ? (size_t)nprob * nb * mm : 0);
   L.off_ubar = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
-  L.small_per = (size_t)M * Din + (size_t)D * Din + D + D + D + (size_t)D * Dy + Dy + Dy;
+  L.small_per = (size_t)M * Din + (size_t)D * Din + D + D + (size_t)D * Dy + Dy + Dy;
   L.off_small = take((size_t)nprob * L.small_per * 8);
   L.off_terms = take((size_t)sumS * FFVD_NTERMS_RAW * 8);
   L.off_status = take((size_t)nprob * (nb > nk ? nb : nk) * sizeof(int));
+  L.off_collb = take((size_t)nprob * nb * 4 * 8);       // collapsed: per (s,d) scalar terms (plain stores; finalize sums them in order)
   L.off_status2 = take((size_t)L.nfac * sizeof(int));
   L.zero_end = o;
   L.total = o;
@@ -554,13 +558,13 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   P.gl = sm; sm += (size_t)L.D * L.Din;
   P.gv = sm; sm += L.D;
   P.gQ = sm; sm += L.D;
-  P.gQrep = sm; sm += L.D;
   P.gC = sm; sm += (size_t)L.D * L.Dy;
   P.gd = sm; sm += L.Dy;
   P.gR = sm;
   P.terms_raw = (double*)(a + L.off_terms) + (size_t)s_begin * FFVD_NTERMS_RAW;
   P.status = (int*)(a + L.off_status) + (size_t)p * (L.nb > L.nk ? L.nb : L.nk);
   P.guard = (unsigned long long*)(a + L.off_guard) + (size_t)p * 4;
+  P.collb = (double*)(a + L.off_collb) + (size_t)p * L.nb * 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -658,10 +662,11 @@ static int dblk_of(int Mp, int D) {
 // Work-item form (see fused_kernel): one item per (sample, tile, block of dblk dims) -- the CTA stages the x tile once and
 // loops over the dims -- when that still leaves >= 32 items per CTA of the persistent grid (tail <= 3%); one item per
 // (sample, tile, d) otherwise.  FFVD_DL=0/1 overrides (A/B timing).
-static void set_items(const ffvd_ctx* c, DevProblem& P, long long pairs_st /* S * ntiles */) {
+static void set_items(const ffvd_ctx* c, DevProblem& P, long long pairs_st /* S * ntiles */, bool force_loop = false) {
   const int nblk = (P.D + P.dblk - 1) / P.dblk;
   bool loop = P.dblk > 1 && pairs_st * nblk >= (long long)32 * c->num_sms;
   if (const char* e = getenv("FFVD_DL")) loop = atoi(e) != 0 && P.dblk > 1;
+  if (force_loop) loop = P.dblk > 1;        // deterministic mode: ONE item per (sample, tile) so that x-bar rows have one writer CTA
   P.dl = loop ? P.dblk : 1;
   P.nitems = loop ? pairs_st * nblk : pairs_st * P.D;
 }
@@ -862,6 +867,9 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   const int Mp = pad_M(M);
   if (Mp < 0) return fail(FFVD_E_LIMIT, "M > 2048 is not supported by this build");
   const bool no_grads = (flags & FFVD_FLAG_NO_GRADS) != 0;
+  const bool det = (flags & FFVD_FLAG_DETERMINISTIC) != 0;
+  if (det && c->capturing) return fail(FFVD_E_UNSUPPORTED, "FFVD_FLAG_DETERMINISTIC is not captured in CUDA graphs");
+  if (det && (flags & (FFVD_FLAG_COLLAPSED_P1_ONLY | FFVD_FLAG_COLLAPSED_RESUME))) return fail(FFVD_E_UNSUPPORTED, "FFVD_FLAG_DETERMINISTIC with a split collapsed evaluation is not built");
   const int nb = collapsed ? pt[0].S * D : D;
   Layout L = make_layout(c, nprob, nb, D, D, M, Mp, Din, Dy, sumS, collapsed != 0, true);
   TRY(ensure_arena(c, L));
@@ -881,9 +889,9 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     P.dvec = t.d.d; P.logR = t.logR.d; P.Y = t.Y.d; P.ctrl = t.ctrl.d;
     P.S = t.S; P.T = t.T; P.D = D; P.Din = Din; P.nc = t.nc; P.Dy = Dy; P.M = M; P.Mp = Mp; P.Dx = D; P.xrows = t.T + 1; P.hs = 1;
     P.ntiles = (t.T + BT - 1) / BT;
-    P.dblk = dblk_of(Mp, D);
+    P.dblk = det ? D : dblk_of(Mp, D);
     P.item_begin = item;
-    set_items(c, P, (long long)t.S * P.ntiles);
+    set_items(c, P, (long long)t.S * P.ntiles, det);
     item += P.nitems;
     bind_problem(c, L, p, s_begin, P);
     s_begin += t.S;
@@ -899,6 +907,48 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     O.g_logQ = t.glogQ.d; O.g_C = t.gC.d; O.g_d = t.gd.d; O.g_logR = t.glogR.d;
   }
   const long long total_items = item;
+  // ---- FFVD_FLAG_DETERMINISTIC: private accumulator copies (one per CTA for the S region, one per (CTA, warp) for u-bar / small
+  //      gradients / raw terms), three extra x-bar planes and the kzz_bwd partials; see det_ptr1 / det_ptr2 (ffvd_common.cuh)
+  const int det_copies = c->num_sms * kMaxCtasPerSm;
+  const size_t det_r1 = L.off_ubar - L.off_Sacc, det_r2 = L.off_status - L.off_ubar;
+  const int kzz_nblk = (M + 7) / 8;
+  size_t det_off2 = 0, det_offp = 0, det_offk = 0, det_total = 0, xtot = 0;
+  if (det) {
+    for (auto& t : pt) xtot += t.X.numel;
+    det_off2 = align_up((size_t)det_copies * det_r1, 256);
+    det_offp = align_up(det_off2 + (size_t)det_copies * FFVD_DET_MAX_WARPS * det_r2, 256);
+    det_offk = align_up(det_offp + 3 * xtot * 8, 256);
+    det_total = det_offk + (size_t)nprob * nb * ((size_t)M * Din + (size_t)kzz_nblk * (Din + 1)) * 8;
+    if (det_total > c->det_cap) {
+      if (c->det_buf) { CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaFree(c->det_buf)); c->det_buf = nullptr; c->det_cap = 0; }
+      CUDA_TRY(cudaMalloc((void**)&c->det_buf, det_total));
+      c->det_cap = det_total;
+    }
+    size_t xo = 0;
+    for (int p = 0; p < nprob; ++p) {
+      DevProblem& P = hp[p];
+      P.det1 = c->det_buf; P.det_base1 = c->arena + L.off_Sacc; P.det_stride1 = (long long)det_r1;
+      P.det2 = c->det_buf + det_off2; P.det_base2 = c->arena + L.off_ubar; P.det_stride2 = (long long)det_r2;
+      if (P.gX) { P.gXp = (double*)(c->det_buf + det_offp) + xo; P.gXp_stride = (long long)xtot; }
+      P.kzzpart = (double*)(c->det_buf + det_offk) + (size_t)p * nb * ((size_t)M * Din + (size_t)kzz_nblk * (Din + 1));
+      xo += pt[p].X.numel;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->det_buf + det_offp, 0, 3 * xtot * 8, c->stream));
+  }
+  auto det_zero = [&]() -> int {           // before every fused launch
+    if (!det) return FFVD_OK;
+    CUDA_TRY(cudaMemsetAsync(c->det_buf, 0, det_offp, c->stream));
+    return FFVD_OK;
+  };
+  auto det_reduce = [&]() -> int {         // after every fused launch: shared accumulators += the private copies, in index order
+    if (!det) return FFVD_OK;
+    det_reduce_kernel<<<grid1d(det_r1 / 8), 256, 0, c->stream>>>((double*)(c->arena + L.off_Sacc), c->det_buf, det_r1, det_r1 / 8, det_copies);
+    det_reduce_kernel<<<grid1d(det_r2 / 8), 256, 0, c->stream>>>((double*)(c->arena + L.off_ubar), c->det_buf + det_off2, det_r2, det_r2 / 8,
+                                                                 det_copies * FFVD_DET_MAX_WARPS);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return FFVD_OK;
+  };
   c->last_off_cvec = L.off_cvec; c->last_off_HxT = L.off_HxT; c->last_Mp = Mp; c->last_nb = nb;
   const bool p1_only = (flags & FFVD_FLAG_COLLAPSED_P1_ONLY) != 0, resume = (flags & FFVD_FLAG_COLLAPSED_RESUME) != 0;
   if ((p1_only || resume) && (!collapsed || no_grads || nprob != 1)) return fail(FFVD_E_BADARG, "COLLAPSED_P1_ONLY / COLLAPSED_RESUME need one collapsed problem with gradients");
@@ -945,14 +995,20 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   const dim3 gsym((unsigned)((size_t)M * M + 255) / 256, nb, nprob);
 
   if (no_grads && !collapsed) {
+    TRY(det_zero());
     TRY((launch_fused<KIND, MODE_FORWARD>(c, Mp, Din, c->d_probs, nprob, total_items)));
+    TRY(det_reduce());
   } else if (!collapsed) {
     if (!ltu_done) { ltu_kernel<<<dim3(D, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
+    TRY(det_zero());
     TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, Din, c->d_probs, nprob, total_items)));
+    TRY(det_reduce());
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 0); c->launches++;
   } else {
     if (!resume) {
+      TRY(det_zero());
       TRY((launch_fused<KIND, MODE_COLLAPSED_P1>(c, Mp, Din, c->d_probs, nprob, total_items)));
+      TRY(det_reduce());
       symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 1); c->launches++;
     }
     if (p1_only) {
@@ -982,7 +1038,9 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       collapsed_vec_kernel<<<dim3(nb, nprob), 1024, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
       TRY(launch_bgemm(c, Hx, Wk, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Mat' L^{-1}
       TRY(launch_bgemm(c, Nmat, LinvT, Hx, Mp, 1.0, nz, idm, lmap, idm));     // N = L^{-T} Mat' L^{-1}
+      TRY(det_zero());
       TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, Din, c->d_probs, nprob, total_items)));
+      TRY(det_reduce());
       TRY(launch_bgemm(c, HxT, Wk, Sacc, Mp, 1.0, nz, idm, idm, idm));        // Mat' S
       symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 2); c->launches++;   // Sacc <- Gs
     } else {
@@ -1002,6 +1060,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       kzz_bwd_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
     } else {
       kzz_bwd_fused_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;
+      if (det) { kzz_bwd_reduce_kernel<<<nprob, 256, 0, c->stream>>>(c->d_probs, nb, (int)grow.x); c->launches++; }
     }
   }
   {

@@ -25,7 +25,7 @@
                                // DMMA fragment reads (row q, column g) and the per-row reads conflict free per half-warp
 #define FFVD_XCOLS 32          // padded column count of X~ = [x, ctrl, 1, 0...]
 #define FFVD_MAX_DIN 31
-#define FFVD_ZTS_ROWS 41         // rows of the scaled Z~^T copy: 0..Din-1 z/l, zeros up to 39 (branch-free padded steps), row 40 = -|z~|^2/2
+#define FFVD_ZTS_ROWS 41         // rows of the scaled, augmented Z~^T copy: 0..Din-1 z/l, row Din = 1, row Din+1 = -|z~|^2/2, zeros (k-steps of 4)
 #define FFVD_NTERMS_RAW 8      // raw per-sample sums, see below
 
 // raw per-sample term slots (sums of J pieces, before the -1/T scaling)
@@ -42,7 +42,7 @@ struct DevProblem {
   // derived inputs (written by kzz_prep)
   double *ZT;          // [32][Mp]    Z~^T: transposed, zero padded inducing inputs, then a row of ones (m < M), zeros
   double *Zf;          // [Mp/4][4][32] the same matrix in DMMA B-fragment order: entry ((m>>2)*4 + (jd>>3))*32 + (jd&7)*4 + (m&3)
-  double *ZTs;         // [nk][FFVD_ZTS_ROWS][Mp] SE: per-kernel scaled copy z~ = z/l (rows 0..Din-1), zero rows, row 40 = -1/2 |z~_m|^2
+  double *ZTs;         // [nk][FFVD_ZTS_ROWS][Mp] SE: per-kernel scaled copy z~ = z/l (rows 0..Din-1), row Din = 1, row Din+1 = -1/2 |z~_m|^2, zero rows
   double *hyp;         // [nk][72]   per kernel: 1/l^2 [0..31], 1/l [32..63], v [64]           (hyper_kernel)
   double *hq;          // [D][4]     per output dim: Q, 1/Q, log Q                              (hyper_kernel)
   double *UT;          // [D][Mp]    U transposed, zero padded (coalesced staging of u_d)       (hyper_kernel)
@@ -56,7 +56,6 @@ struct DevProblem {
   double *gl;          // [D][Din]    raw dJ/dlogl
   double *gv;          // [D]
   double *gQ;          // [D]
-  double *gQrep;       // [D]   collapsed: the part of dJ/dlogQ that depends on H = F^T F / Q + I as a whole (replicated under time sharding)
   double *gC;          // [D][Dy]
   double *gd;          // [Dy]
   double *gR;          // [Dy]   (row 0 of logR)
@@ -68,6 +67,14 @@ struct DevProblem {
   double *Nmat;        // [D][Mp][Mp]  N = L^{-T} Mat' L^{-1}
   double *Hx, *HxT;    // [S*D][Mp][Mp] collapsed scratch: L_H^{-1}, L_H^{-T} / Mat' S
   double *rs;          // [nb][Mp] row sums of Wz
+  // FFVD_FLAG_DETERMINISTIC (all null / zero otherwise): private accumulator copies and x-bar planes, see det_ptr1 / det_ptr2
+  char *det1, *det_base1;      // per-CTA copies of the S region [det_base1, +det_stride1): element p lives at det1 + cta*stride + (p - base)
+  char *det2, *det_base2;      // per-(CTA, warp) copies of the small-accumulator region (u-bar, small gradients, raw terms)
+  long long det_stride1, det_stride2;
+  double *gXp;                 // [3][S][T+1][D] x-bar planes: +-e / +-gx terms, emission, LinearK diagonal term (the W back-propagation
+  long long gXp_stride;        //   goes to g_X itself); summed in a fixed order by finalize_kernel
+  double *kzzpart;             // kzz_bwd_fused partials (deterministic mode): per batch entry [M][Din] | [blocks][Din] | [blocks]
+  double *collb;               // [nb][4] collapsed: per (s,d) -1/2 logdet H, quadratic term, H-part of dJ/dlogQ (plain stores, summed by finalize)
   int *status;         // [D] 0 ok, else 1-based failing pivot
   unsigned long long *guard;   // [4] content guard of the cached K(Z,Z) factors (FFVD_FLAG_REUSE_KZZ): running hash of
                                //     Z / logv / logl, hash at factorisation time, block counter, stale flag (hyper_kernel)
@@ -99,7 +106,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // rounded (64 doubles, staged in shared memory by the caller), exp(r) - 1 = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)
 // (truncation r^6/720 <= 3.5e-17 relative).  11 FP64 operations per value against 19 for the degree-13 polynomial this
 // replaces (the K tile is FP64-pipe work that competes with the DMMAs); <= 1.5 ulp on [-745, 0] (tests: ffvd_debug_exp).
-// The argument is clamped at -745 first: the low word of t must hold the integer, and without the clamp an argument
+// The argument is clamped at -745 (high word: -745.99) first: the low word of t must hold the integer, and without the clamp an argument
 // below ~-2e7 (|x/l - z/l| > 6e3, e.g. a diverging chain on logl) would wrap it and return a huge / Inf / NaN kernel
 // value instead of 0.  Below -708 the scale saturates at 2^-1022 (result ~ 1e-308, i.e. 0 at the scale of every quantity
 // the kernels form).
@@ -121,20 +128,30 @@ static __device__ const double g_exp2_tab[64] = {
   0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
   0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
+// tab may be pre-scaled by a positive factor v (the fused kernels stage v_d * 2^(j/64) per output dim, which saves the
+// multiplication by the kernel variance); nmin then bounds the exponent shift from below so that the exponent field of
+// v * 2^(j/64) * (1 + ...) cannot wrap: nmin = -1022 - min(ilogb(v), 0)  (exp_nmin).
+__device__ __forceinline__ int exp_nmin(double v) {
+  const int e = ((__double2hiint(v) >> 20) & 0x7ff) - 1023;
+  return e < -500 ? 0 : -1022 - min(e, 0);      // v < 2^-500: the caller stages a zero table, and n = 0 keeps the zeros
+}
 template <int N>
-__device__ __forceinline__ void exp_nonpos_n(double (&x)[N], const double* __restrict__ tab /* shared-memory copy of g_exp2_tab */) {
+__device__ __forceinline__ void exp_nonpos_n(double (&x)[N], const double* __restrict__ tab /* shared-memory copy of g_exp2_tab */,
+                                             int nmin = -1022) {
   double r[N], q[N], tj[N];
   int n[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    x[i] = fmax(x[i], -745.0);
+    // x = max(x, -745.99...) on the high word: for negative doubles a larger magnitude is a larger unsigned high word (one
+    // integer min instead of an FP64 compare and two selects; NaN saturates like a very negative argument, as fmax did)
+    x[i] = __hiloint2double((int)min((unsigned)__double2hiint(x[i]), 0xC0874800u), __double2loint(x[i]));
     const double t = fma(x[i], 92.33248261689366, 6755399441055744.0);     // 64 / ln 2, 1.5 * 2^52
     const int k = __double2loint(t);                                        // round(x * 64 / ln 2), two's complement
     const double kd = t - 6755399441055744.0;
     r[i] = fma(kd, -0x1.62e42fec00000p-7, x[i]);                            // ln2/64 head (30 bits: kd * head is exact)
     r[i] = fma(kd, -0x1.d1cf79abc9e3bp-38, r[i]);                           // ln2/64 tail
     tj[i] = tab[k & 63];
-    n[i] = max(k >> 6, -1022);
+    n[i] = max(k >> 6, nmin);
     q[i] = fma(r[i], 1.0 / 120.0, 1.0 / 24.0);
   }
 #pragma unroll
@@ -180,6 +197,20 @@ __device__ __forceinline__ void ldg256_nc(const double* p, double2& lo, double2&
 }
 __device__ __forceinline__ void ldg256_cg(const double* p, double& a, double& b, double& c, double& d) {
   asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(__cvta_generic_to_global(p)));
+}
+
+// FFVD_FLAG_DETERMINISTIC: where an accumulator element lives for this CTA / warp.
+// FP64 REDs from different CTAs (and from different warps of one CTA) land in an order that changes from run to run, so the
+// shared sums differ in their last bits.  In deterministic mode every CTA adds into its OWN copy of the S region and every
+// (CTA, warp) into its own copy of the small accumulators -- each element then has a single writer thread, whose REDs to one
+// address apply in program order -- and det_reduce_kernel sums the copies in a fixed order.  Off: the shared accumulator itself.
+#define FFVD_DET_MAX_WARPS 16
+__device__ __forceinline__ double* det_ptr1(const DevProblem& P, double* p) {
+  return P.det1 ? reinterpret_cast<double*>(P.det1 + (size_t)blockIdx.x * P.det_stride1 + (reinterpret_cast<char*>(p) - P.det_base1)) : p;
+}
+__device__ __forceinline__ double* det_ptr2(const DevProblem& P, double* p) {
+  return P.det2 ? reinterpret_cast<double*>(P.det2 + ((size_t)blockIdx.x * FFVD_DET_MAX_WARPS + (threadIdx.x >> 5)) * P.det_stride2 +
+                                            (reinterpret_cast<char*>(p) - P.det_base2)) : p;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -68,96 +68,101 @@ struct Smem {
 // ---------------------------------------------------------------------------------------------
 // K tile: k(x_r, z_j) for this warp's rows [row0, row0 + 8 RB) and column groups, written to the shared tile (and,
 // when SCR, to the CTA's L2 scratch copy that W = Kbar o K reads back).  Rows >= nvalid are NOT masked here (the
-// caller zeroes them in the rare partial tile); columns >= M get exact zeros through the per-column factor.
+// caller zeroes them in the rare partial tile); columns >= M are set to exact zeros.
 // SE follows the reference's expansion (kernels_multi_output.py:163-182): -r^2/2 = x~.z~ - |x~|^2/2 - |z~|^2/2 with
-// x~ = x/l (sm.xsc, sm.xn2h) and z~ = z/l (ZTd rows 0..Din-1, row Din = -|z~|^2/2, written by hyper_kernel): one FMA per
-// (element, input dim); exp through the branch-free, lock-step exp_nonpos_n.  Linear: ZTd = Z~^T unscaled.
-// The ZTd rows stream from L2 through a 4- or 8-slot register ring (that many input dims ahead); the first rows of the next column
-// group are requested before the exp / store work of the current one.
-template <int KIND, int RB, int NGW, bool SCR, int NCW>
-__device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __restrict__ ZTd, int Mp, int Din, double v,
-                                               int wc, int g, int q, int M, int row0, int lda, double* __restrict__ kscr) {
+// x~ = x/l and z~ = z/l, formed as ONE product of augmented operands on the tensor pipe,
+//     [x~, -|x~|^2/2, 1, 0..] (sm.xsc, BT x 4 KS)  times  [z~; 1; -|z~|^2/2; 0..] (ZTd, 4 KS x Mp, written by hyper_kernel),
+// KS = ceil((Din + 2) / 4) DMMA k-steps.  As scalar FMAs (one per element and input dim, the first version) the phase was
+// issue bound: 3.8k instructions per warp and tile at Din = 9, 2.4x the FP64-pipe time; a DMMA does the work of 8 DFMA
+// warp-instructions in the same pipe time.  The two DMMAs of a 16-column group take the even / the odd columns as their
+// B fragments (one 16-byte load per lane and k-step), so lane (g, q) ends up with row g, columns 4 q .. 4 q + 3 -- the
+// layout of every other tile phase (see gemm_segment).  exp through the branch-free, lock-step exp_nonpos_n with the table pre-scaled by v_d.
+// Linear: ZTd = Z~^T unscaled, KS = ceil(Din / 4), A columns >= Din masked (column Din of xs holds the ones).
+// KS > 0: k-steps unrolled and the B fragments of the NEXT column group requested before the work of the current one
+// (4 KS registers); KS == 0: any Din, k loop rolled, fragments loaded where they are used.
+template <int KIND, int RB, int NGW, bool SCR, int NCW, int KS>
+__device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __restrict__ ZTd, int Mp, int Din, double v, int nmin,
+                                               int ks_rt, int wc, int g, int q, int M, int row0, int lda,
+                                               double* __restrict__ kscr) {
   // The tile of a warp (8 RB rows x 16 NGW columns) is formed in passes of RBB row blocks x one 16-column group: 4 RBB
-  // accumulators per lane.  The pass loop is NOT unrolled: fully unrolled this phase was 38 KB of code (2.4k instructions
-  // for RB = 8, NGW = 2), and the whole item loop (218 KB) then misses the instruction cache on every item (ncu: 16% of
-  // the phase's stall samples were no-instruction).
+  // accumulators per lane.  The pass loop is NOT unrolled (instruction-cache footprint of the item loop).
   constexpr int RBB = RB >= 4 ? 4 : RB;
   constexpr int NPASS = RB / RBB;
-  // The ZTd rows of a pass stream from L2 through an 8-slot register ring, 8 input dims ahead.  SE: the scaled copy has
-  // zero rows after the Din real ones (and x~ has zero columns there), so the steps run in half-trips of 4 with no
-  // per-step branch; the loop leaves after the half-trip that covers Din.  Linear reads Z~^T itself (row Din is the ones
-  // row) and guards every step.
-  double2 ring[8][2], hz[2];
-  auto prologue = [&](int jb) {
+  constexpr int KSA = KS > 0 ? KS : 1;
+  const double* zq = ZTd + (size_t)q * Mp + 2 * g;
+  const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + g) * FFVD_XLD + q;
+  double bc[KSA][2], bn[KSA][2];
+  auto load_b = [&](double (&b)[KSA][2], int jg) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      ring[u][0] = ring[u][1] = make_double2(0.0, 0.0);
-      if (KIND == 0 ? (u < 4 || Din > 4) : (u < Din)) ldg256_nc(ZTd + (size_t)u * Mp + jb, ring[u][0], ring[u][1]);
+    for (int ks = 0; ks < KSA; ++ks) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(zq + (size_t)(4 * ks) * Mp + jg));
+      b[ks][0] = t.x; b[ks][1] = t.y;
     }
-    if (KIND == 0) ldg256_nc(ZTd + (size_t)(FFVD_ZTS_ROWS - 1) * Mp + jb, hz[0], hz[1]);
   };
-  prologue(16 * group_index<NCW>(wc, 0) + 4 * q);
+  if (KS > 0) load_b(bc, 16 * group_index<NCW>(wc, 0));
 #pragma unroll 1
-  for (int pass = 0; pass < NGW * NPASS; ++pass) {
-    const int ng = pass / NPASS, rbase = (pass % NPASS) * RBB;
-    const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
-    const double* xsrc = ((KIND == 0) ? sm.xsc : sm.xs) + (row0 + 8 * rbase + g) * FFVD_XLD;
-    double s[RBB][4];
-    {
-      const double h[4] = {hz[0].x, hz[0].y, hz[1].x, hz[1].y};
+  for (int ng = 0; ng < NGW; ++ng) {
+    const int jg = 16 * group_index<NCW>(wc, ng);
+    const int jb = jg + 4 * q;
+    if (KS > 0 && ng + 1 < NGW) load_b(bn, 16 * group_index<NCW>(wc, ng + 1));
+#pragma unroll 1
+    for (int ps = 0; ps < NPASS; ++ps) {
+      const int rbase = ps * RBB;
+      const double* xa = xsrc + 8 * rbase * FFVD_XLD;
+      double kv[RBB * 4];
 #pragma unroll
-      for (int rb = 0; rb < RBB; ++rb) {
-        const double hx = (KIND == 0) ? sm.xn2h[row0 + 8 * (rbase + rb) + g] : 0.0;
+      for (int i = 0; i < RBB * 4; ++i) kv[i] = 0.0;
+      if (FFVD_ABLATE != 6) {
+        if (KS > 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s[rb][c] = (KIND == 0) ? hx + h[c] : 0.0;
-      }
-    }
-    for (int j0 = 0; j0 < (FFVD_ABLATE == 6 ? 0 : Din); j0 += 8) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1 && j0 + 4 >= Din) break;          // uniform
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-          const int u = 4 * half + uu, jd = j0 + u;
-          if (KIND == 0 || jd < Din) {
-            const double z[4] = {ring[u][0].x, ring[u][0].y, ring[u][1].x, ring[u][1].y};
-            if (KIND == 0) {
-              if (j0 + 8 + 4 * half < Din) ldg256_nc(ZTd + (size_t)(jd + 8) * Mp + jb, ring[u][0], ring[u][1]);   // uniform per half-trip
-            } else if (jd + 8 < Din) {
-              ldg256_nc(ZTd + (size_t)(jd + 8) * Mp + jb, ring[u][0], ring[u][1]);
-            }
+          for (int ks = 0; ks < KSA; ++ks) {
 #pragma unroll
             for (int rb = 0; rb < RBB; ++rb) {
-              const double x = xsrc[8 * rb * FFVD_XLD + jd];
+              double a = xa[8 * rb * FFVD_XLD + 4 * ks];
+              if (KIND == 1 && 4 * ks + 3 >= Din) a = (4 * ks + q < Din) ? a : 0.0;
+              dmma884(kv[4 * rb], kv[4 * rb + 2], a, bc[ks][0]);
+              dmma884(kv[4 * rb + 1], kv[4 * rb + 3], a, bc[ks][1]);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int ks = 0; ks < ks_rt; ++ks) {
+            const double2 b2 = __ldg(reinterpret_cast<const double2*>(zq + (size_t)(4 * ks) * Mp + jg));
 #pragma unroll
-              for (int c = 0; c < 4; ++c) s[rb][c] = fma(x, z[c], s[rb][c]);
+            for (int rb = 0; rb < RBB; ++rb) {
+              double a = xa[8 * rb * FFVD_XLD + 4 * ks];
+              if (KIND == 1) a = (4 * ks + q < Din) ? a : 0.0;
+              dmma884(kv[4 * rb], kv[4 * rb + 2], a, b2.x);
+              dmma884(kv[4 * rb + 1], kv[4 * rb + 3], a, b2.y);
             }
           }
         }
       }
-    }
-    // the first rows of the next pass are requested before the exp / store work of this one
-    if (pass + 1 < NGW * NPASS) prologue(16 * group_index<NCW>(wc, (pass + 1) / NPASS) + 4 * q);
-    double vc[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) vc[c] = (jb + c < M) ? v : 0.0;
-    double kv[RBB * 4];
-#pragma unroll
-    for (int i = 0; i < RBB; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) kv[4 * i + c] = s[i][c];
 #if FFVD_ABLATE != 5
-    if (KIND == 0) exp_nonpos_n<RBB * 4>(kv, sm.exptab);
+      if (KIND == 0) exp_nonpos_n<RBB * 4>(kv, sm.exptab, nmin);
 #endif
+      if (KIND == 1) {
 #pragma unroll
-    for (int i = 0; i < RBB; ++i) {
-      const int row = row0 + 8 * (rbase + i) + g;
+        for (int i = 0; i < RBB * 4; ++i) kv[i] *= v;
+      }
+      if (jg + 16 > M) {               // the group that holds the padded columns (warp uniform): exact zeros there
 #pragma unroll
-      for (int c = 0; c < 4; ++c) kv[4 * i + c] *= vc[c];
-      double* p = sm.tile + row * lda + jb;
-      FFVD_ASSERT(row >= 0 && row < 8 * RB * (FFVD_TILE_ROWS_FACTOR) && jb >= 0 && jb + 4 <= Mp && jb + 4 <= lda);
-      st_tile4(p, g, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
-      if (SCR && FFVD_ABLATE != 4) stg256(kscr + (size_t)row * Mp + jb, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
+        for (int i = 0; i < RBB; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) kv[4 * i + c] = (jb + c < M) ? kv[4 * i + c] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < RBB; ++i) {
+        const int row = row0 + 8 * (rbase + i) + g;
+        double* p = sm.tile + row * lda + jb;
+        FFVD_ASSERT(row >= 0 && row < 8 * RB * (FFVD_TILE_ROWS_FACTOR) && jb >= 0 && jb + 4 <= Mp && jb + 4 <= lda);
+        st_tile4(p, g, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
+        if (SCR && FFVD_ABLATE != 4) stg256(kscr + (size_t)row * Mp + jb, kv[4 * i], kv[4 * i + 1], kv[4 * i + 2], kv[4 * i + 3]);
+      }
+    }
+    if (KS > 0) {
+#pragma unroll
+      for (int ks = 0; ks < KSA; ++ks) { bc[ks][0] = bn[ks][0]; bc[ks][1] = bn[ks][1]; }
     }
   }
 }
@@ -394,7 +399,8 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 #endif
                                            ) {
   const int g = lane >> 2, q = lane & 3;
-  const int Din = P.Din, M = P.M, Mp = P.Mp, D = P.D;
+  const int Din = P.Din, M = P.M, D = P.D;
+  constexpr int Mp = 16 * NGW * (NW < 8 ? NW : 8);      // compile-time width (see fused_kernel)
   constexpr int nbx = NBM;                      // n-blocks covering Din+1 columns
   constexpr int BT = 8 * RB;
   const double* tile = sm.tile;
@@ -467,7 +473,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
                   zb = v * c[u][nb][e];
                 }
                 FFVD_ASSERT(m < M && jd < Din);
-                red_add(P.gZ + (size_t)m * Din + jd, zb);
+                red_add(det_ptr2(P, P.gZ + (size_t)m * Din + jd), zb);
               }
             }
           }
@@ -485,7 +491,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           x += __shfl_xor_sync(0xffffffffu, x, 8);
           x += __shfl_xor_sync(0xffffffffu, x, 16);
           const int jd = 8 * nb + 2 * q + e;
-          if (g == 0 && nb < nbx && jd < Din) red_add(P.gl + (size_t)d * Din + jd, x);
+          if (g == 0 && nb < nbx && jd < Din) red_add(det_ptr2(P, P.gl + (size_t)d * Din + jd), x);
         }
     }
   }
@@ -577,9 +583,9 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
         if (lane < D) red_add(gXs + (size_t)(t0 + r) * D + lane, xb);
       }
     }
-    if (KIND == 0 && lane < Din) red_add(P.gl + (size_t)d * Din + lane, lsum);
+    if (KIND == 0 && lane < Din) red_add(det_ptr2(P, P.gl + (size_t)d * Din + lane), lsum);
     vacc = warp_sum(vacc);
-    if (lane == 0) red_add(P.gv + d, vacc);
+    if (lane == 0) red_add(det_ptr2(P, P.gv + d), vacc);
   }
 }
 
@@ -609,11 +615,6 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 
   __shared__ DevProblem sP;
   int cur_pi = -1;
-  if (KIND == 0 && tid < 64) {      // exp table (read after the first CTA barrier of the item loop)
-    const int Mp0 = probs[0].Mp, Din0 = probs[0].Din;
-    double* tab = smem_raw + fused_smem_bytes(RB, Mp0, NW, (Din0 + 1 + 7) >> 3) / sizeof(double) - 64;
-    tab[tid] = g_exp2_tab[tid];
-  }
 #ifdef FFVD_PHASE_TIMING
   long long _phase_last = clock64();
 #endif
@@ -675,14 +676,23 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         s = (int)(st / P.ntiles);
       }
     }
-    const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, Mp = P.Mp, nc = P.nc;
-    const int lda = Mp + 4;
+    const int T = P.T, D = P.D, Dx = P.Dx, Din = P.Din, M = P.M, nc = P.nc;
+    // The padded width is a property of the instantiation (the host launches the template that matches P.Mp): as compile-time
+    // constants Mp and the tile stride fold into the immediate offsets of the shared / global accesses -- with a run-time
+    // stride every fragment address of the contraction loops was an IMAD of its own (ncu: 0.7 IMAD per DMMA).
+    constexpr int Mp = 16 * NGW * NCW;
+    constexpr int lda = Mp + 4;
     FFVD_ASSERT(li >= 0 && li < P.nitems && d0 >= 0 && nd >= 1 && d0 + nd <= P.D && tile_i >= 0 && tile_i < P.ntiles && s >= 0 && s < P.S);
-    FFVD_ASSERT(Mp == 16 * NGW * NCW);
+    FFVD_ASSERT(P.Mp == Mp);
     const int t0 = tile_i * BT;
     const int nvalid = min(BT, T - t0);
     const double* Xs = P.X + (size_t)s * P.xrows * Dx;
     double* gXs = (MODE == MODE_COND || MODE == MODE_FORWARD) ? nullptr : P.gX + (size_t)s * (T + 1) * D;
+    // deterministic mode: the three other classes of x-bar contributions go to their own planes, so that every element of
+    // every plane has at most two contributing threads (a two-term sum is order independent); finalize adds the planes
+    double* gXb = (gXs && P.gXp) ? P.gXp + (size_t)s * (T + 1) * D : gXs;                        // +-e (uncollapsed) / +-gx (collapsed pass 2)
+    double* gXe = (gXs && P.gXp) ? P.gXp + P.gXp_stride + (size_t)s * (T + 1) * D : gXs;         // emission
+    double* gXl = (gXs && P.gXp) ? P.gXp + 2 * P.gXp_stride + (size_t)s * (T + 1) * D : gXs;     // LinearK: -v/Q x_t
 
     Smem sm;
     {
@@ -738,6 +748,11 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (tid < 32) { hv0 = __ldg(hyp + tid); hv1 = __ldg(hyp + 32 + tid); }
     if (tid == 40) scv = __ldg(hyp + 64);
     if (tid >= 41 && tid < 44) scv = __ldg(P.hq + (size_t)d * 4 + (tid - 41));
+    double tabv = 0.0;                 // SE: the exp table pre-scaled by v_d (threads 64..127)
+    if (KIND == 0 && tid >= 64 && tid < 128) {
+      const double vv = __ldg(hyp + 64);
+      tabv = (exp_nmin(vv) == 0 && vv < 1.0) ? 0.0 : vv * g_exp2_tab[tid - 64];
+    }
     __syncthreads();   // x tile staged (di == 0) / previous d fully done with shared memory (di > 0)
     if (tid < 64) {
       if (tid < 32) { sm.small[tid] = hv0; sm.small[32 + tid] = hv1; }
@@ -745,12 +760,17 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       if (tid == 40) sm.sc[0] = scv;
       if (tid >= 41 && tid < 44) sm.sc[tid - 40] = scv;
     }
+    if (KIND == 0 && tid >= 64 && tid < 128) sm.exptab[tid - 64] = tabv;
     if (KIND == 0) {
-      // x~ = x / l (same rounded products in xsc and in -1/2 |x~|^2)
+      // x~ = x / l (same rounded products in xsc and in -1/2 |x~|^2); columns Din, Din + 1 hold the augmentation
+      // [-1/2 |x~|^2, 1] of the K-tile product (written below), the columns after them zeros
       for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
         const int r = idx >> 5;                         // column == lane
-        sm.xsc[r * FFVD_XLD + lane] = sm.xs[r * FFVD_XLD + lane] * silc;
+        if (lane != Din && lane != Din + 1) sm.xsc[r * FFVD_XLD + lane] = sm.xs[r * FFVD_XLD + lane] * silc;
       }
+      if (Din + 2 > FFVD_XCOLS)
+        for (int idx = tid; idx < BT * 4; idx += NTH)
+          if (32 + (idx & 3) > Din + 1) sm.xsc[(idx >> 2) * FFVD_XLD + 32 + (idx & 3)] = 0.0;
       // -1/2 |x~_r|^2: a quarter-warp per row (8 lanes x 4 columns), rows dealt to the warps
       for (int r = (tid >> 3); r < BT; r += NTH / 8) {
         const int l8 = tid & 7;
@@ -764,7 +784,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (l8 == 0) sm.xn2h[r] = -0.5 * a;
+        if (l8 == 0) {
+          sm.xsc[r * FFVD_XLD + Din] = -0.5 * a;
+          sm.xsc[r * FFVD_XLD + Din + 1] = 1.0;
+        }
       }
     }
     for (int j = tid; j < Mp; j += NTH) {
@@ -780,8 +803,18 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     FFVD_MARK(0);
 
     // ---- P1: K tile -> shared (SE uncollapsed: also to this CTA's L2-resident scratch, needed again for W = Kbar o K)
-    compute_k_tile<KIND, RBW, NGW, (KIND == 0 && MODE == MODE_UNCOLLAPSED), NCW>(
-        sm, (KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT, Mp, Din, v, wc, g, q, M, row0, lda, kscr);
+    {
+      const double* ZTd = (KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT;
+      const int ksn = (KIND == 0) ? (Din + 2 + 3) >> 2 : (Din + 3) >> 2;      // DMMA k-steps of the (augmented) product
+      const int nmin = (KIND == 0) ? exp_nmin(v) : 0;
+      constexpr bool SCR = (KIND == 0 && MODE == MODE_UNCOLLAPSED);
+      switch (ksn) {
+        case 2: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 2>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
+        case 3: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 3>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
+        case 5: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 5>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
+        default: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 0>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
+      }
+    }
     if (nvalid < BT) {
       // partial last tile of a sample: rows >= nvalid must be inert (exact zeros)
       __syncthreads();
@@ -886,13 +919,13 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
               gq = 0.5 * res * res * invQ - 0.5 + 0.5 * sig2 * invQ;
               if (MODE == MODE_UNCOLLAPSED) {
                 FFVD_ASSERT(t0 + r + 1 <= T && d < D);
-                red_add(gXs + (size_t)(t0 + r) * D + d, e);
-                red_add(gXs + (size_t)(t0 + r + 1) * D + d, -e);
+                red_add(gXb + (size_t)(t0 + r) * D + d, e);              // (element [t][d] gets exactly two terms: +e_t, -e_{t-1})
+                red_add(gXb + (size_t)(t0 + r + 1) * D + d, -e);
               }
             }
             gvd = -0.5 * kdiag * invQ;
             if (KIND == 1 && MODE == MODE_UNCOLLAPSED) {
-              for (int c = 0; c < D; ++c) red_add(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
+              for (int c = 0; c < D; ++c) red_add(gXl + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
             }
           }
           sm.es[r] = e;
@@ -919,20 +952,20 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             dy = res / Ry;
             rr = res * res - 1.0;
             if (MODE != MODE_FORWARD)
-              for (int c = 0; c < D; ++c) red_add(gXs + (size_t)(t0 + r + 1) * D + c, dy * P.C[(size_t)c * Dy + y]);
+              for (int c = 0; c < D; ++c) red_add(gXe + (size_t)(t0 + r + 1) * D + c, dy * P.C[(size_t)c * Dy + y]);
           }
           if (MODE != MODE_FORWARD) {
             for (int c = 0; c < D; ++c) {
               const double xc1 = (r < nvalid) ? sm.xs[(r + 1) * FFVD_XLD + c] : 0.0;
               const double t = warp_sum(dy * xc1);
-              if (lane == 0) red_add(P.gC + (size_t)c * Dy + y, t);
+              if (lane == 0) red_add(det_ptr2(P, P.gC + (size_t)c * Dy + y), t);
             }
             const double sd = warp_sum(dy), sr = warp_sum(rr);
-            if (lane == 0) { red_add(P.gd + y, sd); red_add(P.gR + y, sr); }
+            if (lane == 0) { red_add(det_ptr2(P, P.gd + y), sd); red_add(det_ptr2(P, P.gR + y), sr); }
           }
         }
         ll = warp_sum(ll);
-        if (lane == 0) red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS, ll);
+        if (lane == 0) red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS), ll);
       }
       __syncthreads();          // A tile + es[] visible
       FFVD_MARK(3);
@@ -971,8 +1004,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_FORWARD || MODE == MODE_COND) {
       // forward only: flush the scalar sums and move on
       if (MODE == MODE_FORWARD && tid == 0) {
-        red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0] + sm.red[4]);
-        red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1] + sm.red[5]);
+        red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ), sm.red[0] + sm.red[4]);
+        red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE), sm.red[1] + sm.red[5]);
       }
       continue;
     }
@@ -994,12 +1027,12 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             t += __shfl_xor_sync(0xffffffffu, t, 4);
             t += __shfl_xor_sync(0xffffffffu, t, 8);
             t += __shfl_xor_sync(0xffffffffu, t, 16);
-            if (g == 0 && jb + c < M) red_add(P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp + jb + c, t);
+            if (g == 0 && jb + c < M) red_add(det_ptr2(P, P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp + jb + c), t);
           }
         }
       }
       // ---- S += A^T A
-      double* Sd = P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp;
+      double* Sd = det_ptr1(P, P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp);
 #if FFVD_ABLATE != 2
       // unit size fixed at compile time (Mp = 16 NGW NCW): one SYRK variant per instantiation keeps the item loop's code small
       syrk_units<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
@@ -1044,10 +1077,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             if (r < nvalid) {
               delta = sm.xs[(r + 1) * FFVD_XLD + d] - sm.xs[r * FFVD_XLD + d];
               const double gx = t - delta * invQ;
-              red_add(gXs + (size_t)(t0 + r + 1) * D + d, gx);
-              red_add(gXs + (size_t)(t0 + r) * D + d, -gx);
+              red_add(gXb + (size_t)(t0 + r + 1) * D + d, gx);
+              red_add(gXb + (size_t)(t0 + r) * D + d, -gx);
               if (KIND == 1)
-                for (int c = 0; c < D; ++c) red_add(gXs + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
+                for (int c = 0; c < D; ++c) red_add(gXl + (size_t)(t0 + r) * D + c, -v * invQ * sm.xs[r * FFVD_XLD + c]);
             }
             sm.es[r] = delta;
           }
@@ -1124,11 +1157,11 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (tid < 32) {
       if (tid == 0) {
         if (MODE != MODE_COLLAPSED_P2) {
-          red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, sm.red[0] + sm.red[4]);
-          red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, sm.red[1] + sm.red[5]);
-          red_add(P.gQ + d, sm.red[2] + sm.red[6]);
+          red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ), sm.red[0] + sm.red[4]);
+          red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE), sm.red[1] + sm.red[5]);
+          red_add(det_ptr2(P, P.gQ + d), sm.red[2] + sm.red[6]);
         }
-        if (MODE != MODE_COLLAPSED_P1) red_add(P.gv + d, (sm.red[3] + sm.red[7]) + (sm.red[8] + sm.red[9]));
+        if (MODE != MODE_COLLAPSED_P1) red_add(det_ptr2(P, P.gv + d), (sm.red[3] + sm.red[7]) + (sm.red[8] + sm.red[9]));
       }
     }
   }   // d loop

@@ -615,7 +615,8 @@ __global__ void __launch_bounds__(256) collapsed_logdet_kernel(const DevProblem*
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int w = 0; w < 8; ++w) tot += red[w];
-    red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -tot);
+    P.collb[(size_t)b * 4 + 0] = -tot;          // per (s,d), summed over d in a fixed order by finalize_kernel (no RED: repeatable)
+    (void)s;
   }
 }
 
@@ -757,10 +758,14 @@ __global__ void __launch_bounds__(256) wz_kernel(const DevProblem* __restrict__ 
 // A warp per row m of Kbar_zz (in Sacc, left untouched): lanes take n = lane, lane + 32, ...; per n the row Z[n][:] is
 // loaded once and used both for the kernel value and for the weighted sums  wzz[jd] = sum_n Wz[m][n] Z[n][jd].
 // grid (ceil(M/8), batch, nprob); block 256.  hyp (1/l, 1/l^2, v) comes from hyper_kernel.
+// Deterministic mode (P.kzzpart != null): the three kinds of contributions are STORED per batch entry -- Z-bar rows [M][Din], the
+// per-block dJ/dlogl [blocks][Din] and dJ/dlogv [blocks] partials -- and kzz_bwd_reduce_kernel adds them in a fixed order.
 template <int KIND>
 __global__ void __launch_bounds__(256) kzz_bwd_fused_kernel(const DevProblem* __restrict__ probs) {
   const DevProblem& P = probs[blockIdx.z];
   const int b = blockIdx.y, d = b % P.D;
+  const int nblk_ = gridDim.x;
+  double* part = P.kzzpart ? P.kzzpart + (size_t)b * ((size_t)P.M * P.Din + (size_t)nblk_ * (P.Din + 1)) : nullptr;
   const int M = P.M, Mp = P.Mp, Din = P.Din;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m = blockIdx.x * 8 + warp;
@@ -814,7 +819,8 @@ __global__ void __launch_bounds__(256) kzz_bwd_fused_kernel(const DevProblem* __
         zb = 2.0 * v * wzz;
         vpart = 0.5 * zmine * zb;
       }
-      red_add(P.gZ + (size_t)m * Din + lane, zb);
+      if (part) part[(size_t)m * Din + lane] = zb;
+      else red_add(P.gZ + (size_t)m * Din + lane, zb);
     }
   }
   if (KIND == 0) {
@@ -827,11 +833,59 @@ __global__ void __launch_bounds__(256) kzz_bwd_fused_kernel(const DevProblem* __
       double t = 0.0;
 #pragma unroll
       for (int r = 0; r < 8; ++r) t += lsm[r][lane];
-      red_add(P.gl + (size_t)d * Din + lane, t);
+      if (part) part[(size_t)M * Din + (size_t)blockIdx.x * Din + lane] = t;
+      else red_add(P.gl + (size_t)d * Din + lane, t);
     }
   }
   vpart = warp_sum(vpart);
-  if (lane == 0 && vpart != 0.0) red_add(P.gv + d, vpart);
+  if (part) {
+    // the eight row values of the block, summed in warp order
+    __shared__ double vsm[8];
+    if (lane == 0) vsm[warp] = vpart;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int r = 0; r < 8; ++r) t += vsm[r];
+      part[(size_t)M * Din + (size_t)nblk_ * Din + blockIdx.x] = t;
+    }
+  } else if (lane == 0 && vpart != 0.0) {
+    red_add(P.gv + d, vpart);
+  }
+}
+
+// Deterministic mode: gZ / gl / gv += the stored contributions of kzz_bwd_fused_kernel, batch entries and blocks in index order.
+// grid (nprob); block 256.
+__global__ void __launch_bounds__(256) kzz_bwd_reduce_kernel(const DevProblem* __restrict__ probs, int nb, int nblk) {
+  const DevProblem& P = probs[blockIdx.x];
+  const int M = P.M, Din = P.Din, D = P.D;
+  const size_t per = (size_t)M * Din + (size_t)nblk * (Din + 1);
+  for (int i = threadIdx.x; i < M * Din; i += blockDim.x) {
+    double t = P.gZ[i];
+    for (int b = 0; b < nb; ++b) t += P.kzzpart[(size_t)b * per + i];
+    P.gZ[i] = t;
+  }
+  for (int i = threadIdx.x; i < D * Din; i += blockDim.x) {
+    const int d = i / Din, jd = i % Din;
+    double t = P.gl[i];
+    for (int b = d; b < nb; b += D)
+      for (int k = 0; k < nblk; ++k) t += P.kzzpart[(size_t)b * per + (size_t)M * Din + (size_t)k * Din + jd];
+    P.gl[i] = t;
+  }
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double t = P.gv[d];
+    for (int b = d; b < nb; b += D)
+      for (int k = 0; k < nblk; ++k) t += P.kzzpart[(size_t)b * per + (size_t)M * Din + (size_t)nblk * Din + k];
+    P.gv[d] = t;
+  }
+}
+
+// Deterministic mode: dst[i] += sum over the private copies c = 0 .. ncopies-1 of priv[c][i], in index order.
+__global__ void det_reduce_kernel(double* __restrict__ dst, const char* __restrict__ priv, size_t stride_bytes, size_t n, int ncopies) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double t = dst[i];
+    for (int c = 0; c < ncopies; ++c) t += reinterpret_cast<const double*>(priv + (size_t)c * stride_bytes)[i];
+    dst[i] = t;
+  }
 }
 
 // dJ/dZ, dJ/dlogl, dJ/dlogv contributions of Kbar_zz.  grid (ceil(M/8), batch, nprob); block (32, 8).
@@ -921,7 +975,8 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
     double t = 0.0;
     for (int i = tid; i < M; i += 32) t += log(H[(size_t)i * ldh + i]);
     t = warp_sum(t);
-    if (tid == 0) red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_LOGDET, -t);
+    if (tid == 0) P.collb[(size_t)b * 4 + 0] = -t;      // per (s,d); finalize_kernel sums over d in a fixed order
+    (void)s;
   }
   double* X = P.Hx + (size_t)b * Mp * Mp;
   double* XT = P.HxT + (size_t)b * Mp * Mp;
@@ -937,8 +992,8 @@ __global__ void __launch_bounds__(512) collapsed_chol_kernel(const DevProblem* _
 // Per-evaluation scalars the tile kernel would otherwise re-derive (with FP64 exp calls) in every work item:
 // hyp[k] = {1/l_j^2, 1/l_j, v} per kernel, hq[d] = {Q, 1/Q, log Q} per output dim, UT = U^T zero padded.
 // grid (max(nk, D), nprob); block 128.
-// zs != 0 (SE only): also the per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded, 40 rows) and, in
-// row 40, -1/2 |z~_m|^2 -- the column half of the reference's expansion of the scaled squared distance
+// zs != 0 (SE only): also the per-kernel scaled inducing inputs z~ = z / l_d (transposed, zero padded), a row of ones and, in
+// row Din+1, -1/2 |z~_m|^2 -- the column half of the reference's expansion of the scaled squared distance
 // (kernels_multi_output.py:163-182).  Skipped when the factors of the previous call are reused (Z, l unchanged).
 // guard != 0: content guard of FFVD_FLAG_REUSE_KZZ.  Every block adds the (order-independent) hash of its slice of Z, logv,
 // logl to P.guard[0]; the last block to finish either records it as the hash the factors were built from (guard == 1) or
@@ -972,15 +1027,18 @@ __global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int
   __syncthreads();
   if (zs && k < nk) {
     double* out = P.ZTs + (size_t)k * FFVD_ZTS_ROWS * Mp;
+    // rows 0..Din-1: z~; row Din: ones; row Din+1: -1/2 |z~|^2; zero rows up to the next multiple of four and beyond.  The
+    // tile kernel forms -r^2/2 = [x~, -1/2|x~|^2, 1] . [z~; 1; -1/2|z~|^2] as ONE tensor-pipe product over these rows.
     for (int m = t; m < Mp; m += blockDim.x) {
       double a = 0.0;
-      for (int jd = 0; jd < FFVD_ZTS_ROWS - 1; ++jd) {
-        double z = 0.0;
-        if (m < M && jd < Din) z = P.Z[(size_t)m * Din + jd] * sils[jd];
-        out[(size_t)jd * Mp + m] = z;                      // rows Din..39 stay zero: the tile kernel's padded steps read them
+      for (int jd = 0; jd < Din; ++jd) {
+        const double z = (m < M) ? P.Z[(size_t)m * Din + jd] * sils[jd] : 0.0;
+        out[(size_t)jd * Mp + m] = z;
         a = fma(z, z, a);
       }
-      out[(size_t)(FFVD_ZTS_ROWS - 1) * Mp + m] = -0.5 * a;
+      out[(size_t)Din * Mp + m] = 1.0;
+      out[(size_t)(Din + 1) * Mp + m] = -0.5 * a;
+      for (int jd = Din + 2; jd < FFVD_ZTS_ROWS; ++jd) out[(size_t)jd * Mp + m] = 0.0;
     }
   }
   if (k < D) {
@@ -1116,12 +1174,16 @@ __global__ void __launch_bounds__(1024) collapsed_vec_kernel(const DevProblem* _
   }
   for (int m = M + tid; m < Mp; m += nth) w[m] = 0.0;
   qd = warp_sum(qd); tr = warp_sum(tr); csc = warp_sum(csc);
-  if (lane == 0) { atomicAdd(red + 0, qd); atomicAdd(red + 1, tr); atomicAdd(red + 2, csc); }
+  __shared__ double wred[32][3];
+  if (lane == 0) { wred[warp][0] = qd; wred[warp][1] = tr; wred[warp][2] = csc; }
   __syncthreads();
   if (tid == 0) {
-    red_add(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_QUAD, 0.5 * red[0]);
-    red_add(P.gQrep + d, 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq);
+    for (int w = 0; w < nw; ++w) { red[0] += wred[w][0]; red[1] += wred[w][1]; red[2] += wred[w][2]; }     // fixed order
+    // per (s,d) values, summed over d (terms) / over s (dJ/dlogQ) in a fixed order by finalize_kernel
+    P.collb[(size_t)b * 4 + 1] = 0.5 * red[0];
+    P.collb[(size_t)b * 4 + 2] = 0.5 * ((double)M - red[1]) - red[0] + 0.5 * red[2] * iq;
   }
+  (void)s;
   // Mat' in place: four rows per warp in flight (loads of all four first, then the stores)
   for (int m0 = 4 * warp; m0 < M; m0 += 4 * nw)
     for (int n = lane; n < M; n += 32) {
@@ -1154,6 +1216,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
     for (size_t i = (size_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < n; i += (size_t)gx_blocks * blockDim.x) {
       const size_t r = i % per;
       double v = P.gX[i];
+      if (P.gXp) v = ((v + P.gXp[i]) + P.gXp[P.gXp_stride + i]) + P.gXp[2 * P.gXp_stride + i];      // deterministic mode: the x-bar planes
       if (r < (size_t)P.D && !(flags & 32)) v -= P.X[i];
       P.gX[i] = scx * v;
     }
@@ -1223,8 +1286,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
       t[1] = sc * r[FFVD_RAW_EMIS];
       t[2] = sc * r[FFVD_RAW_XQ];
       t[3] = sc * r[FFVD_RAW_TRACE];
-      t[4] = (collapsed && replicated) ? sc * r[FFVD_RAW_LOGDET] : 0.0;
-      t[5] = (collapsed && replicated) ? sc * r[FFVD_RAW_QUAD] : 0.0;
+      double ld = 0.0, qd = 0.0;
+      if (collapsed && replicated)
+        for (int dd = 0; dd < D; ++dd) { ld += P.collb[((size_t)s * D + dd) * 4 + 0]; qd += P.collb[((size_t)s * D + dd) * 4 + 1]; }
+      t[4] = sc * ld;
+      t[5] = sc * qd;
       if (stale) {                  // FFVD_FLAG_REUSE_KZZ with a Z / hyper-parameter content that the cached factors were not built from
 #pragma unroll
         for (int k = 0; k < 6; ++k) t[k] = __longlong_as_double(0x7ff8000000000000ll);
@@ -1241,7 +1307,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(const DevProblem* __restr
   }
   if (O.g_logv) for (int i = tid; i < D; i += nth) O.g_logv[i] = sc * (P.gv[i] - npri * (P.logv[i] - log005));
   if (KIND == 0 && O.g_logl) for (int i = tid; i < D * Din; i += nth) O.g_logl[i] = sc * (P.gl[i] - npri * P.logl[i]);
-  if (O.g_logQ) for (int i = tid; i < D; i += nth) O.g_logQ[i] = sc * (P.gQ[i] + ((collapsed && replicated) ? P.gQrep[i] : 0.0) - npri * P.logQ[i]);
+  if (O.g_logQ) for (int i = tid; i < D; i += nth) {
+    double rep = 0.0;
+    if (collapsed && replicated)
+      for (int ss = 0; ss < S; ++ss) rep += P.collb[((size_t)ss * D + i) * 4 + 2];        // H-dependent part, samples in index order
+    O.g_logQ[i] = sc * ((P.gQ[i] + rep) - npri * P.logQ[i]);
+  }
   if (O.g_C) for (int i = tid; i < D * Dy; i += nth) O.g_C[i] = sc * (P.gC[i] - npri * P.C[i]);
   if (O.g_d) for (int i = tid; i < Dy; i += nth) O.g_d[i] = sc * (P.gd[i] - npri * P.dvec[i]);
   if (O.g_logR) for (int i = tid; i < Dy * Dy; i += nth) O.g_logR[i] = sc * ((i < Dy ? P.gR[i] : 0.0) - npri * P.logR[i]);

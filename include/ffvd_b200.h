@@ -85,6 +85,15 @@ typedef struct DLManagedTensor {
 #define FFVD_FLAG_COLLAPSED_RESUME  256
 #define FFVD_FLAG_NO_REPLICATED     512
 
+/* Bitwise-repeatable results.  By default the shared sums (S = sum a a^T, u-bar, Z-bar, hyper-parameter gradients, x-bar
+ * rows that several work items touch) are accumulated with FP64 REDs whose arrival order changes from run to run, so results
+ * agree only to ~1e-12.  With this flag every accumulator element has ONE writer thread per private copy (a copy of the S
+ * region per CTA, of the small accumulators per (CTA, warp), separate x-bar planes per kind of contribution, stored partials in
+ * the Kzz backward) and the copies are summed in index order: two evaluations of the same inputs on the same device are
+ * bit-identical.  Costs memory (C3: +2.7 GB) and a few percent of time; not capturable in CUDA graphs; the split collapsed
+ * evaluation (P1_ONLY / RESUME) is not covered. */
+#define FFVD_FLAG_DETERMINISTIC 1024
+
 typedef struct ffvd_ctx ffvd_ctx;
 
 /* One GPSSM problem (SURVEY section 8 batch-axis contract).  Shapes:

@@ -1134,3 +1134,48 @@ def test_block_of_dims_work_items(env, collapsed, kind):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+@pytest.mark.parametrize("collapsed,kind,M", ((False, 0, 100), (True, 0, 100), (False, 1, 60), (True, 0, 200), (False, 0, 300)))
+def test_deterministic_flag_is_bitwise_repeatable(env, collapsed, kind, M):
+    """FFVD_FLAG_DETERMINISTIC (two-level reduction option): private accumulator copies summed in index order.
+    Two evaluations of the same inputs are bit-identical in every output, the result agrees with the default (RED-ordered)
+    path to rounding and with the oracle to the parity tolerance.  Enough work items that every CTA of the grid contributes."""
+    from oracle import fixtures, ffvd_oracle as O
+    F = env["ffvd"]
+    prob = fixtures.synthetic_problem(T=3000, M=M, D=4, S=3, kind=kind, seed=11 + M)
+    base = F.FLAG_PRIOR_Z_NORMAL
+    a = run_cuda(env, prob, collapsed, flags=base | F.FLAG_DETERMINISTIC)
+    plain = run_cuda(env, prob, collapsed, flags=base)
+    b = run_cuda(env, prob, collapsed, flags=base | F.FLAG_DETERMINISTIC)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), (k, float(np.max(np.abs(a[k] - b[k]))))
+        assert relerr(plain[k], a[k]) <= 1e-10, k      # RED order of the default path (LinearK: cancellation)
+    check(O.nll_and_grads(prob, collapsed=collapsed), a, what="deterministic M%d" % M)
+    # forward-only evaluation under the flag
+    f1 = run_cuda(env, prob, collapsed, flags=base | F.FLAG_DETERMINISTIC | F.FLAG_NO_GRADS)
+    f2 = run_cuda(env, prob, collapsed, flags=base | F.FLAG_DETERMINISTIC | F.FLAG_NO_GRADS)
+    assert np.array_equal(f1["nll"], f2["nll"]) and relerr(a["nll"], f1["nll"]) <= 1e-12
+
+
+def test_deterministic_flag_batched_chains_and_refusals(env):
+    """The flag on a batched call (ragged T), and what it refuses: graph capture and the split collapsed evaluation."""
+    import torch
+    from oracle import fixtures
+    F = env["ffvd"]
+    probs = [fixtures.synthetic_problem(T=T, M=48, D=3, S=1, seed=T) for T in (700, 1500, 333)]
+    ps = [dev_problem(env, p) for p in probs]
+    res = []
+    for _ in range(2):
+        outs = [alloc_out(env, p) for p in ps]
+        env["ctx"].nll_grads_batched(0, False, ps, outs, flags=F.FLAG_PRIOR_Z_NORMAL | F.FLAG_DETERMINISTIC)
+        torch.cuda.synchronize()
+        res.append([{k: v.cpu().numpy() for k, v in o.items()} for o in outs])
+    for r0, r1, p in zip(res[0], res[1], probs):
+        single = run_cuda(env, p, False)
+        for k in r0:
+            assert np.array_equal(r0[k], r1[k]), k
+            assert relerr(single[k].reshape(r0[k].shape), r0[k]) <= 1e-11, k
+    p = ps[0]
+    with pytest.raises(F.FFVDError):
+        env["ctx"].nll_grads(0, True, p, alloc_out(env, p), flags=F.FLAG_DETERMINISTIC | F.FLAG_COLLAPSED_P1_ONLY)
