@@ -186,6 +186,17 @@ __device__ __forceinline__ double2 ldg_stream2(const double* p) {
   return v;
 }
 
+__device__ __forceinline__ double2 ldg_stream2_v(const double* p) {     // same, pinned in program order (early prologue requests)
+  unsigned long long pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l1(const double* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
+}
+
 // 32-byte (256-bit) global accesses, sm_100a LDG/STG.E.256: one lane moves four consecutive doubles, so the four lanes
 // that own a 16-column group of a tile row write / read one full 128-byte line (two 16-byte accesses per lane leave every
 // 32-byte sector half written per instruction).  Addresses must be 32-byte aligned.

@@ -68,7 +68,9 @@ struct Smem {
 // ---------------------------------------------------------------------------------------------
 // K tile: k(x_r, z_j) for this warp's rows [row0, row0 + 8 RB) and column groups, written to the shared tile (and,
 // when SCR, to the CTA's L2 scratch copy that W = Kbar o K reads back).  Rows >= nvalid are NOT masked here (the
-// caller zeroes them in the rare partial tile); columns >= M are set to exact zeros.
+// caller zeroes them in the rare partial tile).  Columns >= M: Linear gets exact zeros (zero columns of Z~^T); SE gets
+// v * exp(-745) ~ 1e-308 (hyper_kernel puts -1e4 into their -|z~|^2/2 slot), which every consumer multiplies by an exact
+// zero (the padded rows / columns of L^{-1}, L^{-T}, N, u, w) -- no per-element mask in the tile loop.
 // SE follows the reference's expansion (kernels_multi_output.py:163-182): -r^2/2 = x~.z~ - |x~|^2/2 - |z~|^2/2 with
 // x~ = x/l and z~ = z/l, formed as ONE product of augmented operands on the tensor pipe,
 //     [x~, -|x~|^2/2, 1, 0..] (sm.xsc, BT x 4 KS)  times  [z~; 1; -|z~|^2/2; 0..] (ZTd, 4 KS x Mp, written by hyper_kernel),
@@ -144,12 +146,6 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
       if (KIND == 1) {
 #pragma unroll
         for (int i = 0; i < RBB * 4; ++i) kv[i] *= v;
-      }
-      if (jg + 16 > M) {               // the group that holds the padded columns (warp uniform): exact zeros there
-#pragma unroll
-        for (int i = 0; i < RBB; ++i)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) kv[4 * i + c] = (jb + c < M) ? kv[4 * i + c] : 0.0;
       }
 #pragma unroll
       for (int i = 0; i < RBB; ++i) {
@@ -235,8 +231,32 @@ __device__ __forceinline__ void gemm_segments(double (&acc)[NG][RB][4], double2 
   }
 }
 
+// Prologue of a contraction: the B fragments of the first three k-steps of the first segment.  Split from tile_gemm_chunk so
+// that the caller can issue it EARLY (before the CTA barrier / the SYRK in front of the contraction): the operands come from
+// L2 (~800 clk), and with all warps starting a contraction together nothing else hides that round trip.  volatile: the
+// requests must stay where they are written (a plain asm load may be sunk to its first use).
+template <int NGW, int TRI, int NCW>
+__device__ __forceinline__ void tile_gemm_prologue(double2 (&ring)[4][NGW], const double* __restrict__ B, int Mp, int warp, int ng0,
+                                                   int g, int q) {
+  int joff[NGW];
+#pragma unroll
+  for (int ng = 0; ng < NGW; ++ng) joff[ng] = 16 * group_index<NCW>(warp, ng0 + ng);
+  const double* bq = B + (size_t)q * Mp + 2 * g;
+  const int kfirst = (TRI < 0) ? joff[0] : 0;
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+#pragma unroll
+    for (int ng = 0; ng < NGW; ++ng) {
+      ring[u][ng] = make_double2(0.0, 0.0);
+      const bool active = (TRI < 0) ? (ng == 0) : true;    // TRI < 0 starts with group 0 alone; else every group is live at k = 0
+      if (active) ring[u][ng] = ldg_stream2_v(bq + (size_t)(kfirst + 4 * u) * Mp + joff[ng]);
+    }
+#pragma unroll
+  for (int ng = 0; ng < NGW; ++ng) ring[3][ng] = make_double2(0.0, 0.0);
+}
+
 template <int RB, int NGW, int TRI, int NCW, class AOp>
-__device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const double* tile, int lda,
+__device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], double2 (&ring)[4][NGW], const double* tile, int lda,
                                                 const double* __restrict__ B, int Mp, int warp, int ng0, int g, int q, AOp aop) {
   int joff[NGW];
 #pragma unroll
@@ -249,19 +269,6 @@ __device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const
   }
   const double* bq = B + (size_t)q * Mp + 2 * g;
   const double* aq = tile + g * lda + q;
-  double2 ring[4][NGW];
-  // prologue: the first three k-steps of the first segment
-  const int kfirst = (TRI < 0) ? joff[0] : 0;
-#pragma unroll
-  for (int u = 0; u < 3; ++u)
-#pragma unroll
-    for (int ng = 0; ng < NGW; ++ng) {
-      ring[u][ng] = make_double2(0.0, 0.0);
-      const bool active = (TRI < 0) ? (ng == 0) : true;    // TRI < 0 starts with group 0 alone; else every group is live at k = 0
-      if (active) ring[u][ng] = ldg_stream2(bq + (size_t)(kfirst + 4 * u) * Mp + joff[ng]);
-    }
-#pragma unroll
-  for (int ng = 0; ng < NGW; ++ng) ring[3][ng] = make_double2(0.0, 0.0);
   if constexpr (TRI == 0) {
     gemm_segment<RB, NGW, 0, NGW, 0>(acc, ring, aq, lda, bq, Mp, joff, 0, Mp, aop, q);
   } else {
@@ -271,17 +278,25 @@ __device__ __forceinline__ void tile_gemm_chunk(double (&acc)[NGW][RB][4], const
 
 // Column groups are processed at most 4 at a time so that the B-fragment prefetch ring and the running
 // pointers stay in registers for large M (NGW up to 16); the A fragments are re-read from shared memory per chunk.
+// ring0: the prologue of the FIRST chunk, issued by the caller (tile_gemm_prologue<tile_gemm_ch0<NGW>(), TRI, NCW>(ring0, B, Mp, warp, 0, g, q)).
+template <int NGW>
+__host__ __device__ constexpr int tile_gemm_ch0() { return NGW <= 4 ? NGW : ((NGW % 4 == 0) ? 4 : 2); }
+
 template <int RB, int NGW, int TRI, int NCW, class AOp>
-__device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], const double* tile, int lda,
+__device__ __forceinline__ void tile_gemm(double (&acc)[NGW][RB][4], double2 (&ring0)[4][tile_gemm_ch0<NGW>()], const double* tile, int lda,
                                           const double* __restrict__ B, int Mp, int warp, int g, int q, AOp aop) {
   if constexpr (NGW <= 4) {
-    tile_gemm_chunk<RB, NGW, TRI, NCW>(acc, tile, lda, B, Mp, warp, 0, g, q, aop);
+    tile_gemm_chunk<RB, NGW, TRI, NCW>(acc, ring0, tile, lda, B, Mp, warp, 0, g, q, aop);
   } else {
     static_assert(NGW % 2 == 0, "large NGW must be even");
-    constexpr int CH = (NGW % 4 == 0) ? 4 : 2;
+    constexpr int CH = tile_gemm_ch0<NGW>();
+    tile_gemm_chunk<RB, CH, TRI, NCW>(reinterpret_cast<double(&)[CH][RB][4]>(acc[0]), ring0, tile, lda, B, Mp, warp, 0, g, q, aop);
 #pragma unroll
-    for (int c0 = 0; c0 < NGW; c0 += CH)
-      tile_gemm_chunk<RB, CH, TRI, NCW>(reinterpret_cast<double(&)[CH][RB][4]>(acc[c0]), tile, lda, B, Mp, warp, c0, g, q, aop);
+    for (int c0 = CH; c0 < NGW; c0 += CH) {
+      double2 ring[4][CH];
+      tile_gemm_prologue<CH, TRI, NCW>(ring, B, Mp, warp, c0, g, q);
+      tile_gemm_chunk<RB, CH, TRI, NCW>(reinterpret_cast<double(&)[CH][RB][4]>(acc[c0]), ring, tile, lda, B, Mp, warp, c0, g, q, aop);
+    }
   }
 }
 
@@ -379,6 +394,121 @@ __device__ __forceinline__ void syrk_units(const double* tile, int lda, int Mp, 
       const int t = u - nfull;
       syrk_tile<RB, true, NB>(tile, lda, Mp, S, stage_w, 8 * NB * t, 8 * NB * t, lane);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Software-pipelined SYRK (FFVD_SYRK_PIPE): the flush of unit u (transposition through the staging buffer + REDs) is issued
+// in eight slots inside the k loop of unit u + 1, so the warp keeps issuing DMMAs while the results of the previous unit
+// drain.  During a flush executed on its own a warp issues no DMMA and its sub-partition partner alone reaches only ~85% of
+// the issue rate (ncu: the flush regions are 3% of the kernel's warp samples).  Two staging buffers per warp (block rows
+// alternate), so a block row's stores and its loads two k-steps later are separated by exactly one __syncwarp.
+template <int NB>
+struct SyrkPending {
+  double c[NB][NB][2];
+  int m0, n0;
+  bool diag, valid;
+};
+
+// one flush slot: slot = 2 i     -> store block row i of the pending unit into staging buffer (i & 1)
+//                 slot = 2 i + 1 -> load it back transposed and RED it into S
+template <int NB>
+__device__ __forceinline__ void syrk_flush_slot(const SyrkPending<NB>& pd, int slot, int Mp, double* __restrict__ S, double* stage_w,
+                                                int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int i = slot >> 1;
+  double* st = stage_w + (i & 1) * (8 * 40);
+  if ((slot & 1) == 0) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      *reinterpret_cast<double2*>(st + g * 40 + 8 * j + 2 * q) = make_double2(pd.c[i][j][0], pd.c[i][j][1]);
+    __syncwarp();
+  } else {
+    const int ncol = pd.diag ? 8 * (i + 1) : 8 * NB;
+    if (lane < ncol) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        FFVD_ASSERT(pd.m0 + 8 * i + r < Mp && pd.n0 + lane < Mp && pd.n0 <= pd.m0);
+        red_add(S + (size_t)(pd.m0 + 8 * i + r) * Mp + pd.n0 + lane, st[r * 40 + lane]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int RB, bool DIAG, int NB>
+__device__ __forceinline__ void syrk_tile_pipe(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
+                                               int m0, int n0, int lane, SyrkPending<NB>& pd) {
+  const int g = lane >> 2, q = lane & 3;
+  double c[NB][NB][2];
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  constexpr int KSTEPS = 2 * RB;                       // k-steps of 4 rows
+  constexpr int NSLOT = 2 * NB;                        // flush slots of the pending unit
+  constexpr int EVERY = KSTEPS >= NSLOT ? KSTEPS / NSLOT : 1;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    double a[NB], b[NB];
+    const double* row = tile + (4 * ks + q) * lda + g;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) a[i] = row[m0 + 8 * i];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) b[j] = DIAG ? a[j] : row[n0 + 8 * j];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (!DIAG || j <= i) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    if (KSTEPS >= NSLOT) {
+      if (ks % EVERY == EVERY - 1 && ks / EVERY < NSLOT && pd.valid) syrk_flush_slot<NB>(pd, ks / EVERY, Mp, S, stage_w, lane);
+    }
+  }
+  if (KSTEPS < NSLOT && pd.valid) {
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) syrk_flush_slot<NB>(pd, sl, Mp, S, stage_w, lane);
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) { pd.c[i][j][0] = c[i][j][0]; pd.c[i][j][1] = c[i][j][1]; }
+  pd.m0 = m0; pd.n0 = n0; pd.diag = DIAG; pd.valid = true;
+}
+
+template <int RB, int NW, int NB>
+__device__ __forceinline__ void syrk_units_pipe(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
+                                                int warp, int lane) {
+  const int nt = Mp / (8 * NB);
+  const int nfull = nt * (nt - 1) / 2, nunits = nfull + nt;
+  // units of this warp: i = 0 .. nu-1 with u(i) = i NW + (i odd ? NW-1-warp : warp) < nunits  (snake order, see syrk_units)
+  const int full = nunits / NW, rem = nunits % NW;
+  const int nu = full + ((((full & 1) ? (NW - 1 - warp) : warp) < rem) ? 1 : 0);
+  const bool rev = NW >= 8 && (warp & 4) != 0;
+  SyrkPending<NB> pd;
+  pd.valid = false; pd.diag = false; pd.m0 = pd.n0 = 0;
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) pd.c[i][j][0] = pd.c[i][j][1] = 0.0;
+#pragma unroll 1
+  for (int ii = 0; ii < nu; ++ii) {
+    const int i = rev ? nu - 1 - ii : ii;
+    const int u = i * NW + ((i & 1) ? (NW - 1 - warp) : warp);
+    if (u < nfull) {
+      int ti = (int)((sqrtf(8.0f * (float)u + 1.0f) + 1.0f) * 0.5f);
+      ti -= (ti * (ti - 1) / 2 > u) ? 1 : 0;
+      ti += ((ti + 1) * ti / 2 <= u) ? 1 : 0;
+      const int tj = u - ti * (ti - 1) / 2;
+      syrk_tile_pipe<RB, false, NB>(tile, lda, Mp, S, stage_w, 8 * NB * ti, 8 * NB * tj, lane, pd);
+    } else {
+      const int t = u - nfull;
+      syrk_tile_pipe<RB, true, NB>(tile, lda, Mp, S, stage_w, 8 * NB * t, 8 * NB * t, lane, pd);
+    }
+  }
+  if (pd.valid) {
+#pragma unroll
+    for (int sl = 0; sl < 2 * NB; ++sl) syrk_flush_slot<NB>(pd, sl, Mp, S, stage_w, lane);
   }
 }
 
@@ -748,12 +878,34 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (tid < 32) { hv0 = __ldg(hyp + tid); hv1 = __ldg(hyp + 32 + tid); }
     if (tid == 40) scv = __ldg(hyp + 64);
     if (tid >= 41 && tid < 44) scv = __ldg(P.hq + (size_t)d * 4 + (tid - 41));
+    {
+      // first operand fragments of the K-tile product (group 0 of this warp): pulled into L1 while the barriers and the
+      // per-d staging below run (compute_k_tile requests the later groups one group ahead itself)
+      const double* zp = ((KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT) + (size_t)q * Mp + 2 * g + 16 * group_index<NCW>(wc, 0);
+      const int ksn = (KIND == 0) ? (Din + 2 + 3) >> 2 : (Din + 3) >> 2;
+      for (int ks = 0; ks < ksn; ++ks) prefetch_l1(zp + (size_t)(4 * ks) * Mp);
+    }
+    // u_d / w_d (Mp entries each): requested here, stored after the barrier
+    constexpr int NUS = (Mp + NTH - 1) / NTH;
+    double usv[NUS], wsv[NUS];
+#pragma unroll
+    for (int i = 0; i < NUS; ++i) {
+      const int j = tid + i * NTH;
+      usv[i] = wsv[i] = 0.0;
+      if (j < Mp) {
+        if (MODE == MODE_UNCOLLAPSED || MODE == MODE_FORWARD || MODE == MODE_COND) usv[i] = __ldg(P.UT + (size_t)d * Mp + j);
+        else if (MODE == MODE_COLLAPSED_P2) usv[i] = (j < M) ? __ldg(P.wvec + ((size_t)s * D + d) * Mp + j) : 0.0;
+        if (MODE == MODE_UNCOLLAPSED) wsv[i] = __ldg(P.wvec + (size_t)d * Mp + j);
+        if (MODE == MODE_COND) wsv[i] = (P.qmode == 2 && j < M) ? __ldg(P.qmat + (size_t)j * D + d) : 0.0;
+      }
+    }
     double tabv = 0.0;                 // SE: the exp table pre-scaled by v_d (threads 64..127)
     if (KIND == 0 && tid >= 64 && tid < 128) {
       const double vv = __ldg(hyp + 64);
       tabv = (exp_nmin(vv) == 0 && vv < 1.0) ? 0.0 : vv * g_exp2_tab[tid - 64];
     }
     __syncthreads();   // x tile staged (di == 0) / previous d fully done with shared memory (di > 0)
+    FFVD_MARK(11);
     if (tid < 64) {
       if (tid < 32) { sm.small[tid] = hv0; sm.small[32 + tid] = hv1; }
       if (tid < 40) sm.red[tid] = 0.0;
@@ -790,13 +942,13 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         }
       }
     }
-    for (int j = tid; j < Mp; j += NTH) {
-      double u = 0.0;
-      if (MODE == MODE_UNCOLLAPSED || MODE == MODE_FORWARD || MODE == MODE_COND) u = P.UT[(size_t)d * Mp + j];
-      else if (MODE == MODE_COLLAPSED_P2) u = (j < M) ? P.wvec[((size_t)s * D + d) * Mp + j] : 0.0;
-      sm.us[j] = u;
-      if (MODE == MODE_UNCOLLAPSED) sm.ws[j] = P.wvec[(size_t)d * Mp + j];
-      if (MODE == MODE_COND) sm.ws[j] = (P.qmode == 2 && j < M) ? P.qmat[(size_t)j * D + d] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NUS; ++i) {
+      const int j = tid + i * NTH;
+      if (j < Mp) {
+        sm.us[j] = usv[i];
+        if (MODE == MODE_UNCOLLAPSED || MODE == MODE_COND) sm.ws[j] = wsv[i];
+      }
     }
     __syncthreads();
     const double v = sm.sc[0], invQ = sm.sc[2], logQd = sm.sc[3];
@@ -820,17 +972,21 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       __syncthreads();
       for (int idx = tid; idx < (BT - nvalid) * Mp; idx += NTH) sm.tile[(nvalid + idx / Mp) * lda + idx % Mp] = 0.0;
     }
+    const double* LinvT = P.LinvT + (size_t)dh * Mp * Mp;
+    const double* Linv = P.Linv + (size_t)dh * Mp * Mp;
+    constexpr int CH0 = tile_gemm_ch0<NGW>();
+    double2 ring0[4][CH0];            // first operand fragments of the next contraction, requested ahead of the barrier / SYRK in front of it
+    if (MODE != MODE_COLLAPSED_P2) tile_gemm_prologue<CH0, +1, NCW>(ring0, LinvT, Mp, wc, 0, g, q);
+    else tile_gemm_prologue<CH0, 0, NCW>(ring0, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, 0, g, q);
     __syncthreads();
     FFVD_MARK(1);
 
-    const double* LinvT = P.LinvT + (size_t)dh * Mp * Mp;
-    const double* Linv = P.Linv + (size_t)dh * Mp * Mp;
     double acc[NGW][RBW][4];
     double* wtile = sm.tile + (size_t)row0 * lda;     // this warp's rows of the shared tile
 
     if (MODE != MODE_COLLAPSED_P2) {
       // ---- P2: A = K L^{-T}   (rows a_t = L^{-1} k_t)
-      tile_gemm<RBW, NGW, +1, NCW>(acc, wtile, lda, LinvT, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, +1, NCW>(acc, ring0, wtile, lda, LinvT, Mp, wc, g, q,
                               [](double x, int, int) { return x; });
       // row partial sums: a.u and a.a
       {
@@ -875,6 +1031,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       __syncthreads();          // everyone is done reading K from the tile
       FFVD_MARK(2);
       if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);
+      FFVD_MARK(12);
       // ---- per-row statistics (threads 0..BT-1)
       if (tid < 64) {
         double jxq = 0.0, jtr = 0.0, gq = 0.0, gvd = 0.0;
@@ -974,9 +1131,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_COND && P.qmode == 3) {
       // conditionals_multi_output.py:53-62 (q_sqrt R x M x M): fvar += sum_m (Q^T a_t)_m^2, a second contraction of the A
       // tile (still in registers) with the dense zero-padded factor
+      tile_gemm_prologue<CH0, 0, NCW>(ring0, P.qmat + (size_t)(P.nq == 1 ? 0 : d) * Mp * Mp, Mp, wc, 0, g, q);
       store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);
       __syncthreads();
-      tile_gemm<RBW, NGW, 0, NCW>(acc, wtile, lda, P.qmat + (size_t)(P.nq == 1 ? 0 : d) * Mp * Mp, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, 0, NCW>(acc, ring0, wtile, lda, P.qmat + (size_t)(P.nq == 1 ? 0 : d) * Mp * Mp, Mp, wc, g, q,
                              [](double x, int, int) { return x; });
       double sq[RBW];
 #pragma unroll
@@ -1031,11 +1189,19 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
           }
         }
       }
+      // operand prologue of the next contraction (Kbar = A L^{-1}): in flight during the SYRK
+#if FFVD_G2_EARLY
+      if (MODE == MODE_UNCOLLAPSED) tile_gemm_prologue<CH0, -1, NCW>(ring0, Linv, Mp, wc, 0, g, q);
+#endif
       // ---- S += A^T A
       double* Sd = det_ptr1(P, P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp);
 #if FFVD_ABLATE != 2
       // unit size fixed at compile time (Mp = 16 NGW NCW): one SYRK variant per instantiation keeps the item loop's code small
+#if FFVD_SYRK_PIPE
+      syrk_units_pipe<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 2 * 8 * 40, warp, lane);
+#else
       syrk_units<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
+#endif
 #endif
       FFVD_MARK(4);             // warp 0's own time: no barrier between the SYRK and the next contraction
     }
@@ -1043,7 +1209,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_UNCOLLAPSED) {
       // ---- P4: Kbar = Abar L^{-1} with abar_r = e_r u + a_r / Q.  By linearity Kbar = (A L^{-1})/Q + e w^T with
       //      w = L^{-T} u (ltu_kernel, once per evaluation), so the contraction reads A unmodified.
-      tile_gemm<RBW, NGW, -1, NCW>(acc, wtile, lda, Linv, Mp, wc, g, q,
+#if !FFVD_G2_EARLY
+      tile_gemm_prologue<CH0, -1, NCW>(ring0, Linv, Mp, wc, 0, g, q);
+#endif
+      tile_gemm<RBW, NGW, -1, NCW>(acc, ring0, wtile, lda, Linv, Mp, wc, g, q,
                               [](double x, int, int) { return x; });
       double er[RBW];
 #pragma unroll
@@ -1060,7 +1229,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       }
     } else if (MODE == MODE_COLLAPSED_P2) {
       // ---- Kbar = K N + delta w'^T ; also dbar_r = k_r . w'
-      tile_gemm<RBW, NGW, 0, NCW>(acc, wtile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, g, q,
+      tile_gemm<RBW, NGW, 0, NCW>(acc, ring0, wtile, lda, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, g, q,
                              [](double x, int, int) { return x; });
     }
 
@@ -1132,7 +1301,9 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
               acc[ng][rb][c] = (KIND == 0) ? kb * kv[rb][c] : ((jb + c < M && row0 + 8 * rb + g < nvalid) ? kb : 0.0);
             }
         }
+        FFVD_MARK(13);
         __syncthreads();        // all warps done reading A (GEMM2 / SYRK) or K (pass 2)
+        FFVD_MARK(14);
         store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);
       }
       __syncthreads();

@@ -9,6 +9,14 @@ namespace ffvd {
                            // 4 = no K scratch stores, 5 = no exp, 6 = no r^2 loop
 #endif
 
+#ifndef FFVD_SYRK_PIPE
+#define FFVD_SYRK_PIPE 1   // 1: software-pipelined SYRK flush (syrk_units_pipe), two staging buffers per warp
+#endif
+
+#ifndef FFVD_G2_EARLY
+#define FFVD_G2_EARLY 0    // 1: operand prologue of Kbar = A L^{-1} requested before the SYRK (costs the SYRK registers: slower)
+#endif
+
 enum { MODE_UNCOLLAPSED = 0, MODE_COLLAPSED_P1 = 1, MODE_COLLAPSED_P2 = 2, MODE_FORWARD = 3, MODE_COND = 4 };
 
 template <int RB>
@@ -18,7 +26,7 @@ __host__ __device__ constexpr int bt_of() { return 8 * RB; }
 // flush) and part (128 x 32 partial products of W [Z,1], used by the last phase) are live in disjoint phases separated
 // by CTA barriers and share one region
 __host__ __device__ inline size_t fused_xsc_part_doubles(int BT, int NW, int nbm) {
-  const size_t a = ((size_t)BT * FFVD_XLD + 1) & ~(size_t)1, b = (size_t)128 * 8 * nbm, c = (size_t)NW * 8 * 40;
+  const size_t a = ((size_t)BT * FFVD_XLD + 1) & ~(size_t)1, b = (size_t)128 * 8 * nbm, c = (size_t)NW * 8 * 40 * (FFVD_SYRK_PIPE ? 2 : 1);
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 

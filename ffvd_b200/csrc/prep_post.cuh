@@ -1037,7 +1037,7 @@ __global__ void hyper_kernel(const DevProblem* __restrict__ probs, int kind, int
         a = fma(z, z, a);
       }
       out[(size_t)Din * Mp + m] = 1.0;
-      out[(size_t)(Din + 1) * Mp + m] = -0.5 * a;
+      out[(size_t)(Din + 1) * Mp + m] = (m < M) ? -0.5 * a : -1.0e4;     // padded columns: exp saturates at ~1e-308 (see compute_k_tile)
       for (int jd = Din + 2; jd < FFVD_ZTS_ROWS; ++jd) out[(size_t)jd * Mp + m] = 0.0;
     }
   }

@@ -1150,7 +1150,7 @@ def test_deterministic_flag_is_bitwise_repeatable(env, collapsed, kind, M):
     b = run_cuda(env, prob, collapsed, flags=base | F.FLAG_DETERMINISTIC)
     for k in a:
         assert np.array_equal(a[k], b[k]), (k, float(np.max(np.abs(a[k] - b[k]))))
-        assert relerr(plain[k], a[k]) <= 1e-10, k      # RED order of the default path (LinearK: cancellation)
+        assert relerr(plain[k], a[k]) <= TOL, k        # the default path differs by its RED order (1e-10 where the bound cancels: LinearK, collapsed M=200)
     check(O.nll_and_grads(prob, collapsed=collapsed), a, what="deterministic M%d" % M)
     # forward-only evaluation under the flag
     f1 = run_cuda(env, prob, collapsed, flags=base | F.FLAG_DETERMINISTIC | F.FLAG_NO_GRADS)
