@@ -216,12 +216,16 @@ __device__ __forceinline__ void ldg256_cg(const double* p, double& a, double& b,
 // (CTA, warp) into its own copy of the small accumulators -- each element then has a single writer thread, whose REDs to one
 // address apply in program order -- and det_reduce_kernel sums the copies in a fixed order.  Off: the shared accumulator itself.
 #define FFVD_DET_MAX_WARPS 16
-__device__ __forceinline__ double* det_ptr1(const DevProblem& P, double* p) {
-  return P.det1 ? reinterpret_cast<double*>(P.det1 + (size_t)blockIdx.x * P.det_stride1 + (reinterpret_cast<char*>(p) - P.det_base1)) : p;
+// The byte offsets are formed ONCE per work item (det_off1 / det_off2: zero when the mode is off) and added to the
+// accumulator addresses (det_at): looking the mode up per RED cost two shared-memory loads and a divergence region per call.
+__device__ __forceinline__ long long det_off1(const DevProblem& P) {
+  return P.det1 ? (long long)((P.det1 + (size_t)blockIdx.x * P.det_stride1) - P.det_base1) : 0ll;
 }
-__device__ __forceinline__ double* det_ptr2(const DevProblem& P, double* p) {
-  return P.det2 ? reinterpret_cast<double*>(P.det2 + ((size_t)blockIdx.x * FFVD_DET_MAX_WARPS + (threadIdx.x >> 5)) * P.det_stride2 +
-                                            (reinterpret_cast<char*>(p) - P.det_base2)) : p;
+__device__ __forceinline__ long long det_off2(const DevProblem& P) {
+  return P.det2 ? (long long)((P.det2 + ((size_t)blockIdx.x * FFVD_DET_MAX_WARPS + (threadIdx.x >> 5)) * P.det_stride2) - P.det_base2) : 0ll;
+}
+__device__ __forceinline__ double* det_at(double* p, long long off) {
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(p) + off);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -523,7 +523,7 @@ __device__ __forceinline__ void syrk_units_pipe(const double* tile, int lda, int
 // would still occupy the tensor pipe.
 template <int KIND, int RB, int NGW, int NW, int NBM>
 __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevProblem& P, int d, double v, double* gXs,
-                                           int t0, int nvalid, int warp, int lane, int tid
+                                           long long doff2, int t0, int nvalid, int warp, int lane, int tid
 #ifdef FFVD_PHASE_TIMING
                                            , long long& _phase_last
 #endif
@@ -603,7 +603,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
                   zb = v * c[u][nb][e];
                 }
                 FFVD_ASSERT(m < M && jd < Din);
-                red_add(det_ptr2(P, P.gZ + (size_t)m * Din + jd), zb);
+                red_add(det_at(P.gZ + (size_t)m * Din + jd, doff2), zb);
               }
             }
           }
@@ -621,7 +621,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           x += __shfl_xor_sync(0xffffffffu, x, 8);
           x += __shfl_xor_sync(0xffffffffu, x, 16);
           const int jd = 8 * nb + 2 * q + e;
-          if (g == 0 && nb < nbx && jd < Din) red_add(det_ptr2(P, P.gl + (size_t)d * Din + jd), x);
+          if (g == 0 && nb < nbx && jd < Din) red_add(det_at(P.gl + (size_t)d * Din + jd, doff2), x);
         }
     }
   }
@@ -691,15 +691,25 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
   {
     double lsum = 0.0, vacc = 0.0;
     const double il2 = (KIND == 0) ? sm.small[lane] : 0.0;
-    for (int r = warp; r < nvalid; r += NW) {
-      double wz = 0.0, rs = 0.0;
+    // all shared-memory reads of the warp's rows first (one latency, not one per row), then the arithmetic and the REDs
+    constexpr int NR = BT / NW;
+    double wzv[NR], rsv[NR], xv[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = warp + NW * i;
+      wzv[i] = rsv[i] = 0.0;
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        if (lane < PW) wz += sm.part[(size_t)(k * BT + r) * PW + lane];
-        rs += sm.part[(size_t)(k * BT + r) * PW + Din];
+        if (lane < PW) wzv[i] += sm.part[(size_t)(k * BT + r) * PW + lane];
+        rsv[i] += sm.part[(size_t)(k * BT + r) * PW + Din];
       }
-      if (lane < Din) {
-        const double x = sm.xs[r * FFVD_XLD + lane];
+      xv[i] = sm.xs[r * FFVD_XLD + lane];
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = warp + NW * i;
+      if (lane < Din && r < nvalid) {
+        const double x = xv[i], wz = wzv[i], rs = rsv[i];
         double xb;
         if (KIND == 0) {
           xb = -il2 * (x * rs - wz);
@@ -713,9 +723,9 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
         if (lane < D) red_add(gXs + (size_t)(t0 + r) * D + lane, xb);
       }
     }
-    if (KIND == 0 && lane < Din) red_add(det_ptr2(P, P.gl + (size_t)d * Din + lane), lsum);
+    if (KIND == 0 && lane < Din) red_add(det_at(P.gl + (size_t)d * Din + lane, doff2), lsum);
     vacc = warp_sum(vacc);
-    if (lane == 0) red_add(det_ptr2(P, P.gv + d), vacc);
+    if (lane == 0) red_add(det_at(P.gv + d, doff2), vacc);
   }
 }
 
@@ -823,6 +833,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     double* gXb = (gXs && P.gXp) ? P.gXp + (size_t)s * (T + 1) * D : gXs;                        // +-e (uncollapsed) / +-gx (collapsed pass 2)
     double* gXe = (gXs && P.gXp) ? P.gXp + P.gXp_stride + (size_t)s * (T + 1) * D : gXs;         // emission
     double* gXl = (gXs && P.gXp) ? P.gXp + 2 * P.gXp_stride + (size_t)s * (T + 1) * D : gXs;     // LinearK: -v/Q x_t
+    const long long doff1 = det_off1(P), doff2 = det_off2(P);       // deterministic mode: this CTA's / warp's private accumulator copies
 
     Smem sm;
     {
@@ -1115,14 +1126,14 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
             for (int c = 0; c < D; ++c) {
               const double xc1 = (r < nvalid) ? sm.xs[(r + 1) * FFVD_XLD + c] : 0.0;
               const double t = warp_sum(dy * xc1);
-              if (lane == 0) red_add(det_ptr2(P, P.gC + (size_t)c * Dy + y), t);
+              if (lane == 0) red_add(det_at(P.gC + (size_t)c * Dy + y, doff2), t);
             }
             const double sd = warp_sum(dy), sr = warp_sum(rr);
-            if (lane == 0) { red_add(det_ptr2(P, P.gd + y), sd); red_add(det_ptr2(P, P.gR + y), sr); }
+            if (lane == 0) { red_add(det_at(P.gd + y, doff2), sd); red_add(det_at(P.gR + y, doff2), sr); }
           }
         }
         ll = warp_sum(ll);
-        if (lane == 0) red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS), ll);
+        if (lane == 0) red_add(det_at(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_EMIS, doff2), ll);
       }
       __syncthreads();          // A tile + es[] visible
       FFVD_MARK(3);
@@ -1162,8 +1173,8 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_FORWARD || MODE == MODE_COND) {
       // forward only: flush the scalar sums and move on
       if (MODE == MODE_FORWARD && tid == 0) {
-        red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ), sm.red[0] + sm.red[4]);
-        red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE), sm.red[1] + sm.red[5]);
+        red_add(det_at(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, doff2), sm.red[0] + sm.red[4]);
+        red_add(det_at(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, doff2), sm.red[1] + sm.red[5]);
       }
       continue;
     }
@@ -1174,19 +1185,25 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         double er[RBW];
 #pragma unroll
         for (int rb = 0; rb < RBW; ++rb) er[rb] = sm.es[row0 + 8 * rb + g];
+        // four columns at a time: the partial sums first, then the three shuffle rounds with the four chains interleaved (one
+        // column after the other is a dependent shuffle -> add chain of ~100 clk per column with nothing to overlap it)
+        double* ub = det_at(P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp, doff2);
 #pragma unroll
         for (int ng = 0; ng < NGW; ++ng) {
           const int jb = 16 * group_index<NCW>(wc, ng) + 4 * q;
+          double t[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            double t = 0.0;
+            t[c] = 0.0;
 #pragma unroll
-            for (int rb = 0; rb < RBW; ++rb) t = fma(er[rb], acc[ng][rb][c], t);
-            t += __shfl_xor_sync(0xffffffffu, t, 4);
-            t += __shfl_xor_sync(0xffffffffu, t, 8);
-            t += __shfl_xor_sync(0xffffffffu, t, 16);
-            if (g == 0 && jb + c < M) red_add(det_ptr2(P, P.ubar + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp + jb + c), t);
+            for (int rb = 0; rb < RBW; ++rb) t[c] = fma(er[rb], acc[ng][rb][c], t[c]);
           }
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t[c] += __shfl_xor_sync(0xffffffffu, t[c], o);
+          // lanes g = 0..3 of each q flush one column each (all four hold the full sums)
+          if (g < 4 && jb + g < M) red_add(ub + jb + g, g == 0 ? t[0] : (g == 1 ? t[1] : (g == 2 ? t[2] : t[3])));
         }
       }
       // operand prologue of the next contraction (Kbar = A L^{-1}): in flight during the SYRK
@@ -1194,7 +1211,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       if (MODE == MODE_UNCOLLAPSED) tile_gemm_prologue<CH0, -1, NCW>(ring0, Linv, Mp, wc, 0, g, q);
 #endif
       // ---- S += A^T A
-      double* Sd = det_ptr1(P, P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp);
+      double* Sd = det_at(P.Sacc + ((size_t)(MODE == MODE_COLLAPSED_P1 ? s * D + d : d)) * Mp * Mp, doff1);
 #if FFVD_ABLATE != 2
       // unit size fixed at compile time (Mp = 16 NGW NCW): one SYRK variant per instantiation keeps the item loop's code small
 #if FFVD_SYRK_PIPE
@@ -1314,10 +1331,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 #define FFVD_CW_TAIL
 #endif
       switch ((Din + 1 + 7) >> 3) {
-        case 1: contract_W<KIND, RB, NGW, NW, 1>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
-        case 2: contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
-        case 3: contract_W<KIND, RB, NGW, NW, 3>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
-        default: contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 1: contract_W<KIND, RB, NGW, NW, 1>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 2: contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 3: contract_W<KIND, RB, NGW, NW, 3>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        default: contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
       }
 #undef FFVD_CW_TAIL
     }
@@ -1328,11 +1345,11 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (tid < 32) {
       if (tid == 0) {
         if (MODE != MODE_COLLAPSED_P2) {
-          red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ), sm.red[0] + sm.red[4]);
-          red_add(det_ptr2(P, P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE), sm.red[1] + sm.red[5]);
-          red_add(det_ptr2(P, P.gQ + d), sm.red[2] + sm.red[6]);
+          red_add(det_at(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_XQ, doff2), sm.red[0] + sm.red[4]);
+          red_add(det_at(P.terms_raw + (size_t)s * FFVD_NTERMS_RAW + FFVD_RAW_TRACE, doff2), sm.red[1] + sm.red[5]);
+          red_add(det_at(P.gQ + d, doff2), sm.red[2] + sm.red[6]);
         }
-        if (MODE != MODE_COLLAPSED_P1) red_add(det_ptr2(P, P.gv + d), (sm.red[3] + sm.red[7]) + (sm.red[8] + sm.red[9]));
+        if (MODE != MODE_COLLAPSED_P1) red_add(det_at(P.gv + d, doff2), (sm.red[3] + sm.red[7]) + (sm.red[8] + sm.red[9]));
       }
     }
   }   // d loop
