@@ -174,6 +174,13 @@ __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v));
 }
 
+// The same under a predicate, as ONE predicated instruction: `if (c) red_add(...)` compiles to a divergence region
+// (BSSY / BRA / BSYNC) around every call, which in the epilogues with a dozen conditional REDs per lane is most of the code.
+// The address must be valid to FORM, not to access, when c is false.
+__device__ __forceinline__ void red_add_if(double* p, double v, bool c) {
+  asm volatile("{\n\t.reg .pred pr;\n\tsetp.ne.s32 pr, %2, 0;\n\t@pr red.global.add.f64 [%0], %1;\n\t}" ::"l"(__cvta_generic_to_global(p)), "d"(v), "r"((int)c));
+}
+
 // 16-byte read-only load for the L^{-1} / L^{-T} operand streams: no L1 allocation (each element is used once per
 // tile) and an L2 evict-last policy -- the D matrices (8 MB at C3) are re-read by every tile for the whole kernel while
 // X / x-bar (hundreds of MB) stream through the same L2; without the hint the streams kept evicting them and the

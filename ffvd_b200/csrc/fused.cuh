@@ -593,17 +593,19 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int jd = 8 * nb + 2 * q + e;
-              if (jd < Din && m < M) {
+              {
+                // no branch: columns >= Din have a zero scale (sm.small) / zero products, rows >= M zero W columns; the RED
+                // itself is predicated
+                const bool ok = jd < Din && m < M;
                 double zb;
                 if (KIND == 0) {
                   const double z = zr[u][nb][e];
-                  zb = sm.small[jd] * (c[u][nb][e] - cs * z);
+                  zb = ok ? sm.small[jd & 31] * (c[u][nb][e] - cs * z) : 0.0;
                   lacc[nb][e] = fma(-z, zb, lacc[nb][e]);
                 } else {
                   zb = v * c[u][nb][e];
                 }
-                FFVD_ASSERT(m < M && jd < Din);
-                red_add(det_at(P.gZ + (size_t)m * Din + jd, doff2), zb);
+                red_add_if(det_at(P.gZ + (size_t)m * Din + jd, doff2), zb, ok);
               }
             }
           }
@@ -621,7 +623,7 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
           x += __shfl_xor_sync(0xffffffffu, x, 8);
           x += __shfl_xor_sync(0xffffffffu, x, 16);
           const int jd = 8 * nb + 2 * q + e;
-          if (g == 0 && nb < nbx && jd < Din) red_add(det_at(P.gl + (size_t)d * Din + jd, doff2), x);
+          red_add_if(det_at(P.gl + (size_t)d * Din + jd, doff2), x, g == 0 && nb < nbx && jd < Din);
         }
     }
   }
@@ -708,19 +710,20 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       const int r = warp + NW * i;
-      if (lane < Din && r < nvalid) {
-        const double x = xv[i], wz = wzv[i], rs = rsv[i];
+      {
+        // branch free: rows >= nvalid of W and of the x tile are zero, so their terms vanish by themselves
+        const bool in = lane < Din;
+        const double x = in ? xv[i] : 0.0, wz = in ? wzv[i] : 0.0, rs = rsv[i];
         double xb;
         if (KIND == 0) {
           xb = -il2 * (x * rs - wz);
           lsum = fma(-x, xb, lsum);                 // d/dlogl row part
-          if (lane == 0) vacc += rs;                // d/dlogv = sum W
+          vacc += (lane == 0) ? rs : 0.0;           // d/dlogv = sum W
         } else {
           xb = v * wz;
           vacc = fma(x, xb, vacc);                  // sum kbar*k
         }
-        FFVD_ASSERT(t0 + r < P.T);
-        if (lane < D) red_add(gXs + (size_t)(t0 + r) * D + lane, xb);
+        red_add_if(gXs + (size_t)(t0 + r) * D + lane, xb, lane < D && r < nvalid);
       }
     }
     if (KIND == 0 && lane < Din) red_add(det_at(P.gl + (size_t)d * Din + lane, doff2), lsum);
@@ -1203,7 +1206,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 #pragma unroll
             for (int c = 0; c < 4; ++c) t[c] += __shfl_xor_sync(0xffffffffu, t[c], o);
           // lanes g = 0..3 of each q flush one column each (all four hold the full sums)
-          if (g < 4 && jb + g < M) red_add(ub + jb + g, g == 0 ? t[0] : (g == 1 ? t[1] : (g == 2 ? t[2] : t[3])));
+          red_add_if(ub + jb + g, g == 0 ? t[0] : (g == 1 ? t[1] : (g == 2 ? t[2] : t[3])), g < 4 && jb + g < M);
         }
       }
       // operand prologue of the next contraction (Kbar = A L^{-1}): in flight during the SYRK
