@@ -887,7 +887,9 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     //      hyper_kernel; the scaled rows x~ = x/l and -1/2 |x~|^2 are formed from the staged tile.
     const double* hyp = P.hyp + (size_t)dh * 72;
     // requests for this d's vectors go out before the barrier that retires the previous d's use of shared memory
-    const double silc = (KIND == 0 && lane < Din) ? __ldg(hyp + 32 + lane) : 0.0;
+    double sil4[4];                    // 1 / l of the four input columns this thread scales (columns (tid & 7) + 8 c4)
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) sil4[c4] = (KIND == 0 && (tid & 7) + 8 * c4 < Din) ? __ldg(hyp + 32 + (tid & 7) + 8 * c4) : 0.0;
     double hv0 = 0.0, hv1 = 0.0, scv = 0.0;
     if (tid < 32) { hv0 = __ldg(hyp + tid); hv1 = __ldg(hyp + 32 + tid); }
     if (tid == 40) scv = __ldg(hyp + 64);
@@ -928,33 +930,41 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     }
     if (KIND == 0 && tid >= 64 && tid < 128) sm.exptab[tid - 64] = tabv;
     if (KIND == 0) {
-      // x~ = x / l (same rounded products in xsc and in -1/2 |x~|^2); columns Din, Din + 1 hold the augmentation
-      // [-1/2 |x~|^2, 1] of the K-tile product (written below), the columns after them zeros
-      for (int idx = tid; idx < BT * FFVD_XCOLS; idx += NTH) {
-        const int r = idx >> 5;                         // column == lane
-        if (lane != Din && lane != Din + 1) sm.xsc[r * FFVD_XLD + lane] = sm.xs[r * FFVD_XLD + lane] * silc;
+      // x~ = x / l and -1/2 |x~_r|^2 in ONE pass: a quarter-warp per row (8 lanes x 4 columns each, the 1/l of the four
+      // columns in registers since the top of the iteration), all rows of a pass loaded before the first is used.  Columns
+      // Din, Din + 1 of xsc hold the augmentation [-1/2 |x~|^2, 1] of the K-tile product, the columns after them zeros.
+      constexpr int RPP = NTH / 8;                       // rows per pass
+      constexpr int NPS = (BT + RPP - 1) / RPP;
+      const int l8 = tid & 7;
+      double xr[NPS][4];
+#pragma unroll
+      for (int ps = 0; ps < NPS; ++ps) {
+        const int r = (tid >> 3) + ps * RPP;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) xr[ps][c4] = (r < BT) ? sm.xs[r * FFVD_XLD + l8 + 8 * c4] : 0.0;
       }
-      if (Din + 2 > FFVD_XCOLS)
-        for (int idx = tid; idx < BT * 4; idx += NTH)
-          if (32 + (idx & 3) > Din + 1) sm.xsc[(idx >> 2) * FFVD_XLD + 32 + (idx & 3)] = 0.0;
-      // -1/2 |x~_r|^2: a quarter-warp per row (8 lanes x 4 columns), rows dealt to the warps
-      for (int r = (tid >> 3); r < BT; r += NTH / 8) {
-        const int l8 = tid & 7;
+#pragma unroll
+      for (int ps = 0; ps < NPS; ++ps) {
+        const int r = (tid >> 3) + ps * RPP;
         double a = 0.0;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           const int c = l8 + 8 * c4;
-          const double sv = sm.xs[r * FFVD_XLD + c] * ((c < Din) ? __ldg(hyp + 32 + c) : 0.0);
+          const double sv = xr[ps][c4] * sil4[c4];
           a = fma(sv, sv, a);
+          if (r < BT && c != Din && c != Din + 1) sm.xsc[r * FFVD_XLD + c] = sv;
         }
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (l8 == 0) {
+        if (l8 == 0 && r < BT) {
           sm.xsc[r * FFVD_XLD + Din] = -0.5 * a;
           sm.xsc[r * FFVD_XLD + Din + 1] = 1.0;
         }
       }
+      if (Din + 2 > FFVD_XCOLS)
+        for (int idx = tid; idx < BT * 4; idx += NTH)
+          if (32 + (idx & 3) > Din + 1) sm.xsc[(idx >> 2) * FFVD_XLD + 32 + (idx & 3)] = 0.0;
     }
 #pragma unroll
     for (int i = 0; i < NUS; ++i) {
