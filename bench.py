@@ -49,7 +49,7 @@ WORKLOADS = {
 CPU_SAMPLE_T = 20_000          # bounded CPU sample: T=20k, S=1 of the same M, D
 PARITY_TOL = 1e-9              # north star: <= 1e-9 relative in float64 (relative to each tensor's max-norm)
 PARAMS = ("X", "Z", "U", "logv", "logl", "logQ", "C", "d", "logR")
-KERNEL_TAG = "r02"             # version of the fused kernel the committed ncu traffic figure belongs to (profiles/fused_traffic.json)
+KERNEL_TAG = "r02b"            # version of the fused kernel the committed ncu traffic figure belongs to (profiles/fused_traffic.json)
 
 
 def algorithmic_flops_per_unit(M, Din):

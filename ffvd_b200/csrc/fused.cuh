@@ -476,9 +476,9 @@ __device__ __forceinline__ void syrk_tile_pipe(const double* tile, int lda, int 
   pd.m0 = m0; pd.n0 = n0; pd.diag = DIAG; pd.valid = true;
 }
 
-template <int RB, int NW, int NB>
+template <int RB, int NW, int NB, class F>
 __device__ __forceinline__ void syrk_units_pipe(const double* tile, int lda, int Mp, double* __restrict__ S, double* stage_w,
-                                                int warp, int lane) {
+                                                int warp, int lane, F before_drain) {
   const int nt = Mp / (8 * NB);
   const int nfull = nt * (nt - 1) / 2, nunits = nfull + nt;
   // units of this warp: i = 0 .. nu-1 with u(i) = i NW + (i odd ? NW-1-warp : warp) < nunits  (snake order, see syrk_units)
@@ -506,6 +506,9 @@ __device__ __forceinline__ void syrk_units_pipe(const double* tile, int lda, int
       syrk_tile_pipe<RB, true, NB>(tile, lda, Mp, S, stage_w, 8 * NB * t, 8 * NB * t, lane, pd);
     }
   }
+  // the last unit drains on its own; `before_drain` lets the caller put requests in flight under it (the operand prologue of
+  // the next contraction)
+  before_drain();
   if (pd.valid) {
 #pragma unroll
     for (int sl = 0; sl < 2 * NB; ++sl) syrk_flush_slot<NB>(pd, sl, Mp, S, stage_w, lane);
@@ -1228,7 +1231,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 #if FFVD_ABLATE != 2
       // unit size fixed at compile time (Mp = 16 NGW NCW): one SYRK variant per instantiation keeps the item loop's code small
 #if FFVD_SYRK_PIPE
-      syrk_units_pipe<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 2 * 8 * 40, warp, lane);
+      syrk_units_pipe<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 2 * 8 * 40, warp, lane, [&]() {
+        // (only where the prologue is small: at NGW = 4 its 64 registers on top of the draining unit cost more than they hide)
+        if (MODE == MODE_UNCOLLAPSED && !FFVD_G2_EARLY && NGW <= 2) tile_gemm_prologue<CH0, -1, NCW>(ring0, Linv, Mp, wc, 0, g, q);
+      });
 #else
       syrk_units<RB, NW, (16 * NGW * NCW <= 128) ? 2 : 4>(sm.tile, lda, Mp, Sd, sm.stage + warp * 8 * 40, warp, lane);
 #endif
@@ -1239,9 +1245,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (MODE == MODE_UNCOLLAPSED) {
       // ---- P4: Kbar = Abar L^{-1} with abar_r = e_r u + a_r / Q.  By linearity Kbar = (A L^{-1})/Q + e w^T with
       //      w = L^{-T} u (ltu_kernel, once per evaluation), so the contraction reads A unmodified.
-#if !FFVD_G2_EARLY
-      tile_gemm_prologue<CH0, -1, NCW>(ring0, Linv, Mp, wc, 0, g, q);
-#endif
+      if (!FFVD_G2_EARLY && (!FFVD_SYRK_PIPE || FFVD_ABLATE == 2 || NGW > 2)) tile_gemm_prologue<CH0, -1, NCW>(ring0, Linv, Mp, wc, 0, g, q);
       tile_gemm<RBW, NGW, -1, NCW>(acc, ring0, wtile, lda, Linv, Mp, wc, g, q,
                               [](double x, int, int) { return x; });
       double er[RBW];
