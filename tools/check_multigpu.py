@@ -41,6 +41,14 @@ def rel(a, b):
 
 
 worst = 0.0
+parts = {}
+
+
+def note(name, before):
+    """deviation this section added (max over its comparisons)"""
+    parts[name] = max(parts.get(name, 0.0), worst if worst > before else 0.0)
+
+
 # ---- (1) sample sharding
 S = 2 * world + 1
 full_p = to_dev(fixtures.synthetic_problem(T=333, M=150, D=3, S=S))
@@ -54,6 +62,8 @@ fd.allreduce_shared(o)
 for k in fd.SHARED:
     worst = max(worst, rel(full_o[k], o[k]))
 worst = max(worst, rel(full_o["g_X"][lo:hi], o["g_X"]), rel(full_o["nll"][lo:hi], o["nll"]))
+parts["sample_sharding"] = worst
+w1 = worst; worst = 0.0
 # ---- (2) time sharding of one trajectory
 one_p = to_dev(fixtures.synthetic_problem(T=1001, M=150, D=3, S=1))
 one_o = alloc(one_p)
@@ -75,6 +85,8 @@ for k in ("nll", "terms") + fd.SHARED:
     worst = max(worst, rel(one_o[k].reshape(-1), out[k].reshape(-1)))
 rows = slice(0, b - a + (1 if rank == world - 1 else 0))
 worst = max(worst, rel(one_o["g_X"][a:a + rows.stop], out["g_X"][rows]))
+parts["time_sharding_uncollapsed"] = worst
+w2 = worst; worst = 0.0
 # ---- (3) the library's own communicator
 fd.init_native_comm(ctx)
 assert ctx.comm_info()[1] == world
@@ -83,6 +95,8 @@ ctx.nll_grads(0, False, mine, o2)
 ctx.allreduce_shared(o2)
 for k in fd.SHARED:
     worst = max(worst, rel(full_o[k], o2[k]))
+parts["native_communicator"] = worst
+w3 = worst; worst = 0.0
 # ---- (4) collapsed bound, time sharded, statistics all-reduced by the native communicator and by torch
 col_o = alloc(one_p)
 ctx.nll_grads(0, True, one_p, col_o)
@@ -95,9 +109,14 @@ for transport in ("native", "torch"):
     for k in ("nll", "terms") + fd.SHARED:
         worst = max(worst, rel(col_o[k].reshape(-1), outc[k].reshape(-1)))
     worst = max(worst, rel(col_o["g_X"][a:a + rows.stop], outc["g_X"][rows]))
-w = torch.tensor([worst], dtype=torch.float64, device=dev)
+parts["time_sharding_collapsed"] = worst
+names = sorted(parts)
+w = torch.tensor([parts[n] for n in names], dtype=torch.float64, device=dev)
 dist.all_reduce(w, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("multi-GPU check on %d GPUs: worst max-norm relative deviation from the single-GPU evaluation %.3e  %s"
-          % (world, float(w.item()), "OK" if float(w.item()) <= 1e-10 else "FAIL"))
+    TOL = 1e-9     # the north star's float64 tolerance; the sharded sums differ from the single-GPU ones by their summation order only
+    for n, v in zip(names, w.tolist()):
+        print("  %-28s %.3e" % (n, v))
+    print("multi-GPU check on %d GPUs: worst max-norm relative deviation from the single-GPU evaluation %.3e  %s (tolerance %.0e)"
+          % (world, float(w.max().item()), "OK" if float(w.max().item()) <= TOL else "FAIL", TOL))
 dist.destroy_process_group()
