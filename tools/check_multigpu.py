@@ -44,11 +44,6 @@ worst = 0.0
 parts = {}
 
 
-def note(name, before):
-    """deviation this section added (max over its comparisons)"""
-    parts[name] = max(parts.get(name, 0.0), worst if worst > before else 0.0)
-
-
 # ---- (1) sample sharding
 S = 2 * world + 1
 full_p = to_dev(fixtures.synthetic_problem(T=333, M=150, D=3, S=S))
