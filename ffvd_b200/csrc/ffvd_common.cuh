@@ -200,6 +200,12 @@ __device__ __forceinline__ double2 ldg_stream2_v(const double* p) {     // same,
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+#define FFVD_KB0 3      // k-steps of the K-tile product whose group-0 operand fragments are requested as register loads ahead of the phase
+__device__ __forceinline__ double2 ldg_nc2_v(const double* p) {            // 16-byte read-only load, pinned in program order
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(__cvta_generic_to_global(p)));
+  return v;
+}
 __device__ __forceinline__ void prefetch_l1(const double* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
 }

@@ -85,7 +85,7 @@ struct Smem {
 template <int KIND, int RB, int NGW, bool SCR, int NCW, int KS>
 __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __restrict__ ZTd, int Mp, int Din, double v, int nmin,
                                                int ks_rt, int wc, int g, int q, int M, int row0, int lda,
-                                               double* __restrict__ kscr) {
+                                               double* __restrict__ kscr, const double2 (&kb0)[FFVD_KB0]) {
   // The tile of a warp (8 RB rows x 16 NGW columns) is formed in passes of RBB row blocks x one 16-column group: 4 RBB
   // accumulators per lane.  The pass loop is NOT unrolled (instruction-cache footprint of the item loop).
   constexpr int RBB = RB >= 4 ? 4 : RB;
@@ -101,7 +101,17 @@ __device__ __forceinline__ void compute_k_tile(const Smem& sm, const double* __r
       b[ks][0] = t.x; b[ks][1] = t.y;
     }
   };
-  if (KS > 0) load_b(bc, 16 * group_index<NCW>(wc, 0));
+  if (KS > 0) {
+    // group 0: the first FFVD_KB0 k-steps were requested by the caller at the top of the d iteration (kb0)
+#pragma unroll
+    for (int ks = 0; ks < KSA; ++ks) {
+      if (ks < FFVD_KB0) { bc[ks][0] = kb0[ks].x; bc[ks][1] = kb0[ks].y; }
+      else {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(zq + (size_t)(4 * ks) * Mp + 16 * group_index<NCW>(wc, 0)));
+        bc[ks][0] = t.x; bc[ks][1] = t.y;
+      }
+    }
+  }
 #pragma unroll 1
   for (int ng = 0; ng < NGW; ++ng) {
     const int jg = 16 * group_index<NCW>(wc, ng);
@@ -897,12 +907,17 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     if (tid < 32) { hv0 = __ldg(hyp + tid); hv1 = __ldg(hyp + 32 + tid); }
     if (tid == 40) scv = __ldg(hyp + 64);
     if (tid >= 41 && tid < 44) scv = __ldg(P.hq + (size_t)d * 4 + (tid - 41));
+    double2 kb0[FFVD_KB0];
     {
       // first operand fragments of the K-tile product (group 0 of this warp): pulled into L1 while the barriers and the
       // per-d staging below run (compute_k_tile requests the later groups one group ahead itself)
       const double* zp = ((KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT) + (size_t)q * Mp + 2 * g + 16 * group_index<NCW>(wc, 0);
       const int ksn = (KIND == 0) ? (Din + 2 + 3) >> 2 : (Din + 3) >> 2;
-      for (int ks = 0; ks < ksn; ++ks) prefetch_l1(zp + (size_t)(4 * ks) * Mp);
+      for (int ks = FFVD_KB0; ks < ksn; ++ks) prefetch_l1(zp + (size_t)(4 * ks) * Mp);
+      // ... and the first FFVD_KB0 k-steps of them as register loads (ncu: with the L1 prefetch alone the phase still began with
+      // an exposed L2 round trip -- the loads of group 0 and, behind them on the same scoreboard, the requests for group 1)
+#pragma unroll
+      for (int ks = 0; ks < FFVD_KB0; ++ks) kb0[ks] = (ks < ksn) ? ldg_nc2_v(zp + (size_t)(4 * ks) * Mp) : make_double2(0.0, 0.0);
     }
     // u_d / w_d (Mp entries each): requested here, stored after the barrier
     constexpr int NUS = (Mp + NTH - 1) / NTH;
@@ -988,10 +1003,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       const int nmin = (KIND == 0) ? exp_nmin(v) : 0;
       constexpr bool SCR = (KIND == 0 && MODE == MODE_UNCOLLAPSED);
       switch (ksn) {
-        case 2: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 2>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
-        case 3: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 3>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
-        case 5: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 5>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
-        default: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 0>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr); break;
+        case 2: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 2>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr, kb0); break;
+        case 3: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 3>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr, kb0); break;
+        case 5: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 5>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr, kb0); break;
+        default: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 0>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr, kb0); break;
       }
     }
     if (nvalid < BT) {
