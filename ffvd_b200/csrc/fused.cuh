@@ -51,7 +51,7 @@ __device__ __forceinline__ void ld_tile4(const double* p, int g, double& a, doub
 struct Smem {
   double* tile;     // BT x lda
   double* xs;       // (BT+1) x XLD : X~ rows t0..t0+BT  = [x_t, ctrl_t, 1, 0..]
-  double* xsc;      // BT x XLD     : SE: x~ scaled by 1/l_j ; unused for Linear
+  double* xsc;      // BT x XLD     : SE: augmented scaled rows [x/l, -1/2 |x/l|^2, 1, 0..] (A operand of the K-tile product); unused for Linear
   double* us;       // Mp           : u_d (uncollapsed) / w'_d (collapsed pass 2)
   double* ws;       // Mp           : uncollapsed: w_d = L^{-T} u_d
   double* es;       // 64           : e_t (uncollapsed) / delta_t (collapsed)
@@ -59,7 +59,6 @@ struct Smem {
   double* stage;    // NW warps x 8 x 40
   double* part;     // 128 x 8 NBM: partial products of W [Z,1] per k slice (overlays xsc / stage)
   double* small;    // 64: invl2[32], sil[32]
-  double* xn2h;     // 64: SE: -1/2 |x~_r|^2 of the scaled rows
   double* sc;       // 8: per-item scalars v, Q, 1/Q, log Q
   double* red;      // 40: block-level reductions (smem atomics)
   double* exptab;   // 64: 2^(j/64), the table of exp_nonpos_n
@@ -862,7 +861,6 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       sm.es = p; p += 64;
       sm.rowpart = p; p += 3 * 8 * BT;
       sm.small = p; p += 64;
-      sm.xn2h = p; p += 64;
       sm.sc = p; p += 8;
       sm.red = p; p += 40;
       sm.exptab = p;

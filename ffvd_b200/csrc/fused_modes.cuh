@@ -35,7 +35,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int RB, int Mp, int NW, int n
   const int BT = 8 * RB;
   // every sub-array is rounded up to an even number of doubles so that all of them stay 16-byte aligned
   size_t n = (size_t)BT * (Mp + 4) + (((size_t)(BT + 1) * FFVD_XLD + 1) & ~(size_t)1) +
-             fused_xsc_part_doubles(BT, NW, nbm) + 2 * Mp + 64 + 3 * 8 * BT + 64 + 64 + 8 + 40 + 64 /* exp table */;
+             fused_xsc_part_doubles(BT, NW, nbm) + 2 * Mp + 64 + 3 * 8 * BT + 64 + 8 + 40 + 64 /* exp table */;
   return n * sizeof(double);
 }
 
