@@ -3,6 +3,7 @@
 // CPU compute path in this library.
 #include "../../include/ffvd_b200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -724,13 +725,15 @@ static int launch_prep(ffvd_ctx* c, const Layout& L, double jitter, bool reuse =
   return FFVD_OK;
 }
 
+// tri: BGEMM_A_UPPER / BGEMM_B_LOWER when an operand is L^{-T} / L^{-1} (exact zeros in the other triangle): see bgemm_nn_kernel
+enum { BGEMM_A_UPPER = 1, BGEMM_B_LOWER = 2 };
 static int launch_bgemm(ffvd_ctx* c, double* C, const double* A, const double* B, int n, double alpha, int batch,
-                        BatchMap mC, BatchMap mA, BatchMap mB) {
+                        BatchMap mC, BatchMap mA, BatchMap mB, int tri = 0) {
   // half-height tiles while the launch would not fill the GPU with 64 x 64 ones
   if ((long long)(n / 64) * (n / 64) * batch < c->num_sms)
-    bgemm_nn_kernel<32><<<dim3(n / 64, n / 32, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB);
+    bgemm_nn_kernel<32><<<dim3(n / 64, n / 32, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB, tri);
   else
-    bgemm_nn_kernel<64><<<dim3(n / 64, n / 64, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB);
+    bgemm_nn_kernel<64><<<dim3(n / 64, n / 64, batch), 256, 0, c->stream>>>(C, A, B, n, alpha, mC, mA, mB, tri);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return FFVD_OK;
@@ -999,7 +1002,10 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     TRY((launch_fused<KIND, MODE_FORWARD>(c, Mp, Din, c->d_probs, nprob, total_items)));
     TRY(det_reduce());
   } else if (!collapsed) {
-    if (!ltu_done) { ltu_kernel<<<dim3(D, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++; }
+    if (!ltu_done) {
+      const int chunks = std::max(1, std::min((M + 31) / 32, (4 * c->num_sms) / std::max(1, D * nprob)));     // fill the GPU, one 32-row chunk at least
+      ltu_kernel<<<dim3(D, nprob, chunks), 256, 0, c->stream>>>(c->d_probs); c->launches++;
+    }
     TRY(det_zero());
     TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, Din, c->d_probs, nprob, total_items)));
     TRY(det_reduce());
@@ -1034,10 +1040,10 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       collapsed_chol_kernel<<<dim3(nb, nprob), 512, sm_chol, c->stream>>>(c->d_probs, fast ? 1 : 0); c->launches++;
     }
     if (!no_grads) {
-      TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));          // H^{-1} = L_H^{-T} L_H^{-1}
+      TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm, BGEMM_A_UPPER | BGEMM_B_LOWER));          // H^{-1} = L_H^{-T} L_H^{-1}
       collapsed_vec_kernel<<<dim3(nb, nprob), 1024, 0, c->stream>>>(c->d_probs); c->launches++;   // Wk <- Mat'
-      TRY(launch_bgemm(c, Hx, Wk, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Mat' L^{-1}
-      TRY(launch_bgemm(c, Nmat, LinvT, Hx, Mp, 1.0, nz, idm, lmap, idm));     // N = L^{-T} Mat' L^{-1}
+      TRY(launch_bgemm(c, Hx, Wk, Linv, Mp, 1.0, nz, idm, idm, lmap, BGEMM_B_LOWER));        // Mat' L^{-1}
+      TRY(launch_bgemm(c, Nmat, LinvT, Hx, Mp, 1.0, nz, idm, lmap, idm, BGEMM_A_UPPER));     // N = L^{-T} Mat' L^{-1}
       TRY(det_zero());
       TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, Din, c->d_probs, nprob, total_items)));
       TRY(det_reduce());
@@ -1045,15 +1051,15 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 2); c->launches++;   // Sacc <- Gs
     } else {
       // forward only still needs c for the quadratic term
-      TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm));
+      TRY(launch_bgemm(c, Wk, HxT, Hx, Mp, 1.0, nz, idm, idm, idm, BGEMM_A_UPPER | BGEMM_B_LOWER));
       collapsed_vec_kernel<<<dim3(nb, nprob), 1024, 0, c->stream>>>(c->d_probs); c->launches++;
     }
   }
   if (!no_grads && !(collapsed && (flags & FFVD_FLAG_NO_REPLICATED))) {
     // (time-sharded collapsed bound: G = Mat' S + c b^T is built from the all-reduced statistics, identical on every rank,
     //  so only the rank without FFVD_FLAG_NO_REPLICATED pushes it through the Cholesky backward)
-    TRY(launch_bgemm(c, Wk, Sacc, Linv, Mp, 1.0, nz, idm, idm, lmap));        // Gs L^{-1}
-    TRY(launch_bgemm(c, Sacc, LinvT, Wk, Mp, -0.5, nz, idm, lmap, idm));      // Kbar_zz = -1/2 L^{-T} Gs L^{-1}
+    TRY(launch_bgemm(c, Wk, Sacc, Linv, Mp, 1.0, nz, idm, idm, lmap, BGEMM_B_LOWER));        // Gs L^{-1}
+    TRY(launch_bgemm(c, Sacc, LinvT, Wk, Mp, -0.5, nz, idm, lmap, idm, BGEMM_A_UPPER));      // Kbar_zz = -1/2 L^{-T} Gs L^{-1}
     const dim3 grow((M + 7) / 8, nb, nprob);
     if (getenv("FFVD_SPLIT_KZZ_BWD")) {                     // the two-kernel form (kept for A/B timing)
       wz_kernel<KIND><<<grow, 256, 0, c->stream>>>(c->d_probs); c->launches++;

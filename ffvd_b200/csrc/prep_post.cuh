@@ -631,7 +631,10 @@ __device__ __forceinline__ size_t bmap(const BatchMap& m, int z) { return (size_
 template <int TM>
 __global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, const double* __restrict__ A,
                                                         const double* __restrict__ B, int n, double alpha,
-                                                        BatchMap mC, BatchMap mA, BatchMap mB) {
+                                                        BatchMap mC, BatchMap mA, BatchMap mB, int tri) {
+  // tri: bit 0 = A is upper triangular (A[m][k] = 0 for k < m: L^{-T}), bit 1 = B is lower triangular (B[k][n] = 0 for
+  // k < n: L^{-1}).  The k loop then starts at the first slab that can hold a non-zero product (half the work per
+  // triangular operand: at M = 2048 the two products of the Cholesky backward were 9 of 100 ms per evaluation).
   // TM x 64 tile of C per CTA, k in steps of 32.  The next step's A / B slabs are fetched into registers (16-byte
   // loads, all in flight together) while the current one is multiplied out of shared memory: at n = 128 the kernel is
   // four L2 round trips long instead of the 64 serialised ones of a load -> store loop.
@@ -660,8 +663,9 @@ __global__ void __launch_bounds__(256) bgemm_nn_kernel(double* __restrict__ C, c
       rb[i] = *reinterpret_cast<const double2*>(B + (size_t)(k0 + (idx >> 5)) * n + n0 + 2 * (idx & 31));
     }
   };
-  fetch(0);
-  for (int k0 = 0; k0 < n; k0 += BK) {
+  const int kbeg = max((tri & 1) ? m0 : 0, (tri & 2) ? n0 : 0) & ~(BK - 1);
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < n; k0 += BK) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
@@ -1108,7 +1112,7 @@ __device__ __forceinline__ void warp_rows4_dot(const double* __restrict__ A, int
 }
 
 // Uncollapsed: w_d = L_d^{-T} u_d, so that the fused kernel can form Kbar = (A L^{-1})/Q + e w^T without touching the
-// A operand of its second contraction.  grid (D, nprob); block 256 (four rows of L^{-T} per warp; the zero lower part
+// A operand of its second contraction.  grid (D, nprob, row chunks); block 256 (four rows of L^{-T} per warp; the zero lower part
 // of the rows is multiplied through).  u_d is read from the transposed copy written by hyper_kernel.
 __global__ void __launch_bounds__(256) ltu_kernel(const DevProblem* __restrict__ probs) {
   const DevProblem& P = probs[blockIdx.y];
@@ -1117,12 +1121,14 @@ __global__ void __launch_bounds__(256) ltu_kernel(const DevProblem* __restrict__
   const double* LT = P.LinvT + (size_t)d * P.hs * Mp * Mp;
   const double* u = P.UT + (size_t)d * Mp;
   double* w = P.wvec + (size_t)d * Mp;
-  for (int m0 = 4 * warp; m0 < M; m0 += 32) {
+  // rows dealt over gridDim.z CTAs in chunks of 32 (M = 2048: one CTA per d read its 32 MB of L^{-T} alone -- 3 ms)
+  for (int m0 = 4 * warp + 32 * blockIdx.z; m0 < M; m0 += 32 * gridDim.z) {
     double t[4];
     warp_rows4_dot(LT, Mp, u, m0, M, lane, t);
     if (lane < 4 && m0 + lane < M) w[m0 + lane] = (lane == 0) ? t[0] : (lane == 1) ? t[1] : (lane == 2) ? t[2] : t[3];
   }
-  for (int m = M + threadIdx.x; m < Mp; m += 256) w[m] = 0.0;
+  if (blockIdx.z == 0)
+    for (int m = M + threadIdx.x; m < Mp; m += 256) w[m] = 0.0;
 }
 
 // After Hinv = L_H^{-T} L_H^{-1} is in Wk[b]:  c = Hinv b/Q ; w' = L^{-T} c / Q ; quad; dJ/dlogQ;
