@@ -1179,3 +1179,19 @@ def test_deterministic_flag_batched_chains_and_refusals(env):
     p = ps[0]
     with pytest.raises(F.FFVDError):
         env["ctx"].nll_grads(0, True, p, alloc_out(env, p), flags=F.FLAG_DETERMINISTIC | F.FLAG_COLLAPSED_P1_ONLY)
+
+
+@pytest.mark.parametrize("collapsed", (False, True))
+def test_extreme_kernel_variance_and_distance(env, collapsed):
+    """The K tile's exp routine works on a table pre-scaled by v_d with an exponent-shift bound (exp_nmin) and an integer
+    clamp of the argument: kernel variances from 4e-18 to 20 and a trajectory row 1e5 length-scales away from every inducing
+    point (argument ~ -1e9: exact 0 in the reference, v * exp(-745) here) must give the oracle's nll and gradients."""
+    from oracle import fixtures, ffvd_oracle as O
+    prob = fixtures.synthetic_problem(T=200, M=40, D=3, S=1, seed=5)
+    prob.logv = np.array([-40.0, 3.0, np.log(0.3)])
+    prob.X = prob.X.copy()
+    prob.X[7] *= 1.0e5
+    ref = O.nll_and_grads(prob, collapsed=collapsed)
+    got = run_cuda(env, prob, collapsed)
+    assert np.all(np.isfinite(got["nll"])) and all(np.all(np.isfinite(got[k])) for k in got)
+    check(ref, got, what="extreme v / distance")
