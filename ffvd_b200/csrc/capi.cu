@@ -453,7 +453,7 @@ struct Layout {
   long long sumS;
   bool collapsed;
   size_t off_ZT, off_ZTs, off_hyp, off_hq, off_UT, off_Linv, off_LinvT, off_Sacc, off_Wk, off_Nmat, off_Hx, off_HxT, off_ubar, off_cvec, off_wvec, off_rs,
-      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, off_guard, off_collb, total;
+      off_small, off_terms, off_status, off_utmp, off_kscr, off_Lfac, off_Dinv, off_status2, off_guard, off_collb, off_gZd, total;
   int nfac;                        // matrices in the blocked-factorisation pools: nprob * max(nk, nb)
   size_t zero_begin, zero_end;     // region re-zeroed before every evaluation
   size_t small_per;                // doubles of small accumulators per problem
@@ -490,7 +490,8 @@ static Layout make_layout(const ffvd_ctx* c, int nprob, int nb, int nk, int D, i
   L.off_wvec = take((size_t)nprob * nb * Mp * 8);        // uncollapsed: L^{-T} u ; collapsed: w'
   L.off_rs = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
   L.zero_begin = o;
-  L.off_Sacc = take(need_acc ? (size_t)nprob * nb * mm : 0);
+  L.off_gZd = take(need_acc ? (size_t)nprob * D * Mp * 32 * 8 : 0);     // raw Z-bar products per output dim; with S the "per-CTA copies" region
+  L.off_Sacc = take(need_acc ? (size_t)nprob * nb * mm : 0);           //   [off_gZd, off_ubar) of the deterministic mode
   L.off_ubar = take(need_acc ? (size_t)nprob * nb * Mp * 8 : 0);
   L.small_per = (size_t)M * Din + (size_t)D * Din + D + D + (size_t)D * Dy + Dy + Dy;
   L.off_small = take((size_t)nprob * L.small_per * 8);
@@ -566,6 +567,7 @@ static void bind_problem(ffvd_ctx* c, const Layout& L, int p, long long s_begin,
   P.status = (int*)(a + L.off_status) + (size_t)p * (L.nb > L.nk ? L.nb : L.nk);
   P.guard = (unsigned long long*)(a + L.off_guard) + (size_t)p * 4;
   P.collb = (double*)(a + L.off_collb) + (size_t)p * L.nb * 4;
+  P.gZd = (double*)(a + L.off_gZd) + (size_t)p * L.D * L.Mp * 32;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -913,7 +915,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   // ---- FFVD_FLAG_DETERMINISTIC: private accumulator copies (one per CTA for the S region, one per (CTA, warp) for u-bar / small
   //      gradients / raw terms), three extra x-bar planes and the kzz_bwd partials; see det_ptr1 / det_ptr2 (ffvd_common.cuh)
   const int det_copies = c->num_sms * kMaxCtasPerSm;
-  const size_t det_r1 = L.off_ubar - L.off_Sacc, det_r2 = L.off_status - L.off_ubar;
+  const size_t det_r1 = L.off_ubar - L.off_gZd, det_r2 = L.off_status - L.off_ubar;
   const int kzz_nblk = (M + 7) / 8;
   size_t det_off2 = 0, det_offp = 0, det_offk = 0, det_total = 0, xtot = 0;
   if (det) {
@@ -930,7 +932,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     size_t xo = 0;
     for (int p = 0; p < nprob; ++p) {
       DevProblem& P = hp[p];
-      P.det1 = c->det_buf; P.det_base1 = c->arena + L.off_Sacc; P.det_stride1 = (long long)det_r1;
+      P.det1 = c->det_buf; P.det_base1 = c->arena + L.off_gZd; P.det_stride1 = (long long)det_r1;
       P.det2 = c->det_buf + det_off2; P.det_base2 = c->arena + L.off_ubar; P.det_stride2 = (long long)det_r2;
       if (P.gX) { P.gXp = (double*)(c->det_buf + det_offp) + xo; P.gXp_stride = (long long)xtot; }
       P.kzzpart = (double*)(c->det_buf + det_offk) + (size_t)p * nb * ((size_t)M * Din + (size_t)kzz_nblk * (Din + 1));
@@ -945,7 +947,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
   };
   auto det_reduce = [&]() -> int {         // after every fused launch: shared accumulators += the private copies, in index order
     if (!det) return FFVD_OK;
-    det_reduce_kernel<<<grid1d(det_r1 / 8), 256, 0, c->stream>>>((double*)(c->arena + L.off_Sacc), c->det_buf, det_r1, det_r1 / 8, det_copies);
+    det_reduce_kernel<<<grid1d(det_r1 / 8), 256, 0, c->stream>>>((double*)(c->arena + L.off_gZd), c->det_buf, det_r1, det_r1 / 8, det_copies);
     det_reduce_kernel<<<grid1d(det_r2 / 8), 256, 0, c->stream>>>((double*)(c->arena + L.off_ubar), c->det_buf + det_off2, det_r2, det_r2 / 8,
                                                                  det_copies * FFVD_DET_MAX_WARPS);
     c->launches += 2;
@@ -1009,6 +1011,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
     TRY(det_zero());
     TRY((launch_fused<KIND, MODE_UNCOLLAPSED>(c, Mp, Din, c->d_probs, nprob, total_items)));
     TRY(det_reduce());
+    zbar_post_kernel<KIND><<<dim3(D + 1, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
     symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 0); c->launches++;
   } else {
     if (!resume) {
@@ -1047,6 +1050,7 @@ static int run_nll(ffvd_ctx* c, int collapsed, int nprob, const ffvd_problem* pr
       TRY(det_zero());
       TRY((launch_fused<KIND, MODE_COLLAPSED_P2>(c, Mp, Din, c->d_probs, nprob, total_items)));
       TRY(det_reduce());
+      zbar_post_kernel<KIND><<<dim3(D + 1, nprob), 256, 0, c->stream>>>(c->d_probs); c->launches++;
       TRY(launch_bgemm(c, HxT, Wk, Sacc, Mp, 1.0, nz, idm, idm, idm));        // Mat' S
       symmetrize_lower_kernel<<<gsym, 256, 0, c->stream>>>(c->d_probs, 2); c->launches++;   // Sacc <- Gs
     } else {

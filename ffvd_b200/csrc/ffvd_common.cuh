@@ -53,6 +53,8 @@ struct DevProblem {
   double *Wk;          // [D][Mp][Mp] scratch for the M^3 products
   double *ubar;        // [D][Mp]     sum_t e_t a_t   (collapsed: b = F^T delta, unscaled)
   double *gZ;          // [M][Din]    raw dJ/dZ
+  double *gZd;         // [D][Mp][8 NBM] raw W^T [Xc,1] sums per output dim (NBM = ceil((Din+1)/8)): the K(X,Z) part of dJ/dZ, dJ/dlogl before
+                       //             scaling; folded into gZ / gl by zbar_post_kernel.  Lives in the S region (per-CTA copies in deterministic mode)
   double *gl;          // [D][Din]    raw dJ/dlogl
   double *gv;          // [D]
   double *gQ;          // [D]

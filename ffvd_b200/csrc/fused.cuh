@@ -535,7 +535,7 @@ __device__ __forceinline__ void syrk_units_pipe(const double* tile, int lda, int
 // would still occupy the tensor pipe.
 template <int KIND, int RB, int NGW, int NW, int NBM>
 __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevProblem& P, int d, double v, double* gXs,
-                                           long long doff2, int t0, int nvalid, int warp, int lane, int tid
+                                           long long doff1, long long doff2, int t0, int nvalid, int warp, int lane, int tid
 #ifdef FFVD_PHASE_TIMING
                                            , long long& _phase_last
 #endif
@@ -553,23 +553,13 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
     const int wA = warp % NA;
     constexpr int NMB = 2 * NGW;                 // m-blocks per warp = (Mp/8)/NA
     constexpr int MCH = NMB < 4 ? NMB : 4;       // processed MCH at a time
-    const int nbc = Din >> 3, qc = (Din & 7) >> 1, ec = Din & 1;   // where column Din (the ones) sits in a C fragment
-    double lacc[NBM][2];
-#pragma unroll
-    for (int nb = 0; nb < NBM; ++nb) lacc[nb][0] = lacc[nb][1] = 0.0;
+    // The products are flushed RAW: column jd < Din of row m is sum_t W[t][m] x[t][jd], column Din (the ones) the column sum of
+    // W.  Scaling by 1/l^2, the -colsum * z term and the d/dlogl row part are applied once per evaluation by zbar_post_kernel
+    // (prep_post.cuh) on the accumulated [D][Mp][8 NBM] array -- in the tile loop that epilogue was 16 loads of Z, a shuffle, 32 FMAs
+    // and a second reduction per lane and d.
+    double* gzd = det_at(P.gZd + (size_t)d * Mp * (8 * NBM), doff1);
 #pragma unroll 1
     for (int i0 = 0; i0 < NMB; i0 += MCH) {
-      double zr[MCH][NBM][2];
-      if (KIND == 0) {
-        // Z values of the epilogue, requested before the product (rows of Z~^T above Din are one / zero: harmless)
-#pragma unroll
-        for (int u = 0; u < MCH; ++u)
-#pragma unroll
-          for (int nb = 0; nb < NBM; ++nb)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-              zr[u][nb][e] = (nb < nbx) ? __ldg(P.ZT + (size_t)(8 * nb + 2 * q + e) * Mp + 8 * (wA + NA * (i0 + u)) + g) : 0.0;
-      }
       double c[MCH][NBM][2];
 #pragma unroll
       for (int u = 0; u < MCH; ++u)
@@ -592,51 +582,14 @@ __device__ __forceinline__ void contract_W(const Smem& sm, int lda, const DevPro
       }
 #pragma unroll
       for (int u = 0; u < MCH; ++u) {
-        // column sum of W for row m = 8*mb+g sits at column Din of the product
-        double csv = 0.0;
+        const int m = 8 * (wA + NA * (i0 + u)) + g;
+        double* row = gzd + (size_t)m * (8 * NBM) + 2 * q;
 #pragma unroll
         for (int nb = 0; nb < NBM; ++nb)
-          if (nb == nbc) csv = ec ? c[u][nb][1] : c[u][nb][0];
-        const double cs = __shfl_sync(0xffffffffu, csv, g * 4 + qc);
-        const int m = 8 * (wA + NA * (i0 + u)) + g;
 #pragma unroll
-        for (int nb = 0; nb < NBM; ++nb) {
-          if (nb < nbx) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int jd = 8 * nb + 2 * q + e;
-              {
-                // no branch: columns >= Din have a zero scale (sm.small) / zero products, rows >= M zero W columns; the RED
-                // itself is predicated
-                const bool ok = jd < Din && m < M;
-                double zb;
-                if (KIND == 0) {
-                  const double z = zr[u][nb][e];
-                  zb = ok ? sm.small[jd & 31] * (c[u][nb][e] - cs * z) : 0.0;
-                  lacc[nb][e] = fma(-z, zb, lacc[nb][e]);
-                } else {
-                  zb = v * c[u][nb][e];
-                }
-                red_add_if(det_at(P.gZ + (size_t)m * Din + jd, doff2), zb, ok);
-              }
-            }
-          }
-        }
+          for (int e = 0; e < 2; ++e)
+            red_add_if(row + 8 * nb + e, c[u][nb][e], m < M && 8 * nb + 2 * q + e <= Din);
       }
-    }
-    if (KIND == 0) {
-      // reduce over g (lanes with equal q), then one RED per column
-#pragma unroll
-      for (int nb = 0; nb < NBM; ++nb)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double x = lacc[nb][e];
-          x += __shfl_xor_sync(0xffffffffu, x, 4);
-          x += __shfl_xor_sync(0xffffffffu, x, 8);
-          x += __shfl_xor_sync(0xffffffffu, x, 16);
-          const int jd = 8 * nb + 2 * q + e;
-          red_add_if(det_at(P.gl + (size_t)d * Din + jd, doff2), x, g == 0 && nb < nbx && jd < Din);
-        }
     }
   }
   FFVD_MARK(8);
@@ -1361,10 +1314,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
 #define FFVD_CW_TAIL
 #endif
       switch ((Din + 1 + 7) >> 3) {
-        case 1: contract_W<KIND, RB, NGW, NW, 1>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
-        case 2: contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
-        case 3: contract_W<KIND, RB, NGW, NW, 3>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
-        default: contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 1: contract_W<KIND, RB, NGW, NW, 1>(sm, lda, P, d, v, gXs, doff1, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 2: contract_W<KIND, RB, NGW, NW, 2>(sm, lda, P, d, v, gXs, doff1, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        case 3: contract_W<KIND, RB, NGW, NW, 3>(sm, lda, P, d, v, gXs, doff1, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
+        default: contract_W<KIND, RB, NGW, NW, 4>(sm, lda, P, d, v, gXs, doff1, doff2, t0, nvalid, warp, lane, tid FFVD_CW_TAIL); break;
       }
 #undef FFVD_CW_TAIL
     }

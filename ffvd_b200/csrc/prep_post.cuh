@@ -892,6 +892,56 @@ __global__ void det_reduce_kernel(double* __restrict__ dst, const char* __restri
   }
 }
 
+// Fold the raw W^T [Xc,1] sums of the fused kernel (P.gZd: [D][Mp][PW], column jd < Din = sum_t W[t][m] x[t][jd], column Din = the
+// column sum of W) into dJ/dZ and the Z part of dJ/dlogl:
+//   SE:      zb = (c - colsum * z[m][jd]) / l_{d,jd}^2 ;  gZ[m][jd] += sum_d zb ;  gl[d][jd] -= sum_m z[m][jd] zb
+//   Linear:  zb = v_d c                               ;  gZ[m][jd] += sum_d zb
+// grid (D + 1, nprob), block 256 (lane = input column, a warp per row m).  Blocks 0..D-1 form gl[d] (their own row of gl: no
+// other writer), block D forms gZ (the only writer of gZ at this point of the stream, d in index order): plain stores in a
+// fixed order, so the step is repeatable as it stands (FFVD_FLAG_DETERMINISTIC needs nothing extra here).
+template <int KIND>
+__global__ void __launch_bounds__(256) zbar_post_kernel(const DevProblem* __restrict__ probs) {
+  const DevProblem& P = probs[blockIdx.y];
+  const int D = P.D, Din = P.Din, M = P.M, Mp = P.Mp;
+  const int nbm = (Din + 1 + 7) >> 3, PW = 8 * (nbm < 4 ? nbm : 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool in = lane < Din;
+  if ((int)blockIdx.x < D) {
+    if (KIND != 0) return;
+    const int d = blockIdx.x;
+    const double* cz = P.gZd + (size_t)d * Mp * PW;
+    const double il2 = in ? P.hyp[(size_t)d * P.hs * 72 + lane] : 0.0;
+    double ls = 0.0;
+    for (int m = warp; m < M; m += 8) {
+      const double c = in ? cz[(size_t)m * PW + lane] : 0.0, cs = cz[(size_t)m * PW + Din];
+      const double z = in ? P.Z[(size_t)m * Din + lane] : 0.0;
+      const double zb = il2 * (c - cs * z);
+      ls = fma(-z, zb, ls);
+    }
+    __shared__ double part[8][32];
+    part[warp][lane] = ls;
+    __syncthreads();
+    if (warp == 0 && in) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][lane];
+      P.gl[(size_t)d * Din + lane] += t;
+    }
+  } else {
+    for (int m = warp; m < M; m += 8) {
+      if (!in) continue;
+      const double z = P.Z[(size_t)m * Din + lane];
+      double t = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double* cz = P.gZd + ((size_t)d * Mp + m) * PW;
+        if (KIND == 0) t += P.hyp[(size_t)d * P.hs * 72 + lane] * (cz[lane] - cz[Din] * z);
+        else t += P.hyp[(size_t)d * P.hs * 72 + 64] * cz[lane];
+      }
+      P.gZ[(size_t)m * Din + lane] += t;
+    }
+  }
+}
+
 // dJ/dZ, dJ/dlogl, dJ/dlogv contributions of Kbar_zz.  grid (ceil(M/8), batch, nprob); block (32, 8).
 template <int KIND>
 __global__ void __launch_bounds__(256) kzz_bwd_kernel(const DevProblem* __restrict__ probs) {
