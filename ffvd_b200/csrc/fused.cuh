@@ -457,19 +457,26 @@ __device__ __forceinline__ void syrk_tile_pipe(const double* tile, int lda, int 
   constexpr int KSTEPS = 2 * RB;                       // k-steps of 4 rows
   constexpr int NSLOT = 2 * NB;                        // flush slots of the pending unit
   constexpr int EVERY = KSTEPS >= NSLOT ? KSTEPS / NSLOT : 1;
-#pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks) {
-    double a[NB], b[NB];
+  // operand fragments double buffered in registers: the loads of k-step ks + 1 are issued before the DMMAs of k-step ks
+  double a[NB], b[NB], an[NB], bn[NB];
+  auto load_frag = [&](double (&fa)[NB], double (&fb)[NB], int ks) {
     const double* row = tile + (4 * ks + q) * lda + g;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) a[i] = row[m0 + 8 * i];
+    for (int i = 0; i < NB; ++i) fa[i] = row[m0 + 8 * i];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) b[j] = DIAG ? a[j] : row[n0 + 8 * j];
+    for (int j = 0; j < NB; ++j) fb[j] = DIAG ? fa[j] : row[n0 + 8 * j];
+  };
+  load_frag(a, b, 0);
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    if (ks + 1 < KSTEPS) load_frag(an, bn, ks + 1);
 #pragma unroll
     for (int i = 0; i < NB; ++i)
 #pragma unroll
       for (int j = 0; j < NB; ++j)
         if (!DIAG || j <= i) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { a[i] = an[i]; b[i] = bn[i]; }
     if (KSTEPS >= NSLOT) {
       if (ks % EVERY == EVERY - 1 && ks / EVERY < NSLOT && pd.valid) syrk_flush_slot<NB>(pd, ks / EVERY, Mp, S, stage_w, lane);
     }
