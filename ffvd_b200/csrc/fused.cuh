@@ -891,11 +891,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
         if (MODE == MODE_COND) wsv[i] = (P.qmode == 2 && j < M) ? __ldg(P.qmat + (size_t)j * D + d) : 0.0;
       }
     }
-    double tabv = 0.0;                 // SE: the exp table pre-scaled by v_d (threads 64..127)
-    if (KIND == 0 && tid >= 64 && tid < 128) {
-      const double vv = __ldg(hyp + 64);
-      tabv = (exp_nmin(vv) == 0 && vv < 1.0) ? 0.0 : vv * g_exp2_tab[tid - 64];
-    }
+    // SE: the exp table pre-scaled by v_d (threads 64..127).  Only the two REQUESTS go out here: a consumer of a loaded value in
+    // front of the barrier below makes the whole CTA wait there for the L2 round trip (the scaling product sat here at first).
+    double tab_v = 0.0, tab_e = 0.0;
+    if (KIND == 0 && tid >= 64 && tid < 128) { tab_v = __ldg(hyp + 64); tab_e = g_exp2_tab[tid - 64]; }
     __syncthreads();   // x tile staged (di == 0) / previous d fully done with shared memory (di > 0)
     FFVD_MARK(11);
     if (tid < 64) {
@@ -904,7 +903,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       if (tid == 40) sm.sc[0] = scv;
       if (tid >= 41 && tid < 44) sm.sc[tid - 40] = scv;
     }
-    if (KIND == 0 && tid >= 64 && tid < 128) sm.exptab[tid - 64] = tabv;
+    if (KIND == 0 && tid >= 64 && tid < 128) sm.exptab[tid - 64] = (exp_nmin(tab_v) == 0 && tab_v < 1.0) ? 0.0 : tab_v * tab_e;
     if (KIND == 0) {
       // x~ = x / l and -1/2 |x~_r|^2 in ONE pass: a quarter-warp per row (8 lanes x 4 columns each, the 1/l of the four
       // columns in registers since the top of the iteration), all rows of a pass loaded before the first is used.  Columns
