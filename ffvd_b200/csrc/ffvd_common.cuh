@@ -202,6 +202,16 @@ __device__ __forceinline__ double2 ldg_stream2_v(const double* p) {     // same,
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+// Bulk asynchronous copy shared -> global through the TMA engine (SASS UBLKCP): the K tile's scratch copy leaves the SM without
+// passing through registers or the LSU store queue.  16-byte aligned addresses, size a multiple of 16.
+__device__ __forceinline__ void bulk_copy_s2g(double* gdst, const double* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_fence_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 #define FFVD_KB0 3      // k-steps of the K-tile product whose group-0 operand fragments are requested as register loads ahead of the phase
 __device__ __forceinline__ double2 ldg_nc2_v(const double* p) {            // 16-byte read-only load, pinned in program order
   double2 v;

@@ -958,7 +958,10 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
       const double* ZTd = (KIND == 0) ? P.ZTs + (size_t)dh * FFVD_ZTS_ROWS * Mp : P.ZT;
       const int ksn = (KIND == 0) ? (Din + 2 + 3) >> 2 : (Din + 3) >> 2;      // DMMA k-steps of the (augmented) product
       const int nmin = (KIND == 0) ? exp_nmin(v) : 0;
-      constexpr bool SCR = (KIND == 0 && MODE == MODE_UNCOLLAPSED);
+      // SE uncollapsed keeps a copy of the K tile in this CTA's L2 scratch (W = Kbar o K needs it again after the tile has been
+      // overwritten by A).  FFVD_SCR_TMA: the copy is made by bulk shared -> global copies after the phase (below) instead of
+      // 256-bit stores from the lanes' registers inside it (ncu: the next pass waited for those stores to leave the LSU queue).
+      constexpr bool SCR = (KIND == 0 && MODE == MODE_UNCOLLAPSED) && !FFVD_SCR_TMA;
       switch (ksn) {
         case 2: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 2>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr, kb0); break;
         case 3: compute_k_tile<KIND, RBW, NGW, SCR, NCW, 3>(sm, ZTd, Mp, Din, v, nmin, ksn, wc, g, q, M, row0, lda, kscr, kb0); break;
@@ -979,6 +982,13 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     else tile_gemm_prologue<CH0, 0, NCW>(ring0, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, 0, g, q);
     __syncthreads();
     FFVD_MARK(1);
+    if (FFVD_SCR_TMA && KIND == 0 && MODE == MODE_UNCOLLAPSED && warp == 0) {
+      // K tile -> L2 scratch, one bulk copy per row (the rows are lda apart in shared memory, Mp apart in the scratch); in
+      // flight during the whole first contraction, awaited by the issuing lanes in front of the barrier that ends it
+      bulk_fence_shared();
+      for (int r = lane; r < BT; r += 32) bulk_copy_s2g(kscr + (size_t)r * Mp, sm.tile + (size_t)r * lda, (unsigned)(Mp * sizeof(double)));
+      bulk_commit();
+    }
 
     double acc[NGW][RBW][4];
     double* wtile = sm.tile + (size_t)row0 * lda;     // this warp's rows of the shared tile
@@ -1027,6 +1037,7 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
           }
         }
       }
+      if (FFVD_SCR_TMA && KIND == 0 && MODE == MODE_UNCOLLAPSED && warp == 0) bulk_wait_all();     // scratch copy complete (long since)
       __syncthreads();          // everyone is done reading K from the tile
       FFVD_MARK(2);
       if (MODE != MODE_FORWARD && MODE != MODE_COND) store_tile<RBW, NGW, NCW>(acc, wtile, lda, wc, g, q);

@@ -13,6 +13,9 @@ namespace ffvd {
 #define FFVD_SYRK_PIPE 1   // 1: software-pipelined SYRK flush (syrk_units_pipe), two staging buffers per warp
 #endif
 
+#ifndef FFVD_SCR_TMA
+#define FFVD_SCR_TMA 1      // 1: the K tile's L2 scratch copy is made by TMA bulk copies shared -> global (0: 256-bit stores inside the K-tile phase)
+#endif
 #ifndef FFVD_G2_EARLY
 #define FFVD_G2_EARLY 0    // 1: operand prologue of Kbar = A L^{-1} requested before the SYRK (costs the SYRK registers: slower)
 #endif
