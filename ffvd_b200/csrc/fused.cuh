@@ -61,7 +61,7 @@ struct Smem {
   double* small;    // 64: invl2[32], sil[32]
   double* sc;       // 8: per-item scalars v, Q, 1/Q, log Q
   double* red;      // 40: block-level reductions (smem atomics)
-  double* exptab;   // 64: 2^(j/64), the table of exp_nonpos_n
+  double* exptab;   // 64: v_d 2^(j/64), the table of exp_nonpos_n pre-scaled by the current output dim's kernel variance
 };
 
 // ---------------------------------------------------------------------------------------------
