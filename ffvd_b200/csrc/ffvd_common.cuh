@@ -253,6 +253,11 @@ __device__ __forceinline__ double* det_at(double* p, long long off) {
   return reinterpret_cast<double*>(reinterpret_cast<char*>(p) + off);
 }
 
+// Element (row m, column jd) of one output dim's block of DevProblem::gZd (Mp x 8 NBM values, see contract_W / zbar_post_kernel)
+__host__ __device__ __forceinline__ size_t zbar_index(int Mp, int m, int jd) {
+  return ((size_t)(((jd >> 3) << 1) | (jd & 1)) * Mp + m) * 4 + ((jd & 7) >> 1);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

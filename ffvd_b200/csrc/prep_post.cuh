@@ -892,7 +892,7 @@ __global__ void det_reduce_kernel(double* __restrict__ dst, const char* __restri
   }
 }
 
-// Fold the raw W^T [Xc,1] sums of the fused kernel (P.gZd: [D][Mp][PW], column jd < Din = sum_t W[t][m] x[t][jd], column Din = the
+// Fold the raw W^T [Xc,1] sums of the fused kernel (P.gZd: per d Mp x PW values in the zbar_index layout, column jd < Din = sum_t W[t][m] x[t][jd], column Din = the
 // column sum of W) into dJ/dZ and the Z part of dJ/dlogl:
 //   SE:      zb = (c - colsum * z[m][jd]) / l_{d,jd}^2 ;  gZ[m][jd] += sum_d zb ;  gl[d][jd] -= sum_m z[m][jd] zb
 //   Linear:  zb = v_d c                               ;  gZ[m][jd] += sum_d zb
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(256) zbar_post_kernel(const DevProblem* __rest
     const double il2 = in ? P.hyp[(size_t)d * P.hs * 72 + lane] : 0.0;
     double ls = 0.0;
     for (int m = warp; m < M; m += 8) {
-      const double c = in ? cz[(size_t)m * PW + lane] : 0.0, cs = cz[(size_t)m * PW + Din];
+      const double c = in ? cz[zbar_index(Mp, m, lane)] : 0.0, cs = cz[zbar_index(Mp, m, Din)];
       const double z = in ? P.Z[(size_t)m * Din + lane] : 0.0;
       const double zb = il2 * (c - cs * z);
       ls = fma(-z, zb, ls);
@@ -933,9 +933,9 @@ __global__ void __launch_bounds__(256) zbar_post_kernel(const DevProblem* __rest
       const double z = P.Z[(size_t)m * Din + lane];
       double t = 0.0;
       for (int d = 0; d < D; ++d) {
-        const double* cz = P.gZd + ((size_t)d * Mp + m) * PW;
-        if (KIND == 0) t += P.hyp[(size_t)d * P.hs * 72 + lane] * (cz[lane] - cz[Din] * z);
-        else t += P.hyp[(size_t)d * P.hs * 72 + 64] * cz[lane];
+        const double* cz = P.gZd + (size_t)d * Mp * PW;
+        if (KIND == 0) t += P.hyp[(size_t)d * P.hs * 72 + lane] * (cz[zbar_index(Mp, m, lane)] - cz[zbar_index(Mp, m, Din)] * z);
+        else t += P.hyp[(size_t)d * P.hs * 72 + 64] * cz[zbar_index(Mp, m, lane)];
       }
       P.gZ[(size_t)m * Din + lane] += t;
     }
