@@ -1104,29 +1104,38 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
           rw[0] = jxq; rw[1] = jtr; rw[2] = gq; rw[3] = gvd;
         }
       }
+      FFVD_MARK(15);
       // ---- emission term, once per (s, tile): dgp_model.py:248-250,264
       if (d == 0 && MODE != MODE_COLLAPSED_P2 && MODE != MODE_COND && warp >= 2 && warp < 2 + (BT + 31) / 32) {
         const int r = (warp - 2) * 32 + lane;
         const int Dy = P.Dy;
         double ll = 0.0;
         for (int y = 0; y < Dy; ++y) {
-          const double Ry = exp(P.logR[y]);
-          double dy = 0.0, rr = 0.0;
-          if (r < nvalid) {
-            double yhat = P.dvec[y];
-            for (int c = 0; c < D; ++c) yhat = fma(sm.xs[(r + 1) * FFVD_XLD + c], P.C[(size_t)c * Dy + y], yhat);
-            const double res = (P.Y[(size_t)(t0 + r) * Dy + y] - yhat) / Ry;
-            ll += -0.5 * res * res - P.logR[y];
-            dy = res / Ry;
-            rr = res * res - 1.0;
-            if (MODE != MODE_FORWARD)
-              for (int c = 0; c < D; ++c) red_add(gXe + (size_t)(t0 + r + 1) * D + c, dy * P.C[(size_t)c * Dy + y]);
-          }
+          // all requests first: column y of C rides in the lanes (lane c holds C[c][y], D <= 31) and is broadcast by shuffles --
+          // as loads inside the c loops this block was ~7k clk once per work item, with every other warp of the CTA waiting
+          const bool valid = r < nvalid;
+          const double lR = __ldg(P.logR + y), dv = __ldg(P.dvec + y);
+          const double Cl = (lane < D) ? __ldg(P.C + (size_t)lane * Dy + y) : 0.0;
+          const double Yv = valid ? __ldg(P.Y + (size_t)(t0 + r) * Dy + y) : 0.0;
+          const double Ry = exp(lR);
+          double yhat = dv;
+          for (int c = 0; c < D; ++c) yhat = fma(sm.xs[(r + 1) * FFVD_XLD + c], __shfl_sync(0xffffffffu, Cl, c), yhat);
+          const double res = valid ? (Yv - yhat) / Ry : 0.0;
+          if (valid) ll += -0.5 * res * res - lR;
+          const double dy = res / Ry, rr = valid ? res * res - 1.0 : 0.0;
           if (MODE != MODE_FORWARD) {
-            for (int c = 0; c < D; ++c) {
-              const double xc1 = (r < nvalid) ? sm.xs[(r + 1) * FFVD_XLD + c] : 0.0;
-              const double t = warp_sum(dy * xc1);
-              if (lane == 0) red_add(det_at(P.gC + (size_t)c * Dy + y, doff2), t);
+            for (int c = 0; c < D; ++c) red_add_if(gXe + (size_t)(t0 + r + 1) * D + c, dy * __shfl_sync(0xffffffffu, Cl, c), valid);
+            // dJ/dC column: four warp sums at a time (interleaved shuffle rounds)
+            for (int c0 = 0; c0 < D; c0 += 4) {
+              double t[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) t[k] = (valid && c0 + k < D) ? dy * sm.xs[(r + 1) * FFVD_XLD + c0 + k] : 0.0;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) red_add_if(det_at(P.gC + (size_t)(c0 + k) * Dy + y, doff2), t[k], lane == 0 && c0 + k < D);
             }
             const double sd = warp_sum(dy), sr = warp_sum(rr);
             if (lane == 0) { red_add(det_at(P.gd + y, doff2), sd); red_add(det_at(P.gR + y, doff2), sr); }

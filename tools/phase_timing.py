@@ -12,7 +12,7 @@ from bench import make_host_data
 NAMES = ["flush+decode+stage x", "K tile (r2, exp)", "A = K L^-T (+row partials)", "store A, row stats, emission",
          "ubar + SYRK S+=A^T A (warp 0)", "Kbar = Abar L^-1", "W = Kbar o K, store", "contract: rows of xbar (+tail)",
          "contract: W^T X~ -> Zbar (warp 0)", "contract: W Z~ (warp 0)", "contract: barrier wait",
-         "(P0) wait for the previous d / x tile", "(P3) barrier + store A", "(P6) K from scratch, W in registers", "(P6) barrier wait"]
+         "(P0) wait for the previous d / x tile", "(P3) barrier + store A", "(P6) K from scratch, W in registers", "(P6) barrier wait", "(P3) row statistics on warp 0 (phase 3 is then the wait for the other warps)"]
 T, M, D, S = map(int, sys.argv[1:5])
 collapsed = len(sys.argv) > 5 and sys.argv[5] == "collapsed"
 dev = torch.device("cuda:0")
