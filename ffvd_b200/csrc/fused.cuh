@@ -981,12 +981,13 @@ fused_kernel(const DevProblem* __restrict__ probs, int nprob, long long total_it
     double2 ring0[4][CH0];            // first operand fragments of the next contraction, requested ahead of the barrier / SYRK in front of it
     if (MODE != MODE_COLLAPSED_P2) tile_gemm_prologue<CH0, +1, NCW>(ring0, LinvT, Mp, wc, 0, g, q);
     else tile_gemm_prologue<CH0, 0, NCW>(ring0, P.Nmat + ((size_t)s * D + d) * Mp * Mp, Mp, wc, 0, g, q);
+    // every thread orders its own K-tile stores (generic proxy) before the async proxy that will read the tile, THEN the barrier
+    if (FFVD_SCR_TMA && KIND == 0 && MODE == MODE_UNCOLLAPSED) bulk_fence_shared();
     __syncthreads();
     FFVD_MARK(1);
     if (FFVD_SCR_TMA && KIND == 0 && MODE == MODE_UNCOLLAPSED && warp == 0) {
       // K tile -> L2 scratch, one bulk copy per row (the rows are lda apart in shared memory, Mp apart in the scratch); in
       // flight during the whole first contraction, awaited by the issuing lanes in front of the barrier that ends it
-      bulk_fence_shared();
       for (int r = lane; r < BT; r += 32) bulk_copy_s2g(kscr + (size_t)r * Mp, sm.tile + (size_t)r * lda, (unsigned)(Mp * sizeof(double)));
       bulk_commit();
     }
